@@ -1,0 +1,723 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- CPU oracle for the WENO5 MHD hot path.
+ *
+ * A plain-C restatement of the E-branch algorithm of jdonnert/julia's Weno5_2D.jl /
+ * Weno5_1D.jl (reference file:line cited at every function).  It is the checker for the
+ * CUDA path (tests/, __graft_entry__.smoke()) and the timed CPU baseline of bench.py;
+ * nothing in the product (julia_b200/, libweno5mhd.so) may call, link or load it.
+ *
+ * PARITY UNPINNED: the reference has no golden vectors, known-answer tests or fixtures
+ * for this path and cannot be run here (Julia 0.6 source; no julia binary).  This file
+ * is pinned by (i) algebraic identities of the eigen-system, (ii) invariants
+ * (conservation, div B, uniform-state preservation), (iii) agreement to round-off with
+ * the independently written numpy restatement oracle/weno5_numpy.py, which is
+ * array-at-a-time and uses the reference's transpose/rotate formulation, while this file
+ * sweeps lines in place (x lines contiguous, y lines strided, components permuted).
+ *
+ * Layout is the reference's: q[i + Nx*(j + Ny*c)], c = rho,Mx,My,Mz,Bx,By,Bz,S,E;
+ * bxb/byb[i + Nx*j]; NBnd = 3 ghosts.  Indices in this file are 0-based (reference i-1).
+ *
+ * Quirk decisions: Q1 E-only; Q2 2D round-trips E through S every
+ * stage, 1D keeps E; Q3 the stencil cell past the high end of a line continues the
+ * boundary condition (clamp for outflow, wrap for periodic); Q11 flux-term order per
+ * stage as in the reference; vmax sqrt arguments are clamped at 0 (reference: bare sqrt).
+ *
+ * Build: see oracle/Makefile.  The parity build uses -ffp-contract=off; the timed CPU
+ * baseline build (-O3 -march=x86-64-v3 -fopenmp) is the same source.
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define NB 3
+
+typedef struct {
+    int nx, ny;          /* interior cells; ny = 1 for 1-D */
+    double dx, dy, gam, cfl, eps;
+    int bc_x, bc_y;      /* 0 outflow (reference), 1 periodic (addition) */
+    int variant;         /* 0 = 2-D formulas, 1 = 1-D formulas (round-off differences, Q6/Q7) */
+} orc_params;
+
+/* ------------------------------------------------------------------ cell-centred quantities */
+
+/* Weno5_2D.jl:1573-1606  q8 = [rho,M1,M2,M3,B1,B2,B3,E] -> u = [rho,v1,v2,v3,B1,B2,B3,P] */
+static void cell_primitives(const double q[8], double gam, double u[8])
+{
+    u[0] = q[0];
+    u[1] = q[1] / q[0];
+    u[2] = q[2] / q[0];
+    u[3] = q[3] / q[0];
+    u[4] = q[4];
+    u[5] = q[5];
+    u[6] = q[6];
+    double v2 = u[1] * u[1] + u[2] * u[2] + u[3] * u[3];
+    double B2 = u[4] * u[4] + u[5] * u[5] + u[6] * u[6];
+    u[7] = (gam - 1.0) * (q[7] - 0.5 * (q[0] * v2 + B2));
+}
+
+/* Weno5_2D.jl:1608-1667 */
+static void cell_eigenvalues(const double u[8], double gam, double a[7])
+{
+    double B2 = u[4] * u[4] + u[5] * u[5] + u[6] * u[6];
+    double cs2 = fmax(0.0, gam * fabs(u[7] / u[0]));
+    double bnx2 = fmax(0.0, u[4] * u[4] / u[0]);
+    double bbn2 = B2 / u[0];
+    double s = bbn2 + cs2;
+    double root = sqrt(fmax(0.0, s * s - 4.0 * bnx2 * cs2));
+    double lf = sqrt(fmax(0.0, 0.5 * (bbn2 + cs2 + root)));
+    double ls = sqrt(fmax(0.0, 0.5 * (bbn2 + cs2 - root)));
+    double la = sqrt(bnx2);
+    a[0] = u[1] - lf; a[1] = u[1] - la; a[2] = u[1] - ls; a[3] = u[1];
+    a[4] = u[1] + ls; a[5] = u[1] + la; a[6] = u[1] + lf;
+}
+
+/* Weno5_2D.jl:1533-1555 */
+static void cell_fluxes(const double q[8], const double u[8], double F[7])
+{
+    double pt = u[7] + 0.5 * (u[4] * u[4] + u[5] * u[5] + u[6] * u[6]);
+    double vB = u[1] * u[4] + u[2] * u[5] + u[3] * u[6];
+    F[0] = u[0] * u[1];
+    F[1] = q[1] * u[1] + pt - u[4] * u[4];
+    F[2] = q[2] * u[1] - u[4] * u[5];
+    F[3] = q[3] * u[1] - u[4] * u[6];
+    F[4] = u[5] * u[1] - u[4] * u[2];
+    F[5] = u[6] * u[1] - u[4] * u[3];
+    F[6] = (q[7] + pt) * u[1] - u[4] * vB;
+}
+
+/* ------------------------------------------------------------------ face eigen-system */
+
+static double sgn(double x) { return (x > 0.0) - (x < 0.0); }
+
+/* Weno5_2D.jl:1250-1531 (variant 0) / Weno5_1D.jl:784-1003 (variant 1).
+ * L[m][c], R[c][m]; component order [rho,M1,M2,M3,B2,B3,E]. */
+static void face_eigenvectors(const double uL[8], const double uR[8], double EL, double ER,
+                              double gam, int variant, double L[7][7], double R[7][7])
+{
+    const double g0 = 1.0 - gam, g1 = (gam - 1.0) / 2.0, g2 = (gam - 2.0) / (gam - 1.0);
+    double rho = 0.5 * (uL[0] + uR[0]);
+    double r = sqrt(rho);
+    double vx = 0.5 * (uL[1] + uR[1]), vy = 0.5 * (uL[2] + uR[2]), vz = 0.5 * (uL[3] + uR[3]);
+    double Bx = 0.5 * (uL[4] + uR[4]), By = 0.5 * (uL[5] + uR[5]), Bz = 0.5 * (uL[6] + uR[6]);
+    double E = 0.5 * (EL + ER);
+    double B2 = Bx * Bx + By * By + Bz * Bz;
+    double v2 = vx * vx + vy * vy + vz * vz;
+    double pg = (gam - 1.0) * (E - 0.5 * (rho * v2 + B2));
+    double bbn2 = B2 / rho;
+    double cs2 = fmax(0.0, gam * fabs(pg / rho));
+    double bnx2 = Bx * Bx / rho;
+    double a = sqrt(cs2);
+    double s_ = bbn2 + cs2;
+    double root = sqrt(fmax(0.0, s_ * s_ - 4.0 * bnx2 * cs2));
+    double cf = sqrt(fmax(0.0, (bbn2 + cs2 + root) / 2.0));
+    double ca = sqrt(fmax(0.0, bnx2));
+    double cs = sqrt(fmax(0.0, (bbn2 + cs2 - root) / 2.0));
+    double Bt2 = By * By + Bz * Bz;
+    double s = sgn(Bx);
+    if (s == 0.0) s = 1.0;
+    double bty = 1.0 / sqrt(2.0), btz = 1.0 / sqrt(2.0);
+    int degenerate = variant == 0 ? (Bt2 <= 1e-30) : !(Bt2 >= 1e-30);
+    if (!degenerate) { bty = By / sqrt(Bt2); btz = Bz / sqrt(Bt2); }
+    double dl2 = cf * cf - cs * cs;
+    double af = 1.0, as = 1.0;
+    if (dl2 >= 1e-30) {
+        if (variant == 0) {
+            af = sqrt(fmax(0.0, cs2 - cs * cs) / dl2);
+            as = sqrt(fmax(0.0, cf * cf - cs2) / dl2);
+        } else {
+            af = sqrt(fmax(0.0, cs2 - cs * cs)) / sqrt(dl2);
+            as = sqrt(fmax(0.0, cf * cf - cs2)) / sqrt(dl2);
+        }
+    }
+    double sig = bty * vy + btz * vz;
+
+    L[0][0] = af * (g1 * v2 + cf * vx) - as * cs * sig * s;
+    L[0][1] = af * (g0 * vx - cf);
+    L[0][2] = g0 * af * vy + as * cs * bty * s;
+    L[0][3] = g0 * af * vz + as * cs * btz * s;
+    L[0][4] = g0 * af * By + a * as * bty * r;
+    L[0][5] = g0 * af * Bz + a * as * btz * r;
+    L[0][6] = -g0 * af;
+
+    L[1][0] = btz * vy - bty * vz; L[1][1] = 0.0; L[1][2] = -btz; L[1][3] = bty;
+    L[1][4] = -btz * s * r; L[1][5] = bty * s * r; L[1][6] = 0.0;
+
+    L[2][0] = as * (g1 * v2 + cs * vx) + af * cf * sig * s;
+    L[2][1] = g0 * as * vx - as * cs;
+    L[2][2] = g0 * as * vy - af * cf * bty * s;
+    L[2][3] = g0 * as * vz - af * cf * btz * s;
+    L[2][4] = g0 * as * By - a * af * bty * r;
+    L[2][5] = g0 * as * Bz - a * af * btz * r;
+    L[2][6] = -g0 * as;
+
+    L[3][0] = -cs2 / g0 - 0.5 * v2; L[3][1] = vx; L[3][2] = vy; L[3][3] = vz;
+    L[3][4] = By; L[3][5] = Bz; L[3][6] = -1.0;
+
+    L[4][0] = as * (g1 * v2 - cs * vx) - af * cf * sig * s;
+    L[4][1] = as * (g0 * vx + cs);
+    L[4][2] = g0 * as * vy + af * cf * bty * s;
+    L[4][3] = g0 * as * vz + af * cf * btz * s;
+    L[4][4] = g0 * as * By - a * af * bty * r;
+    L[4][5] = g0 * as * Bz - a * af * btz * r;
+    L[4][6] = -g0 * as;
+
+    L[5][0] = btz * vy - bty * vz; L[5][1] = 0.0; L[5][2] = -btz; L[5][3] = bty;
+    L[5][4] = btz * s * r; L[5][5] = -bty * s * r; L[5][6] = 0.0;
+
+    L[6][0] = af * (g1 * v2 - cf * vx) + as * cs * sig * s;
+    L[6][1] = af * (g0 * vx + cf);
+    L[6][2] = g0 * af * vy - as * cs * bty * s;
+    L[6][3] = g0 * af * vz - as * cs * btz * s;
+    L[6][4] = g0 * af * By + a * as * bty * r;
+    L[6][5] = g0 * af * Bz + a * as * btz * r;
+    L[6][6] = -g0 * af;
+
+    R[0][0] = af; R[1][0] = af * (vx - cf);
+    R[2][0] = af * vy + as * cs * bty * s; R[3][0] = af * vz + as * cs * btz * s;
+    R[4][0] = a * as * bty / r; R[5][0] = a * as * btz / r;
+    R[6][0] = af * (cf * cf - cf * vx + 0.5 * v2 - g2 * cs2) + as * cs * sig * s;
+
+    R[0][1] = 0.0; R[1][1] = 0.0; R[2][1] = -btz; R[3][1] = bty;
+    R[4][1] = -btz * s / r; R[5][1] = bty * s / r; R[6][1] = bty * vz - btz * vy;
+
+    R[0][2] = as; R[1][2] = as * (vx - cs);
+    R[2][2] = as * vy - af * cf * bty * s; R[3][2] = as * vz - af * cf * btz * s;
+    R[4][2] = -a * af * bty / r; R[5][2] = -a * af * btz / r;
+    R[6][2] = as * (cs * cs - cs * vx + 0.5 * v2 - g2 * cs2) - af * cf * sig * s;
+
+    R[0][3] = 1.0; R[1][3] = vx; R[2][3] = vy; R[3][3] = vz; R[4][3] = 0.0; R[5][3] = 0.0;
+    R[6][3] = 0.5 * v2;
+
+    R[0][4] = as; R[1][4] = as * (vx + cs);
+    R[2][4] = as * vy + af * cf * bty * s; R[3][4] = as * vz + af * cf * btz * s;
+    R[4][4] = -a * af * bty / r; R[5][4] = -a * af * btz / r;
+    R[6][4] = as * (cs * cs + cs * vx + 0.5 * v2 - g2 * cs2) + af * cf * sig * s;
+
+    R[0][5] = 0.0; R[1][5] = 0.0; R[2][5] = -btz; R[3][5] = bty;
+    R[4][5] = btz * s / r; R[5][5] = -bty * s / r; R[6][5] = bty * vz - btz * vy;
+
+    R[0][6] = af; R[1][6] = af * (vx + cf);
+    R[2][6] = af * vy - as * cs * bty * s; R[3][6] = af * vz - as * cs * btz * s;
+    R[4][6] = a * as * bty / r; R[5][6] = a * as * btz / r;
+    R[6][6] = af * (cf * cf + cf * vx + 0.5 * v2 - g2 * cs2) - as * cs * sig * s;
+
+    const double sc[7] = {0.5 / cs2, 0.5, 0.5 / cs2, -g0 / cs2, 0.5 / cs2, 0.5, 0.5 / cs2};
+    for (int m = 0; m < 7; ++m)
+        for (int c = 0; c < 7; ++c) L[m][c] *= sc[m];
+
+    double sgnBt;
+    if (variant == 0) { sgnBt = sgn(By); if (By == 0.0) sgnBt = sgn(Bz); }
+    else { sgnBt = sgn(Bz); if (By != 0.0) sgnBt = sgn(Bx); }
+    if (sgnBt == 0.0) sgnBt = 1.0;
+    int m1 = (a >= ca) ? 2 : 0, m2 = (a >= ca) ? 4 : 6;
+    for (int c = 0; c < 7; ++c) {
+        L[m1][c] *= sgnBt; L[m2][c] *= sgnBt;
+        R[c][m1] *= sgnBt; R[c][m2] *= sgnBt;
+    }
+}
+
+/* one side of the Jiang & Wu WENO correction, Weno5_2D.jl:1841-1853 */
+static double weno_phi(double a, double b, double c, double d, double eps)
+{
+    double t;
+    t = a - b;       double IS0 = 13.0 * (t * t);
+    t = a - 3.0 * b; IS0 += 3.0 * (t * t);
+    t = b - c;       double IS1 = 13.0 * (t * t);
+    t = b + c;       IS1 += 3.0 * (t * t);
+    t = c - d;       double IS2 = 13.0 * (t * t);
+    t = 3.0 * c - d; IS2 += 3.0 * (t * t);
+    double e0 = eps + IS0, e1 = eps + IS1, e2 = eps + IS2;
+    double al0 = 1.0 / (e0 * e0), al1 = 6.0 / (e1 * e1), al2 = 3.0 / (e2 * e2);
+    double om0 = al0 / (al0 + al1 + al2);
+    double om2 = al2 / (al0 + al1 + al2);
+    return om0 * (a - 2.0 * b + c) / 3.0 + (om2 - 0.5) * (b - 2.0 * c + d) / 6.0;
+}
+
+/* Numerical flux of one face from its 6-cell stencil, Weno5_2D.jl:1810-1888.
+ * Fk[k], qk[k] (k = 0..5) are the flux / conserved 7-vectors of cells f-2 .. f+3;
+ * aL, aR the eigenvalues of cells f and f+1. */
+static void face_flux(const double *const Fk[6], const double *const qk[6],
+                      const double aL[7], const double aR[7],
+                      double L[7][7], double R[7][7], double eps, double fhat[7])
+{
+    double Fs[7];
+    for (int m = 0; m < 7; ++m) {
+        double w[6], v[6];
+        for (int k = 0; k < 6; ++k) {
+            double sw = L[m][0] * Fk[k][0], sv = L[m][0] * qk[k][0];
+            for (int c = 1; c < 7; ++c) { sw += L[m][c] * Fk[k][c]; sv += L[m][c] * qk[k][c]; }
+            w[k] = sw; v[k] = sv;
+        }
+        double first = (-w[1] + 7.0 * w[2] + 7.0 * w[3] - w[4]) / 12.0;
+        double dw[5], dv[5];
+        for (int k = 0; k < 5; ++k) { dw[k] = w[k + 1] - w[k]; dv[k] = v[k + 1] - v[k]; }
+        double amax = fmax(fabs(aL[m]), fabs(aR[m]));
+        double second = weno_phi(0.5 * (dw[0] + amax * dv[0]), 0.5 * (dw[1] + amax * dv[1]),
+                                 0.5 * (dw[2] + amax * dv[2]), 0.5 * (dw[3] + amax * dv[3]), eps);
+        double third = weno_phi(0.5 * (dw[4] - amax * dv[4]), 0.5 * (dw[3] - amax * dv[3]),
+                                0.5 * (dw[2] - amax * dv[2]), 0.5 * (dw[1] - amax * dv[1]), eps);
+        Fs[m] = first - second + third;
+    }
+    for (int c = 0; c < 7; ++c) {
+        double s = Fs[0] * R[c][0];
+        for (int m = 1; m < 7; ++m) s += Fs[m] * R[c][m];
+        fhat[c] = s;
+    }
+}
+
+/* ------------------------------------------------------------------ one line of a sweep
+ *
+ * line[n][8] holds [rho,M1,M2,M3,B1,B2,B3,E] of the n cells of a line, with direction 1 the
+ * sweep direction.  Computes fhat[f][7] for faces f = NB-1 .. n-NB (0-based; the reference's
+ * 1-based NBnd .. Nq-NBnd+1, Weno5_2D.jl:993-1008) and the CT seeds
+ *   bs2[f] = fhat[4] + 0.5 (B1 v2|f + B1 v2|f+1),  bs3[f] = fhat[5] + 0.5 (B1 v3|f + B1 v3|f+1).
+ * The stencil cell f+3 = n of the last face continues the boundary condition (Q3).
+ * work: 4 arrays of n*8 doubles.
+ */
+static void sweep_line(int n, const double (*line)[8], double gam, double eps, int bc, int variant,
+                       double (*fhat)[7], double *bs2, double *bs3, double *work)
+{
+    double (*u)[8] = (double (*)[8])work;
+    double (*a)[8] = (double (*)[8])(work + 8 * (size_t)n);
+    double (*F)[8] = (double (*)[8])(work + 16 * (size_t)n);
+    double (*q7)[8] = (double (*)[8])(work + 24 * (size_t)n);
+    for (int i = 0; i < n; ++i) {
+        cell_primitives(line[i], gam, u[i]);
+        cell_eigenvalues(u[i], gam, a[i]);
+        cell_fluxes(line[i], u[i], F[i]);
+        q7[i][0] = line[i][0]; q7[i][1] = line[i][1]; q7[i][2] = line[i][2]; q7[i][3] = line[i][3];
+        q7[i][4] = line[i][5]; q7[i][5] = line[i][6]; q7[i][6] = line[i][7];
+    }
+    const int ni = n - 2 * NB;
+    for (int f = NB - 1; f <= n - NB; ++f) {
+        double L[7][7], R[7][7];
+        face_eigenvectors(u[f], u[f + 1], line[f][7], line[f + 1][7], gam, variant, L, R);
+        const double *Fk[6], *qk[6];
+        for (int k = 0; k < 6; ++k) {
+            int c = f - 2 + k;
+            if (c >= n) c = (bc == 1) ? c - ni : n - 1;
+            Fk[k] = F[c]; qk[k] = q7[c];
+        }
+        face_flux(Fk, qk, a[f], a[f + 1], L, R, eps, fhat[f]);
+        bs2[f] = fhat[f][4] + 0.5 * (u[f][4] * u[f][2] + u[f + 1][4] * u[f + 1][2]);
+        bs3[f] = fhat[f][5] + 0.5 * (u[f][4] * u[f][3] + u[f + 1][4] * u[f + 1][3]);
+    }
+}
+
+/* ------------------------------------------------------------------ 2-D grid services */
+
+#define IDX(i, j) ((size_t)(i) + (size_t)Nx * (size_t)(j))
+
+static void fill_axis_x(double *f, int Nx, int Ny, int bc)
+{
+    int n = Nx - 2 * NB;
+    for (int j = 0; j < Ny; ++j)
+        for (int g = 0; g < NB; ++g) {
+            if (bc == 1) {
+                f[IDX(g, j)] = f[IDX(n + g, j)];
+                f[IDX(Nx - NB + g, j)] = f[IDX(NB + g, j)];
+            } else {
+                f[IDX(g, j)] = f[IDX(NB, j)];
+                f[IDX(Nx - NB + g, j)] = f[IDX(Nx - NB - 1, j)];
+            }
+        }
+}
+
+static void fill_axis_y(double *f, int Nx, int Ny, int bc)
+{
+    int n = Ny - 2 * NB;
+    for (int g = 0; g < NB; ++g)
+        for (int i = 0; i < Nx; ++i) {
+            if (bc == 1) {
+                f[IDX(i, g)] = f[IDX(i, n + g)];
+                f[IDX(i, Ny - NB + g)] = f[IDX(i, NB + g)];
+            } else {
+                f[IDX(i, g)] = f[IDX(i, NB)];
+                f[IDX(i, Ny - NB + g)] = f[IDX(i, Ny - NB - 1)];
+            }
+        }
+}
+
+/* Weno5_2D.jl:1686-1702: x first, then y (so corners take the y copy of x-filled rows) */
+static void boundaries_q(double *q, int ncomp, int Nx, int Ny, const orc_params *P)
+{
+    for (int c = 0; c < ncomp; ++c) {
+        double *f = q + (size_t)c * Nx * Ny;
+        fill_axis_x(f, Nx, Ny, P->bc_x);
+        if (Ny > 1) fill_axis_y(f, Nx, Ny, P->bc_y);
+    }
+}
+
+/* Weno5_2D.jl:1704-1729 for one flux / face array */
+static void boundaries_flux(double *f, int Nx, int Ny, const orc_params *P)
+{
+    if (P->bc_x == 1) fill_axis_x(f, Nx, Ny, 1);
+    else for (int j = 0; j < Ny; ++j) { f[IDX(1, j)] = f[IDX(2, j)]; f[IDX(0, j)] = f[IDX(2, j)]; }
+    if (P->bc_y == 1) fill_axis_y(f, Nx, Ny, 1);
+    else for (int i = 0; i < Nx; ++i) { f[IDX(i, 1)] = f[IDX(i, 2)]; f[IDX(i, 0)] = f[IDX(i, 2)]; }
+    if (P->bc_x != 1)
+        for (int j = 0; j < Ny; ++j) { f[IDX(Nx - 2, j)] = f[IDX(Nx - 3, j)]; f[IDX(Nx - 1, j)] = f[IDX(Nx - 3, j)]; }
+    if (P->bc_y != 1)
+        for (int i = 0; i < Nx; ++i) { f[IDX(i, Ny - 2)] = f[IDX(i, Ny - 3)]; f[IDX(i, Ny - 1)] = f[IDX(i, Ny - 3)]; }
+    if (P->bc_x != 1) for (int j = 0; j < Ny; ++j) { f[IDX(0, j)] = 0.0; f[IDX(Nx - 1, j)] = 0.0; }
+    if (P->bc_y != 1) for (int i = 0; i < Nx; ++i) { f[IDX(i, 0)] = 0.0; f[IDX(i, Ny - 1)] = 0.0; }
+}
+
+/* Weno5_2D.jl:1770-1793 on planes; qE planes: rho,Mx,My,Mz,Bx,By,Bz,E */
+static double e2s(double rho, double mx, double my, double mz, double bx, double by, double bz,
+                  double E, double gam)
+{
+    double mom2 = mx * mx + my * my + mz * mz;
+    double B2 = bx * bx + by * by + bz * bz;
+    return (E - 0.5 * mom2 / rho - B2 / 2) * (gam - 1) / pow(rho, gam - 1);
+}
+
+static double s2e(double rho, double mx, double my, double mz, double bx, double by, double bz,
+                  double S, double gam)
+{
+    double mom2 = mx * mx + my * my + mz * mz;
+    double B2 = bx * bx + by * by + bz * bz;
+    return pow(rho, gam - 1) * S / (gam - 1) + B2 / 2 + 0.5 * mom2 / rho;
+}
+
+/* ------------------------------------------------------------------ directional sweeps on the grid
+ * q: 8 planes [rho,Mx,My,Mz,Bx,By,Bz,E]; dq: 8 planes (zeroed here); bs: one plane. */
+
+static void sweep_x(const orc_params *P, const double *q, double *dq, double *fsy)
+{
+    const int Nx = P->nx + 2 * NB, Ny = (P->ny > 1) ? P->ny + 2 * NB : 1;
+    const size_t pl = (size_t)Nx * Ny;
+    memset(dq, 0, 8 * pl * sizeof(double));
+    memset(fsy, 0, pl * sizeof(double));
+    const int j0 = (Ny > 1) ? NB - 1 : 0, j1 = (Ny > 1) ? Ny - NB : 0;
+#pragma omp parallel
+    {
+        double (*line)[8] = malloc(sizeof(double[8]) * Nx);
+        double (*fh)[7] = malloc(sizeof(double[7]) * Nx);
+        double *b2 = malloc(sizeof(double) * Nx), *b3 = malloc(sizeof(double) * Nx);
+        double *work = malloc(sizeof(double) * 32 * Nx);
+#pragma omp for schedule(static)
+        for (int j = j0; j <= j1; ++j) {
+            for (int i = 0; i < Nx; ++i)
+                for (int c = 0; c < 8; ++c) line[i][c] = q[c * pl + IDX(i, j)];
+            memset(fh, 0, sizeof(double[7]) * Nx);
+            sweep_line(Nx, line, P->gam, P->eps, P->bc_x, P->variant, fh, b2, b3, work);
+            static const int out[7] = {0, 1, 2, 3, 5, 6, 7};
+            for (int i = NB - 1; i <= Nx - NB; ++i) {
+                for (int c = 0; c < 7; ++c) dq[out[c] * pl + IDX(i, j)] = fh[i][c] - fh[i - 1][c];
+                fsy[IDX(i, j)] = b2[i];
+            }
+        }
+        free(line); free(fh); free(b2); free(b3); free(work);
+    }
+}
+
+/* y sweep without a transposed copy: the line runs along j and the vector components are
+ * permuted (x,y,z) -> (y,z,x) as rotate_state does (Weno5_2D.jl:1897-1927). */
+static void sweep_y(const orc_params *P, const double *q, double *dq, double *gsx)
+{
+    const int Nx = P->nx + 2 * NB, Ny = P->ny + 2 * NB;
+    const size_t pl = (size_t)Nx * Ny;
+    memset(dq, 0, 8 * pl * sizeof(double));
+    memset(gsx, 0, pl * sizeof(double));
+    static const int in[8] = {0, 2, 3, 1, 5, 6, 4, 7};  /* line comp c reads plane in[c] */
+    /* fhat comps [rho,M1,M2,M3,B2,B3,E] of the rotated frame -> planes My,Mz,Mx,Bz,Bx */
+    static const int out[7] = {0, 2, 3, 1, 6, 4, 7};
+#pragma omp parallel
+    {
+        double (*line)[8] = malloc(sizeof(double[8]) * Ny);
+        double (*fh)[7] = malloc(sizeof(double[7]) * Ny);
+        double *b2 = malloc(sizeof(double) * Ny), *b3 = malloc(sizeof(double) * Ny);
+        double *work = malloc(sizeof(double) * 32 * Ny);
+#pragma omp for schedule(static)
+        for (int i = NB - 1; i <= Nx - NB; ++i) {
+            for (int j = 0; j < Ny; ++j)
+                for (int c = 0; c < 8; ++c) line[j][c] = q[in[c] * pl + IDX(i, j)];
+            memset(fh, 0, sizeof(double[7]) * Ny);
+            sweep_line(Ny, line, P->gam, P->eps, P->bc_y, P->variant, fh, b2, b3, work);
+            for (int j = NB - 1; j <= Ny - NB; ++j) {
+                for (int c = 0; c < 7; ++c) dq[out[c] * pl + IDX(i, j)] = fh[j][c] - fh[j - 1][c];
+                gsx[IDX(i, j)] = b3[j];
+            }
+        }
+        free(line); free(fh); free(b2); free(b3); free(work);
+    }
+}
+
+/* Weno5_2D.jl:319-342 + the face-B update lines (:150-151 etc.) + :344-356 */
+static void ct_update(const orc_params *P, const double *fsy, const double *gsx,
+                      const double *bbx, const double *bby, double c, double dt,
+                      double *bxn, double *byn, double *Bx, double *By, double *Ox)
+{
+    const int Nx = P->nx + 2 * NB, Ny = P->ny + 2 * NB;
+    const size_t pl = (size_t)Nx * Ny;
+    memset(Ox, 0, pl * sizeof(double));
+#pragma omp parallel for schedule(static)
+    for (int j = 1; j < Ny - 1; ++j)
+        for (int i = 1; i < Nx - 1; ++i)
+            Ox[IDX(i, j)] = 0.5 * (gsx[IDX(i, j)] + gsx[IDX(i + 1, j)] - fsy[IDX(i, j)] - fsy[IDX(i, j + 1)]);
+    const double cy = c * dt / P->dy, cx = c * dt / P->dx;
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < Ny; ++j)
+        for (int i = 0; i < Nx; ++i) {
+            int inner = (i >= 1 && i < Nx - 1 && j >= 1 && j < Ny - 1);
+            double o = Ox[IDX(i, j)];
+            double oi = inner ? Ox[IDX(i - 1, j)] : 0.0;
+            double oj = inner ? Ox[IDX(i, j - 1)] : 0.0;
+            bxn[IDX(i, j)] = bbx[IDX(i, j)] - cy * (o - oj);
+            byn[IDX(i, j)] = bby[IDX(i, j)] - cx * (oi - o);
+        }
+    memset(Bx, 0, pl * sizeof(double));
+    memset(By, 0, pl * sizeof(double));
+#pragma omp parallel for schedule(static)
+    for (int j = NB; j <= Ny - 3; ++j)
+        for (int i = NB; i <= Nx - 3; ++i) {
+            Bx[IDX(i, j)] = (-bxn[IDX(i - 2, j)] + 9.0 * bxn[IDX(i - 1, j)] + 9.0 * bxn[IDX(i, j)] - bxn[IDX(i + 1, j)]) / 16.0;
+            By[IDX(i, j)] = (-byn[IDX(i, j - 2)] + 9.0 * byn[IDX(i, j - 1)] + 9.0 * byn[IDX(i, j)] - byn[IDX(i, j + 1)]) / 16.0;
+        }
+}
+
+typedef struct { double *dFx, *dFy, *fsy, *gsx, *Ox, *qE; } stage_work;
+
+/* One E-branch stage of classical_RK4_step (Weno5_2D.jl:134-180), including what survives
+ * of ES_Switch (:1734-1768): S = E2S(state), E = S2E(state with S).
+ * qk: 9 planes (input state); base: 8 planes [..,E]; out: 9 planes. */
+static void stage_2d(const orc_params *P, const double *qk, const double *base, const double *bbx,
+                     const double *bby, double c, double dt, int stage, double *out, double *bxn,
+                     double *byn, stage_work *W)
+{
+    const int Nx = P->nx + 2 * NB, Ny = P->ny + 2 * NB;
+    const size_t pl = (size_t)Nx * Ny;
+    memcpy(W->qE, qk, 7 * pl * sizeof(double));
+    memcpy(W->qE + 7 * pl, qk + 8 * pl, pl * sizeof(double));
+    sweep_x(P, W->qE, W->dFx, W->fsy);
+    sweep_y(P, W->qE, W->dFy, W->gsx);
+    double *qn = W->qE;   /* reuse: the state copy is no longer needed */
+    const double hx = dt / P->dx, hy = dt / P->dy;
+    for (int cmp = 0; cmp < 8; ++cmp) {
+        const double *b = base + cmp * pl, *fx = W->dFx + cmp * pl, *fy = W->dFy + cmp * pl;
+        double *o = qn + cmp * pl;
+#pragma omp parallel for schedule(static)
+        for (size_t k = 0; k < pl; ++k) {
+            if (stage <= 2)      o[k] = b[k] - 1.0 / 2 * dt / P->dy * fy[k] - 1.0 / 2 * dt / P->dx * fx[k];
+            else if (stage == 3) o[k] = b[k] - hx * fx[k] - hy * fy[k];
+            else                 o[k] = b[k] + (-1.0 / 6 * dt / P->dx * fx[k] - 1.0 / 6 * dt / P->dy * fy[k]);
+        }
+    }
+    boundaries_q(qn, 8, Nx, Ny, P);
+    boundaries_flux(W->fsy, Nx, Ny, P);
+    boundaries_flux(W->gsx, Nx, Ny, P);
+    ct_update(P, W->fsy, W->gsx, bbx, bby, c, dt, bxn, byn, qn + 4 * pl, qn + 5 * pl, W->Ox);
+    boundaries_q(qn, 8, Nx, Ny, P);
+    memcpy(out, qn, 7 * pl * sizeof(double));
+    double *S = out + 7 * pl, *E = out + 8 * pl;
+#pragma omp parallel for schedule(static)
+    for (size_t k = 0; k < pl; ++k) {
+        S[k] = e2s(qn[k], qn[pl + k], qn[2 * pl + k], qn[3 * pl + k], qn[4 * pl + k], qn[5 * pl + k],
+                   qn[6 * pl + k], qn[7 * pl + k], P->gam);
+        E[k] = s2e(qn[k], qn[pl + k], qn[2 * pl + k], qn[3 * pl + k], qn[4 * pl + k], qn[5 * pl + k],
+                   qn[6 * pl + k], S[k], P->gam);
+    }
+    boundaries_q(out, 9, Nx, Ny, P);
+}
+
+/* ------------------------------------------------------------------ exported entry points */
+
+/* classical_RK4_step(q0,bxb0,byb0,dt) -> (q4,bxb4,byb4), Weno5_2D.jl:125-317 */
+int orc_rk4_step_2d(const orc_params *P, const double *q0, const double *bxb0, const double *byb0,
+                    double dt, double *q4, double *bxb4, double *byb4)
+{
+    const int Nx = P->nx + 2 * NB, Ny = P->ny + 2 * NB;
+    const size_t pl = (size_t)Nx * Ny;
+    stage_work W;
+    W.dFx = malloc(8 * pl * sizeof(double)); W.dFy = malloc(8 * pl * sizeof(double));
+    W.fsy = malloc(pl * sizeof(double)); W.gsx = malloc(pl * sizeof(double));
+    W.Ox = malloc(pl * sizeof(double)); W.qE = malloc(8 * pl * sizeof(double));
+    double *q0E = malloc(8 * pl * sizeof(double)), *base = malloc(8 * pl * sizeof(double));
+    double *q1 = malloc(9 * pl * sizeof(double)), *q2 = malloc(9 * pl * sizeof(double)),
+           *q3 = malloc(9 * pl * sizeof(double));
+    double *bx[4], *by[4];
+    for (int k = 1; k < 4; ++k) { bx[k] = malloc(pl * sizeof(double)); by[k] = malloc(pl * sizeof(double)); }
+    double *bbx = malloc(pl * sizeof(double)), *bby = malloc(pl * sizeof(double));
+    if (!W.dFx || !W.dFy || !W.qE || !q0E || !base || !q1 || !q2 || !q3 || !bby) return -1;
+    memcpy(q0E, q0, 7 * pl * sizeof(double));
+    memcpy(q0E + 7 * pl, q0 + 8 * pl, pl * sizeof(double));
+
+    stage_2d(P, q0, q0E, bxb0, byb0, 0.5, dt, 1, q1, bx[1], by[1], &W);
+    stage_2d(P, q1, q0E, bxb0, byb0, 0.5, dt, 2, q2, bx[2], by[2], &W);
+    stage_2d(P, q2, q0E, bxb0, byb0, 1.0, dt, 3, q3, bx[3], by[3], &W);
+    for (int c = 0; c < 8; ++c) {
+        int src = (c == 7) ? 8 : c;
+        for (size_t k = 0; k < pl; ++k)
+            base[c * pl + k] = 1.0 / 3 * (-q0E[c * pl + k] + q1[src * pl + k] + 2 * q2[src * pl + k] + q3[src * pl + k]);
+    }
+    for (size_t k = 0; k < pl; ++k) {
+        bbx[k] = 1.0 / 3 * (-bxb0[k] + bx[1][k] + 2 * bx[2][k] + bx[3][k]);
+        bby[k] = 1.0 / 3 * (-byb0[k] + by[1][k] + 2 * by[2][k] + by[3][k]);
+    }
+    stage_2d(P, q3, base, bbx, bby, 1.0 / 6, dt, 4, q4, bxb4, byb4, &W);
+    boundaries_flux(bxb4, Nx, Ny, P);   /* Weno5_2D.jl:313 */
+    boundaries_flux(byb4, Nx, Ny, P);
+
+    free(W.dFx); free(W.dFy); free(W.fsy); free(W.gsx); free(W.Ox); free(W.qE);
+    free(q0E); free(base); free(q1); free(q2); free(q3); free(bbx); free(bby);
+    for (int k = 1; k < 4; ++k) { free(bx[k]); free(by[k]); }
+    return 0;
+}
+
+/* timestep / compute_global_vmax, Weno5_2D.jl:1930-1984; q has 9 planes (S in plane 7) */
+int orc_timestep_2d(const orc_params *P, const double *q, double *dt, double *vxmax, double *vymax)
+{
+    const int Nx = P->nx + 2 * NB, Ny = (P->ny > 1) ? P->ny + 2 * NB : 1;
+    const size_t pl = (size_t)Nx * Ny;
+    const int j0 = (Ny > 1) ? NB : 0, j1 = (Ny > 1) ? Ny - NB - 1 : 0;
+    double mx = -INFINITY, my = -INFINITY;
+#pragma omp parallel for reduction(max : mx, my) schedule(static)
+    for (int j = j0; j <= j1; ++j)
+        for (int i = NB; i <= Nx - NB - 1; ++i) {
+            size_t a = IDX(i, j), b = IDX(i + 1, j);
+            double rho = (q[a] + q[b]) / 2;
+            double vx = (q[pl + a] + q[pl + b]) / 2 / rho;
+            double vy = (q[2 * pl + a] + q[2 * pl + b]) / 2 / rho;
+            double Bx = (q[4 * pl + a] + q[4 * pl + b]) / 2;
+            double By = (q[5 * pl + a] + q[5 * pl + b]) / 2;
+            double Bz = (q[6 * pl + a] + q[6 * pl + b]) / 2;
+            double S = (q[7 * pl + a] + q[7 * pl + b]) / 2;
+            double pres = S * pow(rho, P->gam - 1);
+            double cs2 = P->gam * fabs(pres / rho);
+            double B2 = Bx * Bx + By * By + Bz * Bz;
+            double bbn2 = B2 / rho, bnx2 = Bx * Bx / rho, bny2 = By * By / rho;
+            double s = bbn2 + cs2;
+            double rootx = sqrt(fmax(0.0, s * s - 4 * bnx2 * cs2));
+            double rooty = sqrt(fmax(0.0, s * s - 4 * bny2 * cs2));
+            double lfx = sqrt(0.5 * (bbn2 + cs2 + rootx));
+            double lfy = sqrt(0.5 * (bbn2 + cs2 + rooty));
+            mx = fmax(mx, fabs(vx) + lfx);
+            my = fmax(my, fabs(vy) + lfy);
+        }
+    *vxmax = mx; *vymax = my;
+    if (Ny > 1) {
+        double dtx = P->dx / mx, dty = P->dy / my;
+        *dt = P->cfl / (1 / dtx + 1 / dty);
+    } else {
+        *dt = P->cfl * P->dx / mx;   /* Weno5_1D.jl:55 */
+    }
+    return 0;
+}
+
+/* compute_divB, Weno5_2D.jl:1986-1999 */
+int orc_divb(const orc_params *P, const double *bxb, const double *byb, double *divb)
+{
+    const int Nx = P->nx + 2 * NB, Ny = P->ny + 2 * NB;
+    memset(divb, 0, sizeof(double) * (size_t)Nx * Ny);
+    for (int j = NB - 1; j <= Ny - NB - 1; ++j)
+        for (int i = NB - 1; i <= Nx - NB - 1; ++i)
+            divb[IDX(i, j)] = (bxb[IDX(i, j)] - bxb[IDX(i - 1, j)]) / P->dx + (byb[IDX(i, j)] - byb[IDX(i, j - 1)]) / P->dy;
+    return 0;
+}
+
+/* interpolateB_center2face, Weno5_2D.jl:1669-1682; q has >= 6 planes */
+int orc_center2face(const orc_params *P, const double *q, double *bxb, double *byb)
+{
+    const int Nx = P->nx + 2 * NB, Ny = P->ny + 2 * NB;
+    const size_t pl = (size_t)Nx * Ny;
+    memset(bxb, 0, pl * sizeof(double));
+    memset(byb, 0, pl * sizeof(double));
+    const double *Bx = q + 4 * pl, *By = q + 5 * pl;
+    for (int j = 1; j <= Ny - 3; ++j)
+        for (int i = 1; i <= Nx - 3; ++i) {
+            bxb[IDX(i, j)] = (-Bx[IDX(i - 1, j)] + 9 * Bx[IDX(i, j)] + 9 * Bx[IDX(i + 1, j)] - Bx[IDX(i + 2, j)]) / 16;
+            byb[IDX(i, j)] = (-By[IDX(i, j - 1)] + 9 * By[IDX(i, j)] + 9 * By[IDX(i, j + 1)] - By[IDX(i, j + 2)]) / 16;
+        }
+    return 0;
+}
+
+/* boundaries!(q, a, b), Weno5_2D.jl:1684-1732; any of the pointers may be NULL */
+int orc_boundaries_2d(const orc_params *P, double *q9, double *a, double *b)
+{
+    const int Nx = P->nx + 2 * NB, Ny = P->ny + 2 * NB;
+    if (q9) boundaries_q(q9, 9, Nx, Ny, P);
+    if (a) boundaries_flux(a, Nx, Ny, P);
+    if (b) boundaries_flux(b, Nx, Ny, P);
+    return 0;
+}
+
+/* one directional sweep for unit tests: weno5_flux_difference_E (Weno5_2D.jl:973-1018)
+ * applied along x (dir 0) or along y with rotate_state folded in (dir 1).
+ * q8: 8 planes [rho,Mx,My,Mz,Bx,By,Bz,E]; dq: 8 planes; bs: fsy (dir 0) or gsx (dir 1). */
+int orc_sweep_2d(const orc_params *P, const double *q8, int dir, double *dq, double *bs)
+{
+    if (dir == 0) sweep_x(P, q8, dq, bs); else sweep_y(P, q8, dq, bs);
+    return 0;
+}
+
+/* 1-D: classical_RK4_step(q,dt) -> q4, Weno5_1D.jl:152-236 with the E-only ES_Switch
+ * (:238-260: q[1:7] = q_E, q[8] = E2S(q_E), q[9] = E).  q: (N,9) column-major. */
+int orc_rk4_step_1d(const orc_params *Pin, const double *q0, double dt, double *q4)
+{
+    orc_params P = *Pin;
+    P.ny = 1; P.variant = 1;
+    const int N = P.nx + 2 * NB;
+    const size_t pl = (size_t)N;
+    double *qE[4], *Q = malloc(8 * pl * sizeof(double)), *fs = malloc(pl * sizeof(double));
+    double *cur = malloc(9 * pl * sizeof(double)), *nxt = malloc(8 * pl * sizeof(double));
+    for (int k = 0; k < 4; ++k) qE[k] = malloc(8 * pl * sizeof(double));
+    memcpy(cur, q0, 9 * pl * sizeof(double));
+    for (int st = 1; st <= 4; ++st) {
+        double *e = qE[st - 1];
+        memcpy(e, cur, 7 * pl * sizeof(double));
+        memcpy(e + 7 * pl, cur + 8 * pl, pl * sizeof(double));
+        sweep_x(&P, e, Q, fs);
+        /* the reference forms Q only on iMin..iMax (Weno5_1D.jl:766-775) */
+        for (int c = 0; c < 8; ++c) { Q[c * pl + NB - 1] = 0.0; Q[c * pl + N - NB] = 0.0; }
+        for (int c = 0; c < 8; ++c)
+            for (size_t i = 0; i < pl; ++i) {
+                size_t k = c * pl + i;
+                if (st <= 2)      nxt[k] = qE[0][k] - 1.0 / 2 * dt / P.dx * Q[k];
+                else if (st == 3) nxt[k] = qE[0][k] - dt / P.dx * Q[k];
+                else nxt[k] = 1.0 / 3 * (-qE[0][k] + qE[1][k] + 2 * qE[2][k] + qE[3][k] - 1.0 / 2 * dt / P.dx * Q[k]);
+            }
+        memcpy(cur, nxt, 7 * pl * sizeof(double));
+        for (size_t i = 0; i < pl; ++i) {
+            cur[7 * pl + i] = e2s(nxt[i], nxt[pl + i], nxt[2 * pl + i], nxt[3 * pl + i], nxt[4 * pl + i],
+                                  nxt[5 * pl + i], nxt[6 * pl + i], nxt[7 * pl + i], P.gam);
+            cur[8 * pl + i] = nxt[7 * pl + i];
+        }
+        for (int c = 0; c < 9; ++c) fill_axis_x(cur + c * pl, N, 1, P.bc_x);   /* Weno5_1D.jl:1076-1090 */
+    }
+    memcpy(q4, cur, 9 * pl * sizeof(double));
+    for (int k = 0; k < 4; ++k) free(qE[k]);
+    free(Q); free(fs); free(cur); free(nxt);
+    return 0;
+}
+
+/* driver loop used for the CPU baseline: nsteps of (timestep, RK4 step) in place */
+int orc_advance_2d(const orc_params *P, double *q, double *bxb, double *byb, int nsteps, double *t)
+{
+    const int Nx = P->nx + 2 * NB, Ny = P->ny + 2 * NB;
+    const size_t pl = (size_t)Nx * Ny;
+    double *q4 = malloc(9 * pl * sizeof(double)), *bx4 = malloc(pl * sizeof(double)), *by4 = malloc(pl * sizeof(double));
+    for (int s = 0; s < nsteps; ++s) {
+        double dt, vx, vy;
+        orc_timestep_2d(P, q, &dt, &vx, &vy);
+        if (orc_rk4_step_2d(P, q, bxb, byb, dt, q4, bx4, by4)) return -1;
+        memcpy(q, q4, 9 * pl * sizeof(double));
+        memcpy(bxb, bx4, pl * sizeof(double));
+        memcpy(byb, by4, pl * sizeof(double));
+        *t += dt;
+    }
+    free(q4); free(bx4); free(by4);
+    return 0;
+}
+
+int orc_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
