@@ -1,0 +1,133 @@
+/*
+ * libweno5mhd -- C ABI of the B200 (sm_100a) WENO5 ideal-MHD solver.
+ *
+ * Drop-in boundary for the hot path of jdonnert/julia's Weno5_2D.jl / Weno5_1D.jl.  The
+ * reference has no FFI: the path sits behind plain Julia functions.  Each entry point
+ * below names the Julia function (file:line under /root/reference) whose work it does;
+ * julia_b200/julia/Weno5GPU.jl re-exports those names over ccall.
+ *
+ * Conventions
+ *  - plain C, no exceptions cross the boundary; every call returns 0 on success or a
+ *    negative weno5_status, and weno5_last_error() gives a thread-local message;
+ *  - host arrays are exactly the reference's Julia arrays (column-major Float64):
+ *      q   (Nx,Ny,9)  [rho,Mx,My,Mz,Bx,By,Bz,S,E]      Weno5_2D.jl:35,2006
+ *      bxb (Nx,Ny)    Bx on the x-face i+1/2             Weno5_2D.jl:37,1669
+ *      byb (Nx,Ny)    By on the y-face j+1/2
+ *      1-D: q (N,9)                                      Weno5_1D.jl:37,1101
+ *    with Nx = nx + 2*3, Ny = ny + 2*3 (NBnd = 3, Weno5_2D.jl:9-17);
+ *  - the caller owns host buffers, the library owns device memory inside the handle;
+ *  - one host thread per handle; handles are independent;
+ *  - there is no CPU fallback: every call fails with WENO5_ERR_CUDA if no sm_100 device
+ *    is usable.
+ */
+#ifndef WENO5MHD_H
+#define WENO5MHD_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WENO5_NBND 3
+
+typedef enum {
+    WENO5_OK = 0,
+    WENO5_ERR_ARG = -1,      /* bad argument / unsupported configuration */
+    WENO5_ERR_CUDA = -2,     /* CUDA runtime error or no usable device   */
+    WENO5_ERR_NCCL = -3,     /* NCCL missing or failed                   */
+    WENO5_ERR_STATE = -4,    /* call sequence error (e.g. step before upload) */
+    WENO5_ERR_NUMERIC = -5   /* non-finite wave speed / time step        */
+} weno5_status;
+
+enum { WENO5_BC_OUTFLOW = 0,   /* zero-gradient, the reference's only BC (Weno5_2D.jl:1684-1732) */
+       WENO5_BC_PERIODIC = 1 };
+
+/* The reference's module-level constants (Weno5_2D.jl:7-29, Weno5_1D.jl:9-29) as a struct. */
+typedef struct {
+    int nx, ny;              /* interior cells of the GLOBAL grid; ny = 1 selects the 1-D solver */
+    double dx, dy;           /* cell sizes (dy ignored in 1-D)           */
+    double gamma;            /* gam     = 5/3                             */
+    double cfl;              /* courFac = 0.8                             */
+    double eps;              /* eps     = 1e-6 (WENO)                     */
+    int bc_x, bc_y;          /* WENO5_BC_*                                */
+    int es_roundtrip;        /* 1: E <- S2E(E2S(E)) after every stage as the 2-D reference does
+                                (Weno5_2D.jl:1738,1765); 0: keep E (as the 1-D reference does,
+                                Weno5_1D.jl:252-254; round-off-level difference, faster)   */
+} weno5_params;
+
+typedef struct weno5_ctx weno5_ctx;
+
+const char *weno5_last_error(void);
+int weno5_version(void);
+/* number of usable sm_100 devices (0 if none) */
+int weno5_device_count(void);
+
+/* Create a solver on CUDA device `device` for the slab [j_offset, j_offset + ny_local) of the
+ * global grid (single GPU: j_offset = 0, ny_local = params->ny). */
+int weno5_create(const weno5_params *params, int device, int ny_local, int j_offset, weno5_ctx **out);
+int weno5_destroy(weno5_ctx *ctx);
+
+/* ---- multi-GPU: one handle per rank, y-slabs, NCCL send/recv of ghost rows per RK stage and
+ * an NCCL max-allreduce for the time step.  The 128-byte id is produced on rank 0 and
+ * distributed by the host program (Julia Distributed / MPI / torch.distributed). */
+int weno5_comm_unique_id(unsigned char id[128]);
+int weno5_comm_init(weno5_ctx *ctx, int rank, int nranks, const unsigned char id[128]);
+
+/* ---- state transfer.  Host arrays cover the LOCAL slab: (Nx, ny_local+6, 9) etc. */
+/* q/bxb/byb as produced by initial_conditions() (Weno5_2D.jl:2001) and
+ * interpolateB_center2face() (:1669); bxb == NULL derives the face fields on the device with
+ * that same 4th-order interpolation.  Applies boundaries! (:39). */
+int weno5_upload(weno5_ctx *ctx, const double *q, const double *bxb, const double *byb);
+int weno5_download(weno5_ctx *ctx, double *q, double *bxb, double *byb);
+/* 1-D: q is (N,9) */
+int weno5_upload_1d(weno5_ctx *ctx, const double *q);
+int weno5_download_1d(weno5_ctx *ctx, double *q);
+
+/* ---- the hot path */
+/* boundaries!(q, bxb, byb)                    Weno5_2D.jl:1684 ; boundaries!(q) Weno5_1D.jl:1076 */
+int weno5_boundaries(weno5_ctx *ctx);
+/* timestep(q) -> dt, vxmax, vymax             Weno5_2D.jl:1930,1942 ; 1-D: compute_global_vmax
+ * Weno5_1D.jl:1038 and dt = courFac*dx/vmax (:55), vymax = 0.  Global over all ranks. */
+int weno5_timestep(weno5_ctx *ctx, double *dt, double *vxmax, double *vymax);
+/* classical_RK4_step(q,bxb,byb,dt) in place   Weno5_2D.jl:125 ; 1-D (q,dt) Weno5_1D.jl:152 */
+int weno5_rk4_step(weno5_ctx *ctx, double dt);
+/* the driver loop of WENO5_2D()/WENO5_1D() (Weno5_2D.jl:50-72, Weno5_1D.jl:51-71) kept on the
+ * device: repeat {dt = timestep(q); classical_RK4_step} nsteps times, or until t >= tmax when
+ * tmax > 0 (the last step is shortened to land on tmax).  *t is read and updated. */
+int weno5_advance(weno5_ctx *ctx, int nsteps, double tmax, double *t, int *nsteps_done);
+/* compute_divB(bxb,byb) -> divB (Nx,Ny_local+6)          Weno5_2D.jl:1986 */
+int weno5_divb(weno5_ctx *ctx, double *divb);
+/* interior sums of the 9 components of q and of bxb, byb (conservation diagnostics,
+ * cf. the per-component max/mean print at Weno5_2D.jl:69-71); local to this rank */
+int weno5_totals(weno5_ctx *ctx, double sums[11]);
+
+/* ---- one-shot, reference-shaped calls: host arrays in -> host arrays out */
+/* (q4,bxb4,byb4) = classical_RK4_step(q0,bxb0,byb0,dt)   Weno5_2D.jl:125-317 */
+int weno5_classical_rk4_step_2d(const weno5_params *params, const double *q0, const double *bxb0,
+                                const double *byb0, double dt, double *q4, double *bxb4, double *byb4);
+/* q4 = classical_RK4_step(q,dt)[1]                        Weno5_1D.jl:152-236 */
+int weno5_classical_rk4_step_1d(const weno5_params *params, const double *q0, double dt, double *q4);
+/* same through an existing handle (no allocation): upload, step, download */
+int weno5_step_host(weno5_ctx *ctx, const double *q0, const double *bxb0, const double *byb0,
+                    double dt, double *q4, double *bxb4, double *byb4);
+
+/* ---- host memory helpers (page-locked buffers make upload/download asynchronous-capable) */
+int weno5_host_alloc(void **ptr, unsigned long long bytes);
+int weno5_host_free(void *ptr);
+
+/* ---- instrumentation */
+/* kernels launched by this handle since creation */
+unsigned long long weno5_launch_count(const weno5_ctx *ctx);
+/* accumulated device time (ms, CUDA events on the handle's stream) of the flux kernels and
+ * their launch count since the last reset; enables the per-kernel roofline in bench.py */
+int weno5_profile(weno5_ctx *ctx, int enable);
+int weno5_profile_read(weno5_ctx *ctx, double *flux_ms, unsigned long long *flux_launches, int reset);
+/* debug: copy an internal device field (by name: "rhs0".."rhs6","fsy","gsx",...) in the public
+ * (Nx,Ny_local+6) layout to the host */
+int weno5_debug_fetch(weno5_ctx *ctx, const char *name, double *out);
+/* raw CUDA stream of the handle (cudaStream_t as void*) for event timing by the caller */
+void *weno5_stream(weno5_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WENO5MHD_H */

@@ -1,0 +1,744 @@
+// C ABI and host orchestration of libweno5mhd (see include/weno5mhd.h).
+//
+// One handle = one GPU = one y-slab.  All work of a handle is queued on its own stream; the
+// time step, the simulation time and the wave-speed maxima live in device memory (`ctl`), so
+// the step loop of weno5_advance() never synchronises with the host.
+//
+// Stage sequence (replaces classical_RK4_step, Weno5_2D.jl:125-317, E branch):
+//   flux_x  : d fhat_x (6 fields) + fsy                       <- q_k
+//   flux_y  : d fhat_y, fused RK update of rho,M,Bz,E + gsx   <- q_k, rhs, base
+//   ct_faces: corner EMF, bxb/byb RK update                   <- fsy, gsx
+//   ct_centers: Bx,By from the faces (4th order)
+//   entropy : S = E2S(q) (and E = S2E(q,S) if es_roundtrip)   [every stage or last only]
+//   bc_fill : ghosts of the 8(9) cell fields; NCCL exchange of 4 ghost rows on slab cuts
+// RK storage: Q0 (step input, overwritten by the result in stage 4), QA/QB ping-pong,
+// ACC = -q0 + q1 + 2 q2 accumulated while q1, q2 are read anyway.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "../../include/weno5mhd.h"
+#include "weno5_kernels.cuh"
+
+using namespace w5;
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(WENO5_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------------------ NCCL through dlopen
+// The library has no link-time NCCL dependency: single-GPU users (and Julia) need none, and a
+// host process that already loaded NCCL (e.g. torch) shares that copy.
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess = 0 };
+enum { ncclFloat64 = 8, ncclUint64 = 5 };
+enum { ncclMax = 2 };
+
+struct NcclApi {
+    void *h = nullptr;
+    int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_load()
+{
+    if (g_nccl.h) return 0;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *n : names) { h = dlopen(n, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL); if (h) break; }
+    const char *env = getenv("WENO5_NCCL_LIB");
+    if (!h && env) h = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+    for (const char *n : names) { if (h) break; h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); }
+    if (!h) return fail(WENO5_ERR_NCCL, "cannot load libnccl.so.2 (set WENO5_NCCL_LIB): %s", dlerror());
+#define SYM(field, name)                                                                  \
+    *(void **)(&g_nccl.field) = dlsym(h, name);                                            \
+    if (!g_nccl.field) return fail(WENO5_ERR_NCCL, "libnccl lacks symbol %s", name);
+    SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
+    SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(AllReduce, "ncclAllReduce")
+    SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+    g_nccl.h = h;
+    return 0;
+}
+
+#define NC(call)                                                                                  \
+    do {                                                                                          \
+        int r_ = (call);                                                                          \
+        if (r_ != ncclSuccess)                                                                    \
+            return fail(WENO5_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?"); \
+    } while (0)
+
+// ------------------------------------------------------------------ handle
+struct State {                 // 9 cell planes + 2 face planes
+    double *q[NCELL];
+    double *bx, *by;
+};
+
+struct weno5_ctx {
+    weno5_params P;
+    int device;
+    int ny_local, j_offset;
+    Geom g;
+    cudaStream_t stream = nullptr;
+    double *pool = nullptr;          // one allocation for every plane
+    State Q0, QA, QB;
+    double *acc[6], *accbx, *accby, *acc_by1d;
+    double *rhs[7];
+    double *fsy, *gsx;
+    double *scratch;                 // one plane (divB)
+    double *ctl = nullptr;           // device: dt, t, vxmax, vymax, tmax, steps, bad
+    unsigned long long *vmax_bits = nullptr;
+    double *sums = nullptr;
+    double *h_ctl = nullptr;         // pinned mirror
+    int side[4];                     // SideBC of x-lo, x-hi, y-lo, y-hi for this slab
+    bool uploaded = false;
+    // multi-GPU
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+    int up = -1, down = -1;          // neighbour ranks (-1: none)
+    // instrumentation
+    unsigned long long launches = 0;
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+    size_t ev_used = 0;
+    double prof_ms = 0.0;
+    unsigned long long prof_launches = 0;
+    // launch decomposition
+    int segx_len, nsegx, segy_len, nsegy;
+};
+
+static void choose_segments(int nfaces, int NS, int strips, int &seg_len, int &nseg)
+{
+    const int chunks = (nfaces + NS - 1) / NS;
+    int want = (8 * 148 + strips - 1) / strips;          // aim at >= 8 waves of one CTA per SM
+    if (want < 1) want = 1;
+    if (want > chunks) want = chunks;
+    const int per = (chunks + want - 1) / want;
+    seg_len = per * NS;
+    nseg = (nfaces + seg_len - 1) / seg_len;
+}
+
+extern "C" const char *weno5_last_error(void) { return g_err; }
+extern "C" int weno5_version(void) { return 100; }
+
+extern "C" int weno5_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major == 10) ++ok;
+    }
+    return ok;
+}
+
+static State carve_state(double *&cur, size_t plane)
+{
+    State s;
+    for (int k = 0; k < NCELL; ++k) { s.q[k] = cur; cur += plane; }
+    s.bx = cur; cur += plane;
+    s.by = cur; cur += plane;
+    return s;
+}
+
+extern "C" int weno5_create(const weno5_params *P, int device, int ny_local, int j_offset, weno5_ctx **out)
+{
+    if (!P || !out) return fail(WENO5_ERR_ARG, "null argument");
+    const bool is1d = P->ny == 1;
+    if (P->nx < 8 || (!is1d && (P->ny < 8 || ny_local < 8)))
+        return fail(WENO5_ERR_ARG, "grid too small: nx=%d ny=%d ny_local=%d (need >= 8, or ny = 1)", P->nx, P->ny, ny_local);
+    if (is1d && (ny_local != 1 || j_offset != 0)) return fail(WENO5_ERR_ARG, "1-D grids cannot be decomposed");
+    if (!is1d && (j_offset < 0 || j_offset + ny_local > P->ny)) return fail(WENO5_ERR_ARG, "slab outside the grid");
+    if (!(P->dx > 0) || (!is1d && !(P->dy > 0)) || !(P->gamma > 1.0)) return fail(WENO5_ERR_ARG, "bad dx/dy/gamma");
+    for (int b : {P->bc_x, P->bc_y})
+        if (b != WENO5_BC_OUTFLOW && b != WENO5_BC_PERIODIC) return fail(WENO5_ERR_ARG, "unknown boundary condition %d", b);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(WENO5_ERR_CUDA, "no CUDA device: libweno5mhd has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(WENO5_ERR_ARG, "device %d out of range (0..%d)", device, ndev - 1);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(WENO5_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    CU(cudaSetDevice(device));
+
+    weno5_ctx *c = new weno5_ctx();
+    c->P = *P;
+    c->device = device;
+    c->ny_local = ny_local;
+    c->j_offset = j_offset;
+    Geom &g = c->g;
+    g.is1d = is1d;
+    g.NXI = P->nx + 2 * G;
+    g.NYI = is1d ? 1 : ny_local + 2 * G;
+    g.pitch = (g.NXI + 15) / 16 * 16;
+    g.Nx = P->nx + 2 * WENO5_NBND;
+    g.Ny = is1d ? 1 : ny_local + 2 * WENO5_NBND;
+    g.plane = (size_t)g.pitch * g.NYI;
+
+    c->side[0] = c->side[1] = P->bc_x == WENO5_BC_PERIODIC ? SIDE_PERIODIC : SIDE_OUTFLOW;
+    const int ybc = P->bc_y == WENO5_BC_PERIODIC ? SIDE_PERIODIC : SIDE_OUTFLOW;
+    const bool whole = ny_local == P->ny;
+    c->side[2] = (j_offset == 0) ? (whole || ybc == SIDE_OUTFLOW ? ybc : SIDE_NONE) : SIDE_NONE;
+    c->side[3] = (j_offset + ny_local == P->ny) ? (whole || ybc == SIDE_OUTFLOW ? ybc : SIDE_NONE) : SIDE_NONE;
+    if (is1d) c->side[2] = c->side[3] = SIDE_NONE;
+
+    // planes: 3 states x 11 + acc 6+2+1 + rhs 7 + fsy,gsx + scratch
+    const size_t nplanes = 3 * 11 + 9 + 7 + 2 + 1;
+    if (cudaMalloc(&c->pool, nplanes * g.plane * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError();
+        delete c;
+        return fail(WENO5_ERR_CUDA, "cudaMalloc of %.2f GB failed", nplanes * g.plane * 8.0 / 1e9);
+    }
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaMemsetAsync(c->pool, 0, nplanes * g.plane * sizeof(double), c->stream));
+    double *cur = c->pool;
+    c->Q0 = carve_state(cur, g.plane);
+    c->QA = carve_state(cur, g.plane);
+    c->QB = carve_state(cur, g.plane);
+    for (int k = 0; k < 6; ++k) { c->acc[k] = cur; cur += g.plane; }
+    c->accbx = cur; cur += g.plane;
+    c->accby = cur; cur += g.plane;
+    c->acc_by1d = cur; cur += g.plane;
+    for (int k = 0; k < 7; ++k) { c->rhs[k] = cur; cur += g.plane; }
+    c->fsy = cur; cur += g.plane;
+    c->gsx = cur; cur += g.plane;
+    c->scratch = cur; cur += g.plane;
+
+    CU(cudaMalloc(&c->ctl, 8 * sizeof(double)));
+    CU(cudaMemsetAsync(c->ctl, 0, 8 * sizeof(double), c->stream));
+    CU(cudaMalloc(&c->vmax_bits, 2 * sizeof(unsigned long long)));
+    CU(cudaMalloc(&c->sums, 16 * sizeof(double)));
+    CU(cudaMallocHost(&c->h_ctl, 16 * sizeof(double)));
+
+    choose_segments(g.NXI - 4, 64, (g.NYI + 3) / 4, c->segx_len, c->nsegx);
+    if (!is1d) choose_segments(g.NYI - 4, 8, (g.NXI + 31) / 32, c->segy_len, c->nsegy);
+    CU(cudaStreamSynchronize(c->stream));
+    *out = c;
+    return 0;
+}
+
+extern "C" int weno5_destroy(weno5_ctx *c)
+{
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    for (auto &e : c->ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    cudaFree(c->pool); cudaFree(c->ctl); cudaFree(c->vmax_bits); cudaFree(c->sums);
+    cudaFreeHost(c->h_ctl);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+// ------------------------------------------------------------------ multi-GPU plumbing
+extern "C" int weno5_comm_unique_id(unsigned char id[128])
+{
+    if (int r = nccl_load()) return r;
+    ncclUniqueId u;
+    NC(g_nccl.GetUniqueId(&u));
+    memcpy(id, u.internal, 128);
+    return 0;
+}
+
+extern "C" int weno5_comm_init(weno5_ctx *c, int rank, int nranks, const unsigned char id[128])
+{
+    if (!c || !id) return fail(WENO5_ERR_ARG, "null argument");
+    if (c->g.is1d) return fail(WENO5_ERR_ARG, "1-D grids cannot be decomposed");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(WENO5_ERR_ARG, "bad rank %d of %d", rank, nranks);
+    if (int r = nccl_load()) return r;
+    CU(cudaSetDevice(c->device));
+    ncclUniqueId u;
+    memcpy(u.internal, id, 128);
+    NC(g_nccl.CommInitRank(&c->comm, nranks, u, rank));
+    c->rank = rank;
+    c->nranks = nranks;
+    const bool per = c->P.bc_y == WENO5_BC_PERIODIC;
+    c->up = rank + 1 < nranks ? rank + 1 : (per && nranks > 1 ? 0 : -1);
+    c->down = rank > 0 ? rank - 1 : (per && nranks > 1 ? nranks - 1 : -1);
+    return 0;
+}
+
+// send the 4 outermost interior rows, receive the 4 ghost rows, for each plane
+static int exchange_rows(weno5_ctx *c, double *const planes[], int n)
+{
+    if (!c->comm || (c->up < 0 && c->down < 0)) return 0;
+    const Geom &g = c->g;
+    const size_t cnt = (size_t)G * g.pitch;
+    NC(g_nccl.GroupStart());
+    for (int k = 0; k < n; ++k) {
+        double *p = planes[k];
+        if (c->up >= 0) {
+            NC(g_nccl.Send(p + (size_t)(g.NYI - 2 * G) * g.pitch, cnt, ncclFloat64, c->up, c->comm, c->stream));
+        }
+        if (c->down >= 0) {
+            NC(g_nccl.Recv(p, cnt, ncclFloat64, c->down, c->comm, c->stream));
+            NC(g_nccl.Send(p + (size_t)G * g.pitch, cnt, ncclFloat64, c->down, c->comm, c->stream));
+        }
+        if (c->up >= 0) {
+            NC(g_nccl.Recv(p + (size_t)(g.NYI - G) * g.pitch, cnt, ncclFloat64, c->up, c->comm, c->stream));
+        }
+    }
+    NC(g_nccl.GroupEnd());
+    c->launches += 1;
+    return 0;
+}
+
+// ------------------------------------------------------------------ transfers
+// host component order is the reference's [rho,Mx,My,Mz,Bx,By,Bz,S,E]; on the device E sits before S
+// so that the eight fields the sweeps read are planes 0..7
+static inline int host_comp(int k) { return k == C_E ? 8 : (k == C_S ? 7 : k); }
+
+static int copy_plane(weno5_ctx *c, double *dev, const double *host_in, double *host_out)
+{
+    const Geom &g = c->g;
+    double *d = dev + 1 + (g.is1d ? 0 : g.pitch);          // public (1,1) -> internal (1,1)
+    const size_t w = (size_t)g.Nx * sizeof(double);
+    if (host_in) CU(cudaMemcpy2DAsync(d, g.pitch * sizeof(double), host_in, w, w, g.Ny, cudaMemcpyHostToDevice, c->stream));
+    if (host_out) CU(cudaMemcpy2DAsync(host_out, w, d, g.pitch * sizeof(double), w, g.Ny, cudaMemcpyDeviceToHost, c->stream));
+    return 0;
+}
+
+static int apply_boundaries(weno5_ctx *c, State &S, bool faces)
+{
+    launch_bc_fill(S.q, NCELL, c->g, c->side, nullptr, c->stream);
+    c->launches++;
+    if (c->comm) { if (int r = exchange_rows(c, S.q, NCELL)) return r; }
+    if (faces && !c->g.is1d) {
+        launch_face_bc(S.bx, S.by, c->g, c->side, nullptr, c->stream);
+        c->launches++;
+        if (c->comm) {
+            double *f[2] = {S.bx, S.by};
+            if (int r = exchange_rows(c, f, 2)) return r;
+        }
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int weno5_upload(weno5_ctx *c, const double *q, const double *bxb, const double *byb)
+{
+    if (!c || !q) return fail(WENO5_ERR_ARG, "null argument");
+    if (c->g.is1d) return fail(WENO5_ERR_ARG, "use weno5_upload_1d for 1-D grids");
+    if ((bxb == nullptr) != (byb == nullptr)) return fail(WENO5_ERR_ARG, "pass both face fields or neither");
+    CU(cudaSetDevice(c->device));
+    const size_t hp = (size_t)c->g.Nx * c->g.Ny;
+    for (int k = 0; k < NCELL; ++k) if (int r = copy_plane(c, c->Q0.q[k], q + host_comp(k) * hp, nullptr)) return r;
+    if (bxb) {
+        if (int r = copy_plane(c, c->Q0.bx, bxb, nullptr)) return r;
+        if (int r = copy_plane(c, c->Q0.by, byb, nullptr)) return r;
+    } else {
+        launch_center2face(c->Q0.q[C_BX], c->Q0.q[C_BY], c->Q0.bx, c->Q0.by, c->g, c->stream);
+        c->launches++;
+    }
+    if (int r = apply_boundaries(c, c->Q0, true)) return r;
+    CU(cudaStreamSynchronize(c->stream));
+    c->uploaded = true;
+    return 0;
+}
+
+extern "C" int weno5_download(weno5_ctx *c, double *q, double *bxb, double *byb)
+{
+    if (!c) return fail(WENO5_ERR_ARG, "null argument");
+    if (c->g.is1d) return fail(WENO5_ERR_ARG, "use weno5_download_1d for 1-D grids");
+    if (!c->uploaded) return fail(WENO5_ERR_STATE, "no state on the device yet");
+    CU(cudaSetDevice(c->device));
+    const size_t hp = (size_t)c->g.Nx * c->g.Ny;
+    if (q) for (int k = 0; k < NCELL; ++k) if (int r = copy_plane(c, c->Q0.q[k], nullptr, q + host_comp(k) * hp)) return r;
+    if (bxb) if (int r = copy_plane(c, c->Q0.bx, nullptr, bxb)) return r;
+    if (byb) if (int r = copy_plane(c, c->Q0.by, nullptr, byb)) return r;
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int weno5_upload_1d(weno5_ctx *c, const double *q)
+{
+    if (!c || !q) return fail(WENO5_ERR_ARG, "null argument");
+    if (!c->g.is1d) return fail(WENO5_ERR_ARG, "handle is 2-D");
+    CU(cudaSetDevice(c->device));
+    for (int k = 0; k < NCELL; ++k) if (int r = copy_plane(c, c->Q0.q[k], q + (size_t)host_comp(k) * c->g.Nx, nullptr)) return r;
+    if (int r = apply_boundaries(c, c->Q0, false)) return r;
+    CU(cudaStreamSynchronize(c->stream));
+    c->uploaded = true;
+    return 0;
+}
+
+extern "C" int weno5_download_1d(weno5_ctx *c, double *q)
+{
+    if (!c || !q) return fail(WENO5_ERR_ARG, "null argument");
+    if (!c->g.is1d) return fail(WENO5_ERR_ARG, "handle is 2-D");
+    if (!c->uploaded) return fail(WENO5_ERR_STATE, "no state on the device yet");
+    CU(cudaSetDevice(c->device));
+    for (int k = 0; k < NCELL; ++k) if (int r = copy_plane(c, c->Q0.q[k], nullptr, q + (size_t)host_comp(k) * c->g.Nx)) return r;
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int weno5_boundaries(weno5_ctx *c)
+{
+    if (!c) return fail(WENO5_ERR_ARG, "null argument");
+    if (!c->uploaded) return fail(WENO5_ERR_STATE, "no state on the device yet");
+    CU(cudaSetDevice(c->device));
+    if (int r = apply_boundaries(c, c->Q0, true)) return r;
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------ time step
+static int enqueue_timestep(weno5_ctx *c)
+{
+    launch_vmax(c->Q0.q, c->g, c->P.gamma, c->vmax_bits, c->stream);
+    c->launches += 1;
+    if (c->comm && c->nranks > 1) {
+        NC(g_nccl.AllReduce(c->vmax_bits, c->vmax_bits, 2, ncclUint64, ncclMax, c->comm, c->stream));
+        c->launches += 1;
+    }
+    launch_dt_from_vmax(c->vmax_bits, c->ctl, c->P.dx, c->P.dy, c->P.cfl, c->g.is1d, c->stream);
+    c->launches += 1;
+    return 0;
+}
+
+extern "C" int weno5_timestep(weno5_ctx *c, double *dt, double *vxmax, double *vymax)
+{
+    if (!c) return fail(WENO5_ERR_ARG, "null argument");
+    if (!c->uploaded) return fail(WENO5_ERR_STATE, "no state on the device yet");
+    CU(cudaSetDevice(c->device));
+    const double zero[2] = {0.0, 0.0};
+    CU(cudaMemcpyAsync(c->ctl + 4, zero, sizeof(double), cudaMemcpyHostToDevice, c->stream));   // tmax off
+    if (int r = enqueue_timestep(c)) return r;
+    CU(cudaMemcpyAsync(c->h_ctl, c->ctl, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    if (c->h_ctl[6] != 0.0) {
+        CU(cudaMemsetAsync(c->ctl + 6, 0, sizeof(double), c->stream));
+        return fail(WENO5_ERR_NUMERIC, "non-finite wave speed (vxmax=%g vymax=%g)", c->h_ctl[2], c->h_ctl[3]);
+    }
+    if (dt) *dt = c->h_ctl[0];
+    if (vxmax) *vxmax = c->h_ctl[2];
+    if (vymax) *vymax = c->h_ctl[3];
+    return 0;
+}
+
+// ------------------------------------------------------------------ one RK4 step
+struct ProfScope {
+    weno5_ctx *c; size_t idx; bool on;
+    ProfScope(weno5_ctx *c_) : c(c_), idx(0), on(c_->profiling)
+    {
+        if (!on) return;
+        if (c->ev_used == c->ev.size()) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a); cudaEventCreate(&b);
+            c->ev.emplace_back(a, b);
+        }
+        idx = c->ev_used++;
+        cudaEventRecord(c->ev[idx].first, c->stream);
+    }
+    ~ProfScope() { if (on) cudaEventRecord(c->ev[idx].second, c->stream); }
+};
+
+static int enqueue_stage(weno5_ctx *c, int stage, State &cur, State &nxt)
+{
+    static const double ck[4] = {0.5, 0.5, 1.0, 1.0 / 6.0};
+    const weno5_params &P = c->P;
+    const Geom &g = c->g;
+    const double *dtp = c->ctl;
+    // the six flux-advanced cell fields
+    static const int six[6] = {C_RHO, C_MX, C_MY, C_MZ, C_BZ, C_E};
+
+    FluxArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int k = 0; k < 8; ++k) a.qc[k] = cur.q[k];
+    for (int k = 0; k < 7; ++k) a.rhs[k] = c->rhs[k];
+    a.dtp = dtp;
+    a.c_dx = ck[stage - 1] / P.dx;
+    a.c_dy = g.is1d ? 0.0 : ck[stage - 1] / P.dy;
+    a.stage = stage;
+    a.gam = P.gamma; a.eps = P.eps;
+    a.is1d = g.is1d;
+    a.pitch = g.pitch;
+
+    // x sweep
+    a.N = g.NXI; a.NP = g.NYI; a.bs = c->fsy;
+    a.seg_len = c->segx_len; a.nseg = c->nsegx;
+    { ProfScope ps(c); launch_flux_x(a, c->stream); }
+    c->launches++; c->prof_launches += c->profiling;
+
+    if (g.is1d) {
+        double *qn7[7]; const double *base7[7]; double *acc7[7];
+        static const int seven[7] = {C_RHO, C_MX, C_MY, C_MZ, C_BZ, C_E, C_BY};
+        for (int k = 0; k < 7; ++k) {
+            qn7[k] = nxt.q[seven[k]];
+            base7[k] = c->Q0.q[seven[k]];
+            acc7[k] = k < 6 ? c->acc[k] : c->acc_by1d;
+        }
+        launch_update_1d(a, qn7, base7, acc7, c->stream);
+        c->launches++;
+        // Bx is constant in 1-D (Weno5_1D.jl:771)
+        if (nxt.q[C_BX] != c->Q0.q[C_BX])
+            CU(cudaMemcpyAsync(nxt.q[C_BX], c->Q0.q[C_BX], g.plane * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        // 1-D keeps E (Weno5_1D.jl:252-254); S = E2S(q) is only read by the next timestep
+        if (stage == 4) { launch_entropy(nxt.q, g, P.gamma, 0, 0, dtp, c->stream); c->launches++; }
+        launch_bc_fill(nxt.q, stage == 4 ? NCELL : 8, g, c->side, dtp, c->stream);
+        c->launches++;
+        CU(cudaGetLastError());
+        return 0;
+    }
+
+    // y sweep + RK update
+    a.N = g.NYI; a.NP = g.NXI; a.bs = c->gsx;
+    a.seg_len = c->segy_len; a.nseg = c->nsegy;
+    for (int k = 0; k < 6; ++k) { a.base[k] = c->Q0.q[six[k]]; a.acc[k] = c->acc[k]; a.qn[k] = nxt.q[six[k]]; }
+    { ProfScope ps(c); launch_flux_y(a, c->stream); }
+    c->launches++; c->prof_launches += c->profiling;
+
+    // constrained transport
+    CtArgs t;
+    memset(&t, 0, sizeof(t));
+    t.fsy = c->fsy; t.gsx = c->gsx;
+    t.bx0 = c->Q0.bx; t.by0 = c->Q0.by; t.bxc = cur.bx; t.byc = cur.by;
+    t.accbx = c->accbx; t.accby = c->accby; t.bxn = nxt.bx; t.byn = nxt.by;
+    t.dtp = dtp; t.c_dx = a.c_dx; t.c_dy = a.c_dy; t.stage = stage;
+    t.Nx = g.Nx; t.Ny = g.Ny; t.pitch = g.pitch;
+    t.oxlo = c->side[0] == SIDE_OUTFLOW; t.oxhi = c->side[1] == SIDE_OUTFLOW;
+    t.oylo = c->side[2] == SIDE_OUTFLOW; t.oyhi = c->side[3] == SIDE_OUTFLOW;
+    // outflow sides follow the reference's full-array update; elsewhere only faces whose corner
+    // EMFs have complete stencils are written (they are what the 4th-order centring needs)
+    t.bx_i0 = t.oxlo ? 1 : 2; t.bx_i1 = t.oxhi ? g.Nx : g.Nx - 2;
+    t.bx_j0 = t.oylo ? 1 : 3; t.bx_j1 = t.oyhi ? g.Ny : g.Ny - 2;
+    t.by_i0 = t.oxlo ? 1 : 3; t.by_i1 = t.oxhi ? g.Nx : g.Nx - 2;
+    t.by_j0 = t.oylo ? 1 : 2; t.by_j1 = t.oyhi ? g.Ny : g.Ny - 2;
+    launch_ct_faces(t, c->stream);
+    launch_ct_centers(nxt.bx, nxt.by, nxt.q[C_BX], nxt.q[C_BY], g, dtp, c->stream);
+    c->launches += 2;
+    if (stage == 4) {                                   // boundaries!(q4, bxb4, byb4), Weno5_2D.jl:313
+        launch_face_bc(nxt.bx, nxt.by, g, c->side, dtp, c->stream);
+        c->launches++;
+    }
+    const bool ent = P.es_roundtrip || stage == 4;
+    if (ent) { launch_entropy(nxt.q, g, P.gamma, P.es_roundtrip, 0, dtp, c->stream); c->launches++; }
+    const int nfill = ent ? NCELL : 8;
+    launch_bc_fill(nxt.q, nfill, g, c->side, dtp, c->stream);
+    c->launches++;
+    if (c->comm) { if (int r = exchange_rows(c, nxt.q, nfill)) return r; }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+static int enqueue_step(weno5_ctx *c)
+{
+    if (int r = enqueue_stage(c, 1, c->Q0, c->QA)) return r;
+    if (int r = enqueue_stage(c, 2, c->QA, c->QB)) return r;
+    if (int r = enqueue_stage(c, 3, c->QB, c->QA)) return r;
+    if (int r = enqueue_stage(c, 4, c->QA, c->Q0)) return r;
+    return 0;
+}
+
+extern "C" int weno5_rk4_step(weno5_ctx *c, double dt)
+{
+    if (!c) return fail(WENO5_ERR_ARG, "null argument");
+    if (!c->uploaded) return fail(WENO5_ERR_STATE, "no state on the device yet");
+    if (!(dt > 0.0) || !std::isfinite(dt)) return fail(WENO5_ERR_ARG, "dt must be positive and finite (got %g)", dt);
+    CU(cudaSetDevice(c->device));
+    c->h_ctl[8] = dt;
+    CU(cudaMemcpyAsync(c->ctl, c->h_ctl + 8, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (int r = enqueue_step(c)) return r;
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int weno5_advance(weno5_ctx *c, int nsteps, double tmax, double *t, int *nsteps_done)
+{
+    if (!c) return fail(WENO5_ERR_ARG, "null argument");
+    if (!c->uploaded) return fail(WENO5_ERR_STATE, "no state on the device yet");
+    if (nsteps < 0) return fail(WENO5_ERR_ARG, "nsteps < 0");
+    CU(cudaSetDevice(c->device));
+    double *h = c->h_ctl + 8;
+    h[0] = 0.0; h[1] = t ? *t : 0.0; h[2] = 0.0; h[3] = 0.0; h[4] = tmax > 0.0 ? tmax : 0.0; h[5] = 0.0; h[6] = 0.0;
+    CU(cudaMemcpyAsync(c->ctl, h, 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    for (int s = 0; s < nsteps; ++s) {
+        if (int r = enqueue_timestep(c)) return r;
+        if (int r = enqueue_step(c)) return r;
+        launch_advance_time(c->ctl, c->stream);
+        c->launches++;
+        if (tmax > 0.0 && (s % 16) == 15) {               // look at the clock now and then
+            CU(cudaMemcpyAsync(c->h_ctl, c->ctl, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            if (c->h_ctl[1] >= tmax || c->h_ctl[6] != 0.0) break;
+        }
+    }
+    CU(cudaMemcpyAsync(c->h_ctl, c->ctl, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    if (t) *t = c->h_ctl[1];
+    if (nsteps_done) *nsteps_done = (int)c->h_ctl[5];
+    if (c->h_ctl[6] != 0.0) return fail(WENO5_ERR_NUMERIC, "non-finite wave speed / time step at t=%g", c->h_ctl[1]);
+    return 0;
+}
+
+// ------------------------------------------------------------------ diagnostics
+extern "C" int weno5_divb(weno5_ctx *c, double *divb)
+{
+    if (!c || !divb) return fail(WENO5_ERR_ARG, "null argument");
+    if (c->g.is1d) return fail(WENO5_ERR_ARG, "divB is a 2-D diagnostic");
+    if (!c->uploaded) return fail(WENO5_ERR_STATE, "no state on the device yet");
+    CU(cudaSetDevice(c->device));
+    launch_divb(c->Q0.bx, c->Q0.by, c->scratch, c->g, c->P.dx, c->P.dy, c->stream);
+    c->launches++;
+    if (int r = copy_plane(c, c->scratch, nullptr, divb)) return r;
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int weno5_totals(weno5_ctx *c, double sums[11])
+{
+    if (!c || !sums) return fail(WENO5_ERR_ARG, "null argument");
+    if (!c->uploaded) return fail(WENO5_ERR_STATE, "no state on the device yet");
+    CU(cudaSetDevice(c->device));
+    const double *pl[11];
+    for (int k = 0; k < NCELL; ++k) pl[k] = c->Q0.q[k];
+    pl[9] = c->Q0.bx; pl[10] = c->Q0.by;
+    launch_totals(pl, c->g.is1d ? 9 : 11, c->g, c->sums, c->stream);
+    c->launches++;
+    CU(cudaMemcpyAsync(c->h_ctl, c->sums, 11 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 11; ++k) sums[k] = (c->g.is1d && k >= 9) ? 0.0 : c->h_ctl[k];
+    return 0;
+}
+
+// ------------------------------------------------------------------ reference-shaped one-shot calls
+extern "C" int weno5_step_host(weno5_ctx *c, const double *q0, const double *bxb0, const double *byb0, double dt,
+                               double *q4, double *bxb4, double *byb4)
+{
+    if (!c || !q0 || !q4) return fail(WENO5_ERR_ARG, "null argument");
+    if (c->g.is1d) {
+        if (int r = weno5_upload_1d(c, q0)) return r;
+        if (int r = weno5_rk4_step(c, dt)) return r;
+        return weno5_download_1d(c, q4);
+    }
+    if (int r = weno5_upload(c, q0, bxb0, byb0)) return r;
+    if (int r = weno5_rk4_step(c, dt)) return r;
+    return weno5_download(c, q4, bxb4, byb4);
+}
+
+extern "C" int weno5_classical_rk4_step_2d(const weno5_params *P, const double *q0, const double *bxb0,
+                                           const double *byb0, double dt, double *q4, double *bxb4, double *byb4)
+{
+    if (!P) return fail(WENO5_ERR_ARG, "null argument");
+    if (P->ny == 1) return fail(WENO5_ERR_ARG, "use weno5_classical_rk4_step_1d for ny = 1");
+    weno5_ctx *c = nullptr;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (int r = weno5_create(P, dev, P->ny, 0, &c)) return r;
+    const int r = weno5_step_host(c, q0, bxb0, byb0, dt, q4, bxb4, byb4);
+    weno5_destroy(c);
+    return r;
+}
+
+extern "C" int weno5_classical_rk4_step_1d(const weno5_params *P, const double *q0, double dt, double *q4)
+{
+    if (!P) return fail(WENO5_ERR_ARG, "null argument");
+    weno5_params P1 = *P;
+    P1.ny = 1;
+    weno5_ctx *c = nullptr;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (int r = weno5_create(&P1, dev, 1, 0, &c)) return r;
+    const int r = weno5_step_host(c, q0, nullptr, nullptr, dt, q4, nullptr, nullptr);
+    weno5_destroy(c);
+    return r;
+}
+
+// ------------------------------------------------------------------ host memory, instrumentation
+extern "C" int weno5_host_alloc(void **ptr, unsigned long long bytes)
+{
+    if (!ptr) return fail(WENO5_ERR_ARG, "null argument");
+    CU(cudaMallocHost(ptr, bytes));
+    return 0;
+}
+
+extern "C" int weno5_host_free(void *ptr)
+{
+    CU(cudaFreeHost(ptr));
+    return 0;
+}
+
+extern "C" unsigned long long weno5_launch_count(const weno5_ctx *c) { return c ? c->launches : 0; }
+
+extern "C" int weno5_profile(weno5_ctx *c, int enable)
+{
+    if (!c) return fail(WENO5_ERR_ARG, "null argument");
+    c->profiling = enable != 0;
+    return 0;
+}
+
+extern "C" int weno5_profile_read(weno5_ctx *c, double *flux_ms, unsigned long long *flux_launches, int reset)
+{
+    if (!c) return fail(WENO5_ERR_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    for (size_t k = 0; k < c->ev_used; ++k) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, c->ev[k].first, c->ev[k].second));
+        c->prof_ms += ms;
+    }
+    c->ev_used = 0;
+    if (flux_ms) *flux_ms = c->prof_ms;
+    if (flux_launches) *flux_launches = c->prof_launches;
+    if (reset) { c->prof_ms = 0.0; c->prof_launches = 0; }
+    return 0;
+}
+
+extern "C" void *weno5_stream(weno5_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+extern "C" int weno5_debug_fetch(weno5_ctx *c, const char *name, double *out)
+{
+    if (!c || !name || !out) return fail(WENO5_ERR_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    const std::string n(name);
+    double *src = nullptr;
+    if (n == "fsy") src = c->fsy;
+    else if (n == "gsx") src = c->gsx;
+    else if (n.rfind("rhs", 0) == 0 && n.size() == 4 && n[3] >= '0' && n[3] <= '6') src = c->rhs[n[3] - '0'];
+    else if (n.rfind("qa", 0) == 0 && n.size() == 3 && n[2] >= '0' && n[2] <= '8') { int hk = n[2] - '0'; src = c->QA.q[hk == 7 ? C_S : (hk == 8 ? C_E : hk)]; }
+    else if (n.rfind("qb", 0) == 0 && n.size() == 3 && n[2] >= '0' && n[2] <= '8') { int hk = n[2] - '0'; src = c->QB.q[hk == 7 ? C_S : (hk == 8 ? C_E : hk)]; }
+    else if (n == "qa_bx") src = c->QA.bx;
+    else if (n == "qa_by") src = c->QA.by;
+    else return fail(WENO5_ERR_ARG, "unknown field '%s'", name);
+    if (int r = copy_plane(c, src, nullptr, out)) return r;
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}

@@ -1,0 +1,669 @@
+// Hand-written sm_100a kernels of libweno5mhd.
+//
+// flux_kernel<DIR>  the fused per-face kernel: cons->prim, wave speeds, physical flux (cell
+//                   phase, once per cell, kept in shared memory), then per face the structured
+//                   characteristic projection, WENO5 and back-projection (weno5_math.cuh),
+//                   then the flux difference.  DIR 0 sweeps x and writes d fhat + fsy;
+//                   DIR 1 sweeps y IN PLACE (threads stay along x, stencil along j -- no
+//                   transposed copy like the reference's rotate_state, Weno5_2D.jl:1897-1927)
+//                   and is fused with the RK stage update of the six flux-advanced fields.
+//                   A CTA marches along the sweep direction; cell data of the 5 overlapping
+//                   stencil cells is carried in shared memory, so nothing is recomputed.
+// ct_faces/ct_centers  corner EMF, face-field RK update, 4th-order face->centre interpolation
+//                   (Weno5_2D.jl:319-356 and the bxb/byb lines of :125-317).
+// bc_fill/face_bc   boundaries! (Weno5_2D.jl:1684-1732) + periodic addition.
+// entropy/vmax/dt   E2S/S2E (:1770-1793), compute_global_vmax/timestep (:1930-1984).
+#include "weno5_kernels.cuh"
+#include "weno5_math.cuh"
+
+namespace w5 {
+
+constexpr int NTHREADS = 256;
+
+template <int DIR> struct Tile;
+template <> struct Tile<0> { static constexpr int NS = 64, NPB = 4; };   // 4 rows x 64 faces
+template <> struct Tile<1> { static constexpr int NS = 8, NPB = 32; };   // 8 face rows x 32 columns
+
+template <int DIR> __device__ __forceinline__ int cbi(int slot, int p)
+{
+    return DIR == 0 ? p * (Tile<DIR>::NS + 5) + slot : slot * Tile<DIR>::NPB + p;
+}
+template <int DIR> __device__ __forceinline__ int fbi(int slot, int p)
+{
+    return DIR == 0 ? p * (Tile<DIR>::NS + 1) + slot : slot * Tile<DIR>::NPB + p;
+}
+
+template <int DIR> __host__ __device__ constexpr int cb_size() { return (Tile<DIR>::NS + 5) * Tile<DIR>::NPB; }
+template <int DIR> __host__ __device__ constexpr int fb_size() { return (Tile<DIR>::NS + 1) * Tile<DIR>::NPB; }
+
+int flux_smem_bytes(int dir)
+{
+    return dir == 0 ? (CQ_COUNT * cb_size<0>() + 7 * fb_size<0>()) * (int)sizeof(double)
+                    : (CQ_COUNT * cb_size<1>() + 7 * fb_size<1>()) * (int)sizeof(double);
+}
+
+// cons->prim, eigenvalues, flux of one cell -> shared memory slot
+template <int DIR>
+__device__ __forceinline__ void cell_phase(const FluxArgs &a, double *cb, int c, int line, int slot, int p)
+{
+    constexpr int CBS = cb_size<DIR>();
+    // sweep-frame component c reads physical plane in[c]: (x,y,z) -> (y,z,x) for the y sweep
+    constexpr int in[8] = {0, DIR ? 2 : 1, DIR ? 3 : 2, DIR ? 1 : 3, DIR ? 5 : 4, DIR ? 6 : 5, DIR ? 4 : 6, 7};
+    const int cc = min(c, a.N - 1), ll = min(line, a.NP - 1);
+    const size_t g = DIR == 0 ? (size_t)cc + (size_t)a.pitch * ll : (size_t)ll + (size_t)a.pitch * cc;
+    double q[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) q[k] = __ldg(a.qc[in[k]] + g);
+    CellOut o;
+    cell_quantities(q, a.gam, o);
+    const int i = cbi<DIR>(slot, p);
+#pragma unroll
+    for (int m = 0; m < 7; ++m) cb[(CQ_F0 + m) * CBS + i] = o.F[m];
+    cb[(CQ_Q0 + 0) * CBS + i] = q[0];
+    cb[(CQ_Q0 + 1) * CBS + i] = q[1];
+    cb[(CQ_Q0 + 2) * CBS + i] = q[2];
+    cb[(CQ_Q0 + 3) * CBS + i] = q[3];
+    cb[(CQ_Q0 + 4) * CBS + i] = q[5];
+    cb[(CQ_Q0 + 5) * CBS + i] = q[6];
+    cb[(CQ_Q0 + 6) * CBS + i] = q[7];
+    cb[CQ_V1 * CBS + i] = o.v1;
+    cb[CQ_V2 * CBS + i] = o.v2;
+    cb[CQ_V3 * CBS + i] = o.v3;
+    cb[CQ_B1 * CBS + i] = q[4];
+    cb[CQ_LF * CBS + i] = o.lf;
+    cb[CQ_LA * CBS + i] = o.la;
+    cb[CQ_LS * CBS + i] = o.ls;
+}
+
+template <int DIR>
+__global__ void __launch_bounds__(NTHREADS, 1) flux_kernel(const FluxArgs a)
+{
+    constexpr int NS = Tile<DIR>::NS, NPB = Tile<DIR>::NPB;
+    constexpr int CBS = cb_size<DIR>(), FBS = fb_size<DIR>();
+    extern __shared__ double sm[];
+    double *cb = sm;
+    double *fb = sm + CQ_COUNT * CBS;
+
+    const double dt = *a.dtp;
+    if (dt == 0.0) return;                       // advance() past tmax: leave the state untouched
+
+    const int t = threadIdx.x;
+    const int s = DIR == 0 ? (t % NS) : (t / NPB);
+    const int p = DIR == 0 ? (t / NS) : (t % NPB);
+    const int line = blockIdx.x * NPB + p;
+    const int seg = blockIdx.y;
+
+    // this CTA owns faces [fA, fB) of its lines; it starts one face early (seg > 0) so that the
+    // first owned cell has both of its faces
+    const int fA = 2 + seg * a.seg_len;
+    const int fB = min(fA + a.seg_len, a.N - 2);
+    const int fStart = seg == 0 ? fA : fA - 1;
+
+    if (s < 5) cell_phase<DIR>(a, cb, fStart - 2 + s, line, s, p);
+
+    for (int s0 = fStart; s0 < fB; s0 += NS) {
+        cell_phase<DIR>(a, cb, s0 + 3 + s, line, 5 + s, p);
+        __syncthreads();
+
+        // ---------------- face phase: face f between cells f and f+1 (slots s+2, s+3)
+        const int f = s0 + s;
+        if (f < fB) {
+            const int iL = cbi<DIR>(s + 2, p), iR = cbi<DIR>(s + 3, p);
+            FaceCoef fc;
+            face_coefficients(cb[CQ_Q0 * CBS + iL], cb[CQ_Q0 * CBS + iR], cb[CQ_V1 * CBS + iL], cb[CQ_V1 * CBS + iR],
+                              cb[CQ_V2 * CBS + iL], cb[CQ_V2 * CBS + iR], cb[CQ_V3 * CBS + iL], cb[CQ_V3 * CBS + iR],
+                              cb[CQ_B1 * CBS + iL], cb[CQ_B1 * CBS + iR], cb[(CQ_Q0 + 4) * CBS + iL],
+                              cb[(CQ_Q0 + 4) * CBS + iR], cb[(CQ_Q0 + 5) * CBS + iL], cb[(CQ_Q0 + 5) * CBS + iR],
+                              cb[(CQ_Q0 + 6) * CBS + iL], cb[(CQ_Q0 + 6) * CBS + iR], a.gam, fc);
+            double amax[7];
+            face_amax(cb[CQ_V1 * CBS + iL], cb[CQ_LF * CBS + iL], cb[CQ_LA * CBS + iL], cb[CQ_LS * CBS + iL],
+                      cb[CQ_V1 * CBS + iR], cb[CQ_LF * CBS + iR], cb[CQ_LA * CBS + iR], cb[CQ_LS * CBS + iR], amax);
+            auto load = [&](int k, double F[7], double x[7]) {
+                const int ii = cbi<DIR>(s + k, p);
+#pragma unroll
+                for (int m = 0; m < 7; ++m) {
+                    F[m] = cb[(CQ_F0 + m) * CBS + ii];
+                    x[m] = cb[(CQ_Q0 + m) * CBS + ii];
+                }
+            };
+            double fh[7];
+            face_flux(fc, amax, a.eps, load, fh);
+            const int io = fbi<DIR>(s + 1, p);
+#pragma unroll
+            for (int m = 0; m < 7; ++m) fb[m * FBS + io] = fh[m];
+            // CT seed flux, Weno5_2D.jl:1005-1008: x sweep -> fsy (tangential comp 2),
+            // y sweep -> gsx (tangential comp 3 of the rotated frame)
+            if (!a.is1d && line < a.NP && (seg == 0 || f >= fA)) {
+                constexpr int TV = DIR == 0 ? CQ_V2 : CQ_V3;
+                const double bv = cb[CQ_B1 * CBS + iL] * cb[TV * CBS + iL] + cb[CQ_B1 * CBS + iR] * cb[TV * CBS + iR];
+                const size_t g = DIR == 0 ? (size_t)f + (size_t)a.pitch * line : (size_t)line + (size_t)a.pitch * f;
+                a.bs[g] = fma(0.5, bv, fh[DIR == 0 ? 4 : 5]);
+            }
+        }
+        __syncthreads();
+
+        // ---------------- update phase: cell c with faces c-1 (slot s) and c (slot s+1)
+        {
+            const int c = s0 + s;
+            const bool line_ok = a.is1d ? (line == 0) : (line >= G && line < a.NP - G);
+            if (c > fStart && c < fB && c >= G && c < a.N - G && line_ok) {
+                const int i0 = fbi<DIR>(s, p), i1 = fbi<DIR>(s + 1, p);
+                const size_t g = DIR == 0 ? (size_t)c + (size_t)a.pitch * line : (size_t)line + (size_t)a.pitch * c;
+                if constexpr (DIR == 0) {
+                    constexpr int fi[6] = {0, 1, 2, 3, 5, 6};      // rho,Mx,My,Mz,Bz,E in fhat
+#pragma unroll
+                    for (int m = 0; m < 6; ++m) a.rhs[m][g] = fb[fi[m] * FBS + i1] - fb[fi[m] * FBS + i0];
+                    if (a.is1d) a.rhs[6][g] = fb[4 * FBS + i1] - fb[4 * FBS + i0];   // By
+                } else {
+                    // rotated frame (rho,My,Mz,Mx,Bz,Bx,E): physical rho,Mx,My,Mz,Bz,E
+                    constexpr int fi[6] = {0, 3, 1, 2, 4, 6};
+                    const int ic = cbi<DIR>(s + 2, p);
+                    const double cx = a.c_dx * dt, cy = a.c_dy * dt;
+#pragma unroll
+                    for (int m = 0; m < 6; ++m) {
+                        const double dfy = fb[fi[m] * FBS + i1] - fb[fi[m] * FBS + i0];
+                        const double qcen = cb[(CQ_Q0 + fi[m]) * CBS + ic];
+                        double b;
+                        if (a.stage <= 3) {
+                            b = a.base[m][g];
+                            if (a.stage == 2) a.acc[m][g] = qcen - b;                       // -q0 + q1
+                            if (a.stage == 3) a.acc[m][g] = fma(2.0, qcen, a.acc[m][g]);    // + 2 q2
+                        } else {
+                            b = (a.acc[m][g] + qcen) * (1.0 / 3.0);                         // Weno5_2D.jl:279
+                        }
+                        a.qn[m][g] = fma(-cx, a.rhs[m][g], fma(-cy, dfy, b));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---------------- carry the 5 trailing cells and the last face to the front
+        for (int e = t; e < 5 * NPB * CQ_COUNT; e += NTHREADS) {
+            const int qn_ = e / (5 * NPB), rem = e % (5 * NPB);
+            const int sl = DIR == 0 ? rem % 5 : rem / NPB;
+            const int pp = DIR == 0 ? rem / 5 : rem % NPB;
+            cb[qn_ * CBS + cbi<DIR>(sl, pp)] = cb[qn_ * CBS + cbi<DIR>(NS + sl, pp)];
+        }
+        for (int e = t; e < 7 * NPB; e += NTHREADS) {
+            const int m = e / NPB, pp = e % NPB;
+            fb[m * FBS + fbi<DIR>(0, pp)] = fb[m * FBS + fbi<DIR>(NS, pp)];
+        }
+        __syncthreads();
+    }
+}
+
+static void flux_grid(const FluxArgs &a, int NS, int NPB, dim3 &grid)
+{
+    grid = dim3((a.NP + NPB - 1) / NPB, a.nseg, 1);
+    (void)NS;
+}
+
+void launch_flux_x(const FluxArgs &a, cudaStream_t s)
+{
+    static bool once = false;
+    const int smem = flux_smem_bytes(0);
+    if (!once) { cudaFuncSetAttribute(flux_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); once = true; }
+    dim3 grid;
+    flux_grid(a, Tile<0>::NS, Tile<0>::NPB, grid);
+    flux_kernel<0><<<grid, NTHREADS, smem, s>>>(a);
+}
+
+void launch_flux_y(const FluxArgs &a, cudaStream_t s)
+{
+    static bool once = false;
+    const int smem = flux_smem_bytes(1);
+    if (!once) { cudaFuncSetAttribute(flux_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); once = true; }
+    dim3 grid;
+    flux_grid(a, Tile<1>::NS, Tile<1>::NPB, grid);
+    flux_kernel<1><<<grid, NTHREADS, smem, s>>>(a);
+}
+
+// ------------------------------------------------------------------ 1-D stage update
+// Weno5_1D.jl:152-205: q_{k+1} = base - c dt/dx Q for the 7 flux-advanced components
+// (Bx constant).  order of the 7: rho,Mx,My,Mz,Bz,E,By
+struct Upd1dArgs {
+    const double *rhs[7]; const double *qc[7]; const double *base[7]; double *acc[7]; double *qn[7];
+    const double *dtp; double c_dx; int stage; int N;
+};
+
+__global__ void update_1d_kernel(const Upd1dArgs a)
+{
+    const double dt = *a.dtp;
+    if (dt == 0.0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < G || i >= a.N - G) return;
+    const double cx = a.c_dx * dt;
+#pragma unroll
+    for (int m = 0; m < 7; ++m) {
+        const double qcen = a.qc[m][i];
+        double b;
+        if (a.stage <= 3) {
+            b = a.base[m][i];
+            if (a.stage == 2) a.acc[m][i] = qcen - b;
+            if (a.stage == 3) a.acc[m][i] = fma(2.0, qcen, a.acc[m][i]);
+        } else {
+            b = (a.acc[m][i] + qcen) * (1.0 / 3.0);
+        }
+        a.qn[m][i] = fma(-cx, a.rhs[m][i], b);
+    }
+}
+
+void launch_update_1d(const FluxArgs &a, double *const qn7[7], const double *const base7[7],
+                      double *const acc7[7], cudaStream_t s)
+{
+    Upd1dArgs u;
+    // current-state planes in the order rho,Mx,My,Mz,Bz,E,By
+    const int cur[7] = {C_RHO, C_MX, C_MY, C_MZ, C_BZ, C_E, C_BY};
+    for (int m = 0; m < 7; ++m) {
+        u.rhs[m] = a.rhs[m]; u.qc[m] = a.qc[cur[m]]; u.base[m] = base7[m]; u.acc[m] = acc7[m]; u.qn[m] = qn7[m];
+    }
+    u.dtp = a.dtp; u.c_dx = a.c_dx; u.stage = a.stage; u.N = a.N;
+    update_1d_kernel<<<(a.N + 255) / 256, 256, 0, s>>>(u);
+}
+
+// ------------------------------------------------------------------ constrained transport
+// flux arrays with the reference's boundary rules applied on outflow sides
+// (Weno5_2D.jl:1704-1729): rows/cols 1,2 := 3; Nx-1,Nx := Nx-2; then the rim := 0
+__device__ __forceinline__ double ld_flux(const double *f, int i, int j, const CtArgs &a)
+{
+    if ((a.oxlo && i <= 1) || (a.oxhi && i >= a.Nx) || (a.oylo && j <= 1) || (a.oyhi && j >= a.Ny)) return 0.0;
+    if (a.oxlo) i = max(i, 3);
+    if (a.oxhi) i = min(i, a.Nx - 2);
+    if (a.oylo) j = max(j, 3);
+    if (a.oyhi) j = min(j, a.Ny - 2);
+    return f[(size_t)i + (size_t)a.pitch * j];
+}
+
+__device__ __forceinline__ bool ct_outside(int i, int j, const CtArgs &a)
+{
+    return (a.oxlo && i < 2) || (a.oxhi && i > a.Nx - 1) || (a.oylo && j < 2) || (a.oyhi && j > a.Ny - 1);
+}
+
+// corner EMF, Weno5_2D.jl:328-332 (zero outside 2..N-1 on outflow sides)
+__device__ __forceinline__ double corner(int i, int j, const CtArgs &a)
+{
+    if (ct_outside(i, j, a)) return 0.0;
+    return 0.5 * (ld_flux(a.gsx, i, j, a) + ld_flux(a.gsx, i + 1, j, a) - ld_flux(a.fsy, i, j, a) -
+                  ld_flux(a.fsy, i, j + 1, a));
+}
+
+__global__ void ct_faces_kernel(const CtArgs a)
+{
+    const double dt = *a.dtp;
+    if (dt == 0.0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+    if (i > a.Nx || j > a.Ny) return;
+    const bool wbx = i >= a.bx_i0 && i <= a.bx_i1 && j >= a.bx_j0 && j <= a.bx_j1;
+    const bool wby = i >= a.by_i0 && i <= a.by_i1 && j >= a.by_j0 && j <= a.by_j1;
+    if (!wbx && !wby) return;
+    const size_t g = (size_t)i + (size_t)a.pitch * j;
+    const double cy = a.c_dy * dt, cx = a.c_dx * dt;
+    const double o = corner(i, j, a);
+    // Oxi/Oxj are only filled on 2..N-1 (Weno5_2D.jl:334-339)
+    const bool inner = !ct_outside(i, j, a);
+    if (wbx) {
+        const double oj = inner ? corner(i, j - 1, a) : 0.0;
+        const double cur = a.bxc[g];
+        double b;
+        if (a.stage <= 3) {
+            b = a.bx0[g];
+            if (a.stage == 2) a.accbx[g] = cur - b;
+            if (a.stage == 3) a.accbx[g] = fma(2.0, cur, a.accbx[g]);
+        } else {
+            b = (a.accbx[g] + cur) * (1.0 / 3.0);
+        }
+        a.bxn[g] = b - cy * (o - oj);                       // Weno5_2D.jl:150
+    }
+    if (wby) {
+        const double oi = inner ? corner(i - 1, j, a) : 0.0;
+        const double cur = a.byc[g];
+        double b;
+        if (a.stage <= 3) {
+            b = a.by0[g];
+            if (a.stage == 2) a.accby[g] = cur - b;
+            if (a.stage == 3) a.accby[g] = fma(2.0, cur, a.accby[g]);
+        } else {
+            b = (a.accby[g] + cur) * (1.0 / 3.0);
+        }
+        a.byn[g] = b - cx * (oi - o);                       // Weno5_2D.jl:151
+    }
+}
+
+void launch_ct_faces(const CtArgs &a, cudaStream_t s)
+{
+    dim3 block(64, 4), grid((a.Nx + 63) / 64, (a.Ny + 3) / 4);
+    ct_faces_kernel<<<grid, block, 0, s>>>(a);
+}
+
+// interpolateB_face2center, Weno5_2D.jl:344-356, interior cells (ghosts come from bc_fill)
+__global__ void ct_centers_kernel(const double *__restrict__ bxn, const double *__restrict__ byn,
+                                  double *__restrict__ Bx, double *__restrict__ By, int NXI, int NYI, int pitch,
+                                  const double *dtp)
+{
+    if (*dtp == 0.0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + G;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y + G;
+    if (i >= NXI - G || j >= NYI - G) return;
+    const size_t g = (size_t)i + (size_t)pitch * j;
+    Bx[g] = (-bxn[g - 2] + 9.0 * bxn[g - 1] + 9.0 * bxn[g] - bxn[g + 1]) / 16.0;
+    By[g] = (-byn[g - 2 * (size_t)pitch] + 9.0 * byn[g - pitch] + 9.0 * byn[g] - byn[g + pitch]) / 16.0;
+}
+
+void launch_ct_centers(const double *bxn, const double *byn, double *Bx, double *By, const Geom &g,
+                       const double *dtp, cudaStream_t s)
+{
+    dim3 block(64, 4), grid((g.NXI - 2 * G + 63) / 64, (g.NYI - 2 * G + 3) / 4);
+    ct_centers_kernel<<<grid, block, 0, s>>>(bxn, byn, Bx, By, g.NXI, g.NYI, g.pitch, dtp);
+}
+
+// boundaries! applied to the face fields themselves (Weno5_2D.jl:313 and :39), in place:
+// targets lie outside the source range so there is no read-after-write hazard.
+__global__ void face_bc_kernel(double *bx, double *by, int Nx, int Ny, int pitch, int sxlo, int sxhi, int sylo,
+                               int syhi, const double *dtp)
+{
+    if (dtp && *dtp == 0.0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+    if (i > Nx || j > Ny) return;
+    const int nx = Nx - 2 * 3, ny = Ny - 2 * 3;
+    // new(i,j) = 0 on the outflow rim, else old(map(i), map(j)); map clamps to 3..N-2 (outflow) or
+    // wraps by the interior size (periodic); mapped indices are fixed points of the map
+    int si = i, sj = j;
+    bool zero = false;
+    if (i <= 3) {
+        if (sxlo == SIDE_OUTFLOW) { si = 3; zero |= i == 1; }
+        else if (sxlo == SIDE_PERIODIC) si = i + nx;
+    } else if (i >= Nx - 2) {
+        if (sxhi == SIDE_OUTFLOW) { si = Nx - 2; zero |= i == Nx; }
+        else if (sxhi == SIDE_PERIODIC) si = i - nx;
+    }
+    if (j <= 3) {
+        if (sylo == SIDE_OUTFLOW) { sj = 3; zero |= j == 1; }
+        else if (sylo == SIDE_PERIODIC) sj = j + ny;
+    } else if (j >= Ny - 2) {
+        if (syhi == SIDE_OUTFLOW) { sj = Ny - 2; zero |= j == Ny; }
+        else if (syhi == SIDE_PERIODIC) sj = j - ny;
+    }
+    if (si == i && sj == j && !zero) return;
+    const size_t g = (size_t)i + (size_t)pitch * j, sg = (size_t)si + (size_t)pitch * sj;
+    bx[g] = zero ? 0.0 : bx[sg];
+    by[g] = zero ? 0.0 : by[sg];
+}
+
+void launch_face_bc(double *bx, double *by, const Geom &g, const int side[4], const double *dtp, cudaStream_t s)
+{
+    dim3 block(64, 4), grid((g.Nx + 63) / 64, (g.Ny + 3) / 4);
+    face_bc_kernel<<<grid, block, 0, s>>>(bx, by, g.Nx, g.Ny, g.pitch, side[0], side[1], side[2], side[3], dtp);
+}
+
+// ------------------------------------------------------------------ ghost fill of cell fields
+struct BcArgs { double *pl[NCELL]; int n; int NXI, NYI, pitch; int sxlo, sxhi, sylo, syhi; const double *dtp; };
+
+__device__ __forceinline__ int bc_map(int i, int N, int lo, int hi, bool &skip)
+{
+    const int n = N - 2 * G;
+    if (i < G) {
+        if (lo == SIDE_OUTFLOW) return G;
+        if (lo == SIDE_PERIODIC) return i + n;
+        skip = true; return i;
+    }
+    if (i >= N - G) {
+        if (hi == SIDE_OUTFLOW) return N - G - 1;
+        if (hi == SIDE_PERIODIC) return i - n;
+        skip = true; return i;
+    }
+    return i;
+}
+
+// every ghost cell copies the interior cell its (x-fill then y-fill) chain ends at
+// (Weno5_2D.jl:1686-1702); ghost rows of slab-internal sides are left to the exchange.
+__global__ void bc_fill_kernel(const BcArgs a)
+{
+    if (a.dtp && *a.dtp == 0.0) return;
+    const int nyg = a.NYI > 1 ? 2 * G : 0;
+    const long nrowcells = (long)nyg * a.NXI;                   // ghost rows, all columns
+    const long ncolcells = (long)(a.NYI - nyg) * 2 * G;         // interior rows, ghost columns
+    const long id = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= nrowcells + ncolcells) return;
+    int i, j;
+    if (id < nrowcells) {
+        const int r = (int)(id / a.NXI);
+        i = (int)(id % a.NXI);
+        j = r < G ? r : a.NYI - 2 * G + r;
+    } else {
+        const long e = id - nrowcells;
+        const int r = (int)(e / (2 * G)), c = (int)(e % (2 * G));
+        j = (a.NYI > 1 ? G : 0) + r;
+        i = c < G ? c : a.NXI - 2 * G + c;
+    }
+    bool skip = false;
+    const int si = bc_map(i, a.NXI, a.sxlo, a.sxhi, skip);
+    const int sj = a.NYI > 1 ? bc_map(j, a.NYI, a.sylo, a.syhi, skip) : j;
+    if (skip) return;
+    const size_t g = (size_t)i + (size_t)a.pitch * j, sg = (size_t)si + (size_t)a.pitch * sj;
+    for (int k = 0; k < a.n; ++k) a.pl[k][g] = a.pl[k][sg];
+}
+
+void launch_bc_fill(double *const planes[], int nplanes, const Geom &g, const int side[4], const double *dtp,
+                    cudaStream_t s)
+{
+    BcArgs a;
+    a.n = nplanes;
+    for (int k = 0; k < nplanes; ++k) a.pl[k] = planes[k];
+    a.NXI = g.NXI; a.NYI = g.NYI; a.pitch = g.pitch;
+    a.sxlo = side[0]; a.sxhi = side[1]; a.sylo = side[2]; a.syhi = side[3];
+    a.dtp = dtp;
+    const int nyg = g.NYI > 1 ? 2 * G : 0;
+    const long total = (long)nyg * g.NXI + (long)(g.NYI - nyg) * 2 * G;
+    bc_fill_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a);
+}
+
+// ------------------------------------------------------------------ entropy variable
+// ES_Switch residue (Weno5_2D.jl:1737-1765): S = E2S(q); with roundtrip E = S2E(q,S)
+struct EntArgs { double *q[9]; int NXI, NYI, pitch; double gam; int roundtrip; int all_cells; const double *dtp; };
+
+__global__ void entropy_kernel(const EntArgs a)
+{
+    if (a.dtp && *a.dtp == 0.0) return;
+    const int off = a.all_cells ? 0 : G;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + off;
+    const int j = a.NYI > 1 ? blockIdx.y * blockDim.y + threadIdx.y + off : 0;
+    if (i >= a.NXI - off || (a.NYI > 1 && j >= a.NYI - off)) return;
+    const size_t g = (size_t)i + (size_t)a.pitch * j;
+    const double rho = a.q[C_RHO][g], mx = a.q[C_MX][g], my = a.q[C_MY][g], mz = a.q[C_MZ][g];
+    const double bx = a.q[C_BX][g], by = a.q[C_BY][g], bz = a.q[C_BZ][g];
+    const double S = e2s(rho, mx, my, mz, bx, by, bz, a.q[C_E][g], a.gam);
+    a.q[C_S][g] = S;
+    if (a.roundtrip) a.q[C_E][g] = s2e(rho, mx, my, mz, bx, by, bz, S, a.gam);
+}
+
+void launch_entropy(double *const q9[9], const Geom &g, double gam, int roundtrip, int all_cells,
+                    const double *dtp, cudaStream_t s)
+{
+    EntArgs a;
+    for (int k = 0; k < 9; ++k) a.q[k] = q9[k];
+    a.NXI = g.NXI; a.NYI = g.NYI; a.pitch = g.pitch; a.gam = gam; a.roundtrip = roundtrip;
+    a.all_cells = all_cells; a.dtp = dtp;
+    dim3 block(64, 4), grid((g.NXI + 63) / 64, g.NYI > 1 ? (g.NYI + 3) / 4 : 1);
+    entropy_kernel<<<grid, block, 0, s>>>(a);
+}
+
+// ------------------------------------------------------------------ CFL reduction
+// compute_global_vmax, Weno5_2D.jl:1942-1984 (x-face averages for both directions, pressure
+// from S); 1-D twin Weno5_1D.jl:1038-1074.  Non-negative doubles order like their bit
+// patterns, so the grid-wide maximum is an integer atomicMax; NaN maps to the largest
+// pattern and is caught by dt_kernel.
+struct VmaxArgs { const double *q[9]; int NXI, NYI, pitch; double gam; unsigned long long *out; };
+
+__global__ void vmax_kernel(const VmaxArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + G;
+    const int j = a.NYI > 1 ? blockIdx.y * blockDim.y + threadIdx.y + G : 0;
+    double vxm = 0.0, vym = 0.0;
+    if (i < a.NXI - G && (a.NYI == 1 || j < a.NYI - G)) {
+        const size_t g = (size_t)i + (size_t)a.pitch * j;
+        const double rho = (a.q[C_RHO][g] + a.q[C_RHO][g + 1]) / 2;
+        const double vx = (a.q[C_MX][g] + a.q[C_MX][g + 1]) / 2 / rho;
+        const double vy = (a.q[C_MY][g] + a.q[C_MY][g + 1]) / 2 / rho;
+        const double Bx = (a.q[C_BX][g] + a.q[C_BX][g + 1]) / 2;
+        const double By = (a.q[C_BY][g] + a.q[C_BY][g + 1]) / 2;
+        const double Bz = (a.q[C_BZ][g] + a.q[C_BZ][g + 1]) / 2;
+        const double S = (a.q[C_S][g] + a.q[C_S][g + 1]) / 2;
+        const double pres = S * pow(rho, a.gam - 1.0);
+        const double cs2 = a.gam * fabs(pres / rho);
+        const double B2 = Bx * Bx + By * By + Bz * Bz;
+        const double bbn2 = B2 / rho, bnx2 = Bx * Bx / rho, bny2 = By * By / rho;
+        const double sm = bbn2 + cs2;
+        const double rootx = sqrt(fmax(0.0, sm * sm - 4 * bnx2 * cs2));
+        const double rooty = sqrt(fmax(0.0, sm * sm - 4 * bny2 * cs2));
+        vxm = fabs(vx) + sqrt(0.5 * (sm + rootx));
+        vym = fabs(vy) + sqrt(0.5 * (sm + rooty));
+    }
+    unsigned long long bx_ = (unsigned long long)__double_as_longlong(vxm);
+    unsigned long long by_ = (unsigned long long)__double_as_longlong(vym);
+    if (vxm != vxm || vxm < 0.0) bx_ = ~0ull;
+    if (vym != vym || vym < 0.0) by_ = ~0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        bx_ = max(bx_, __shfl_xor_sync(0xffffffffu, bx_, o));
+        by_ = max(by_, __shfl_xor_sync(0xffffffffu, by_, o));
+    }
+    __shared__ unsigned long long sx[8], sy[8];
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    if ((tid & 31) == 0) { sx[tid >> 5] = bx_; sy[tid >> 5] = by_; }
+    __syncthreads();
+    if (tid == 0) {
+        const int nw = (blockDim.x * blockDim.y + 31) / 32;
+        for (int w = 1; w < nw; ++w) { bx_ = max(bx_, sx[w]); by_ = max(by_, sy[w]); }
+        atomicMax(a.out, bx_);
+        atomicMax(a.out + 1, by_);
+    }
+}
+
+void launch_vmax(const double *const q9[9], const Geom &g, double gam, unsigned long long *vmax_bits,
+                 cudaStream_t s)
+{
+    VmaxArgs a;
+    for (int k = 0; k < 9; ++k) a.q[k] = q9[k];
+    a.NXI = g.NXI; a.NYI = g.NYI; a.pitch = g.pitch; a.gam = gam; a.out = vmax_bits;
+    cudaMemsetAsync(vmax_bits, 0, 2 * sizeof(unsigned long long), s);
+    dim3 block(64, 4), grid((g.NXI - 2 * G + 63) / 64, g.NYI > 1 ? (g.NYI - 2 * G + 3) / 4 : 1);
+    vmax_kernel<<<grid, block, 0, s>>>(a);
+}
+
+// timestep(), Weno5_2D.jl:1930-1940; 1-D: dt = courFac*dx/vmax (Weno5_1D.jl:55).
+// With tmax > 0 the step is shortened to land on tmax and becomes 0 once t >= tmax.
+__global__ void dt_kernel(const unsigned long long *vb, double *ctl, double dx, double dy, double cfl, int is1d)
+{
+    const double vx = __longlong_as_double((long long)vb[0]);
+    const double vy = __longlong_as_double((long long)vb[1]);
+    ctl[2] = vx; ctl[3] = vy;
+    double dt;
+    if (is1d) {
+        dt = cfl * dx / vx;
+    } else {
+        const double dtx = dx / vx, dty = dy / vy;
+        dt = cfl / (1 / dtx + 1 / dty);
+    }
+    if (!(dt > 0.0) || !(dt < 1e300)) { ctl[6] = 1.0; dt = 0.0; }
+    const double t = ctl[1], tmax = ctl[4];
+    if (tmax > 0.0) {
+        if (t >= tmax) dt = 0.0;
+        else if (t + dt > tmax) dt = tmax - t;
+    }
+    ctl[0] = dt;
+}
+
+void launch_dt_from_vmax(const unsigned long long *vmax_bits, double *ctl, double dx, double dy, double cfl,
+                         int is1d, cudaStream_t s)
+{
+    dt_kernel<<<1, 1, 0, s>>>(vmax_bits, ctl, dx, dy, cfl, is1d);
+}
+
+__global__ void advance_time_kernel(double *ctl)
+{
+    if (ctl[0] > 0.0) { ctl[1] += ctl[0]; ctl[5] += 1.0; }
+}
+
+void launch_advance_time(double *ctl, cudaStream_t s) { advance_time_kernel<<<1, 1, 0, s>>>(ctl); }
+
+// ------------------------------------------------------------------ start-up and diagnostics
+// interpolateB_center2face, Weno5_2D.jl:1669-1682 (public i = 2..Nx-2, j = 2..Ny-2; 0 elsewhere)
+__global__ void center2face_kernel(const double *__restrict__ Bx, const double *__restrict__ By,
+                                   double *__restrict__ bxb, double *__restrict__ byb, int Nx, int Ny, int pitch)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+    if (i > Nx || j > Ny) return;
+    const size_t g = (size_t)i + (size_t)pitch * j;
+    double fx = 0.0, fy = 0.0;
+    if (i >= 2 && i <= Nx - 2 && j >= 2 && j <= Ny - 2) {
+        fx = (-Bx[g - 1] + 9 * Bx[g] + 9 * Bx[g + 1] - Bx[g + 2]) / 16;
+        fy = (-By[g - pitch] + 9 * By[g] + 9 * By[g + pitch] - By[g + 2 * (size_t)pitch]) / 16;
+    }
+    bxb[g] = fx;
+    byb[g] = fy;
+}
+
+void launch_center2face(const double *Bx, const double *By, double *bxb, double *byb, const Geom &g,
+                        cudaStream_t s)
+{
+    dim3 block(64, 4), grid((g.Nx + 63) / 64, (g.Ny + 3) / 4);
+    center2face_kernel<<<grid, block, 0, s>>>(Bx, By, bxb, byb, g.Nx, g.Ny, g.pitch);
+}
+
+// compute_divB, Weno5_2D.jl:1986-1999 (public i = 3..Nx-3, j = 3..Ny-3)
+__global__ void divb_kernel(const double *__restrict__ bxb, const double *__restrict__ byb,
+                            double *__restrict__ divb, int Nx, int Ny, int pitch, double dx, double dy)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y + 1;
+    if (i > Nx || j > Ny) return;
+    const size_t g = (size_t)i + (size_t)pitch * j;
+    double d = 0.0;
+    if (i >= 3 && i <= Nx - 3 && j >= 3 && j <= Ny - 3)
+        d = (bxb[g] - bxb[g - 1]) / dx + (byb[g] - byb[g - pitch]) / dy;
+    divb[g] = d;
+}
+
+void launch_divb(const double *bxb, const double *byb, double *divb, const Geom &g, double dx, double dy,
+                 cudaStream_t s)
+{
+    dim3 block(64, 4), grid((g.Nx + 63) / 64, (g.Ny + 3) / 4);
+    divb_kernel<<<grid, block, 0, s>>>(bxb, byb, divb, g.Nx, g.Ny, g.pitch, dx, dy);
+}
+
+// interior sums per plane (deterministic: one block per plane, fixed reduction tree)
+struct TotArgs { const double *pl[11]; int NXI, NYI, pitch; double *out; };
+
+__global__ void totals_kernel(const TotArgs a)
+{
+    const double *f = a.pl[blockIdx.x];
+    const int nxi = a.NXI - 2 * G, nyi = a.NYI > 1 ? a.NYI - 2 * G : 1;
+    const long n = (long)nxi * nyi;
+    double acc = 0.0;
+    for (long e = threadIdx.x; e < n; e += blockDim.x) {
+        const int i = (int)(e % nxi) + G, j = a.NYI > 1 ? (int)(e / nxi) + G : 0;
+        acc += f[(size_t)i + (size_t)a.pitch * j];
+    }
+    __shared__ double sh[1024];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) a.out[blockIdx.x] = sh[0];
+}
+
+void launch_totals(const double *const planes[], int nplanes, const Geom &g, double *sums, cudaStream_t s)
+{
+    TotArgs a;
+    for (int k = 0; k < nplanes; ++k) a.pl[k] = planes[k];
+    a.NXI = g.NXI; a.NYI = g.NYI; a.pitch = g.pitch; a.out = sums;
+    totals_kernel<<<nplanes, 1024, 0, s>>>(a);
+}
+
+}  // namespace w5

@@ -1,0 +1,86 @@
+// Kernel-side data structures and launcher declarations of libweno5mhd (sm_100a).
+//
+// Device layout (DESIGN.md "data layout in HBM"): every field is its own plane of
+// pitch x NYI doubles, i fastest, with G = 4 ghost layers per side (one more than the
+// reference's NBnd = 3, so that every face the CT update needs has a complete stencil
+// and y-slabs need a single exchange per stage).  With G = 4 the internal 0-based index
+// equals the reference's 1-based public index: internal (i,j) == public (i,j).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace w5 {
+
+constexpr int G = 4;
+
+struct Geom {
+    int NXI, NYI;        // cells incl. 4 ghosts per side (NYI = 1 in 1-D)
+    int pitch;           // doubles per row (multiple of 16 -> 128-byte aligned rows)
+    int Nx, Ny;          // public array sizes (nx+6, ny_local+6; Ny = 1 in 1-D)
+    int is1d;
+    size_t plane;        // pitch * NYI
+};
+
+// physical components of the cell state planes
+enum { C_RHO = 0, C_MX, C_MY, C_MZ, C_BX, C_BY, C_BZ, C_E, C_S, NCELL = 9 };
+// the six cell fields advanced by flux differences in 2-D (Bx,By come from the CT update)
+// order: rho, Mx, My, Mz, Bz, E  (+ By as 7th entry of rhs in 1-D)
+
+enum SideBC { SIDE_OUTFLOW = 0, SIDE_PERIODIC = 1, SIDE_NONE = 2 /* slab-internal: filled by exchange */ };
+
+struct FluxArgs {
+    const double *qc[8];     // current state: rho,Mx,My,Mz,Bx,By,Bz,E
+    double *rhs[7];          // x sweep: out (d fhat);  y sweep: in
+    double *bs;              // fsy (x sweep) / gsx (y sweep)
+    const double *base[6];   // y sweep: RK base state (stages 1-3)
+    double *acc[6];          // y sweep: running RK combination -q0 + q1 + 2 q2
+    double *qn[6];           // y sweep: new state
+    const double *dtp;       // device time step
+    double c_dx, c_dy;       // c_k/dx, c_k/dy
+    int stage;               // 1..4
+    int N, NP, pitch;        // cells along the sweep, lines across it
+    int seg_len, nseg;       // faces per segment, segments per line
+    double gam, eps;
+    int is1d;
+};
+
+struct CtArgs {
+    const double *fsy, *gsx;
+    const double *bx0, *by0;     // base face fields (stages 1-3)
+    const double *bxc, *byc;     // current face fields (for the RK combination)
+    double *accbx, *accby;
+    double *bxn, *byn;
+    const double *dtp;
+    double c_dx, c_dy;
+    int stage;
+    int Nx, Ny, pitch;
+    int oxlo, oxhi, oylo, oyhi;  // 1 where the side is a physical outflow boundary
+    int bx_i0, bx_i1, bx_j0, bx_j1;   // write ranges (inclusive) of bxn
+    int by_i0, by_i1, by_j0, by_j1;   // and of byn
+};
+
+void launch_flux_x(const FluxArgs &a, cudaStream_t s);
+void launch_flux_y(const FluxArgs &a, cudaStream_t s);
+void launch_update_1d(const FluxArgs &a, double *const qn7[7], const double *const base7[7],
+                      double *const acc7[7], cudaStream_t s);
+void launch_ct_faces(const CtArgs &a, cudaStream_t s);
+void launch_ct_centers(const double *bxn, const double *byn, double *Bx, double *By,
+                       const Geom &g, const double *dtp, cudaStream_t s);
+void launch_face_bc(double *bx, double *by, const Geom &g, const int side[4], const double *dtp, cudaStream_t s);
+void launch_bc_fill(double *const planes[], int nplanes, const Geom &g, const int side[4],
+                    const double *dtp, cudaStream_t s);
+void launch_entropy(double *const q9[9], const Geom &g, double gam, int roundtrip, int all_cells,
+                    const double *dtp, cudaStream_t s);
+void launch_vmax(const double *const q9[9], const Geom &g, double gam, unsigned long long *vmax_bits,
+                 cudaStream_t s);
+// ctl[0]=dt ctl[1]=t ctl[2]=vxmax ctl[3]=vymax ctl[4]=tmax ctl[5]=steps_done ctl[6]=bad-flag
+void launch_dt_from_vmax(const unsigned long long *vmax_bits, double *ctl, double dx, double dy,
+                         double cfl, int is1d, cudaStream_t s);
+void launch_advance_time(double *ctl, cudaStream_t s);
+void launch_center2face(const double *Bx, const double *By, double *bxb, double *byb, const Geom &g,
+                        cudaStream_t s);
+void launch_divb(const double *bxb, const double *byb, double *divb, const Geom &g, double dx, double dy,
+                 cudaStream_t s);
+void launch_totals(const double *const planes[], int nplanes, const Geom &g, double *sums, cudaStream_t s);
+int flux_smem_bytes(int dir);
+
+}  // namespace w5

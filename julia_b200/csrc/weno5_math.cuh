@@ -1,0 +1,316 @@
+// Per-cell and per-face arithmetic of the WENO5 MHD sweep, written for the B200 FP64 pipe.
+//
+// What the reference does per face (Weno5_2D.jl:1250-1531 eigenvectors, :1795-1895 WENO):
+// build dense 7x7 matrices L and R (98 doubles), project the 6-cell stencil of F and q
+// with 588 multiply-adds, run WENO5 on the 7 characteristic fields, multiply by R.
+// This file computes the same quantities without ever forming L or R: the rows of L and
+// the columns of R are linear combinations of a few shared inner products (see
+// DESIGN.md "structured eigen-system"), which brings the projection from 49 to 32 FMAs per
+// stencil vector and the back-projection from 49 to ~35.  The WENO weights use one
+// reciprocal per side instead of five divisions (same rational function of the
+// smoothness indicators).  All of it is algebraically identical to the reference; the
+// difference is round-off (checked against the CPU oracle, tolerance 1e-10 on smooth
+// problems per BASELINE.json).
+//
+// The functions are __host__ __device__ so that tests/ can compile them for the host and
+// compare against the oracle without a GPU; the product only ever runs them on the device.
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define W5_HD __host__ __device__ __forceinline__
+#else
+#define W5_HD inline
+#endif
+
+namespace w5 {
+
+// quantities stored per cell in shared memory by the cell phase
+enum CellQ {
+    CQ_F0 = 0,            // F[0..6]  physical flux, Weno5_2D.jl:1533-1555
+    CQ_Q0 = 7,            // q7[0..6] = rho, M1, M2, M3, B2, B3, E
+    CQ_V1 = 14, CQ_V2 = 15, CQ_V3 = 16,
+    CQ_B1 = 17,
+    CQ_LF = 18, CQ_LA = 19, CQ_LS = 20,
+    CQ_COUNT = 21
+};
+
+struct CellOut {
+    double F[7];
+    double v1, v2, v3;
+    double lf, la, ls;
+};
+
+// 1/x good to ~1 ulp without the slow-path branch of IEEE division (x is a sum of
+// positive terms here, never 0/inf/denormal)
+W5_HD double fast_rcp(double x)
+{
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+#else
+    return 1.0 / x;
+#endif
+}
+
+// cons -> prim, cell-centre wave speeds and flux in the sweep frame
+// (Weno5_2D.jl:1573-1606, :1608-1667, :1533-1555).  q = [rho,M1,M2,M3,B1,B2,B3,E].
+W5_HD void cell_quantities(const double q[8], double gam, CellOut &o)
+{
+    const double rho = q[0];
+    const double ri = 1.0 / rho;
+    const double v1 = q[1] * ri, v2 = q[2] * ri, v3 = q[3] * ri;
+    const double B1 = q[4], B2 = q[5], B3 = q[6], E = q[7];
+    const double vv = v1 * v1 + v2 * v2 + v3 * v3;
+    const double BB = B1 * B1 + B2 * B2 + B3 * B3;
+    const double P = (gam - 1.0) * (E - 0.5 * (rho * vv + BB));
+    const double cs2 = fmax(0.0, gam * fabs(P * ri));
+    const double bnx2 = fmax(0.0, B1 * B1 * ri);
+    const double bbn2 = BB * ri;
+    const double s = bbn2 + cs2;
+    const double root = sqrt(fmax(0.0, s * s - 4.0 * bnx2 * cs2));
+    o.lf = sqrt(fmax(0.0, 0.5 * (s + root)));
+    o.ls = sqrt(fmax(0.0, 0.5 * (s - root)));
+    o.la = sqrt(bnx2);
+    o.v1 = v1; o.v2 = v2; o.v3 = v3;
+    const double pt = P + 0.5 * BB;
+    const double vB = v1 * B1 + v2 * B2 + v3 * B3;
+    o.F[0] = rho * v1;
+    o.F[1] = q[1] * v1 + pt - B1 * B1;
+    o.F[2] = q[2] * v1 - B1 * B2;
+    o.F[3] = q[3] * v1 - B1 * B3;
+    o.F[4] = B2 * v1 - B1 * v2;
+    o.F[5] = B3 * v1 - B1 * v3;
+    o.F[6] = (E + pt) * v1 - B1 * vB;
+}
+
+// Face-averaged state and everything the structured projection needs.
+// Field order m: fast-, Alfven-, slow-, entropy, slow+, Alfven+, fast+.
+struct FaceCoef {
+    // shared inner products
+    double hv2, vx, vy, vz, By, Bz;       // n = -hv2 x1 + vx x2 + vy x3 + vz x4 + By x5 + Bz x6 - x7
+    double bty, btz;                      // t = bty x5 + btz x6, u = bty x3 + btz x4
+    // fast pair (rows 1,7), slow pair (rows 3,5): w = k_n n + k_t t +- (k_1 x1 + k_2 x2 + k_u u)
+    double kf_n, kf_t, kf_1, kf_2, kf_u;
+    double ks_n, ks_t, ks_1, ks_2, ks_u;
+    // Alfven pair (rows 2,6): w = (ka_1 x1 + ka_3 x3 + ka_4 x4) +- (kb_5 x5 + kb_6 x6)
+    double ka_1, ka_3, ka_4, kb_5, kb_6;
+    double ke_n;                          // entropy row: w = ke_n n + x1
+    // back-projection
+    double af, as_, afcf, ascs, a_r, s_r, sgn, sig, hf, hs, axy;
+};
+
+// Weno5_2D.jl:1273-1359 (face averages, wave speeds, degeneracy handling) and the
+// coefficient groups of L (:1368-1426, scaling :1490-1502) and R (:1428-1486).
+// The sgnBt flip (:1506-1528) multiplies row m of L and column m of R by the same +-1 and
+// WENO is odd in its inputs, so it cancels exactly and is not applied.
+W5_HD void face_coefficients(double rhoL, double rhoR, double v1L, double v1R, double v2L, double v2R,
+                             double v3L, double v3R, double B1L, double B1R, double B2L, double B2R,
+                             double B3L, double B3R, double EL, double ER, double gam, FaceCoef &c)
+{
+    const double g0 = 1.0 - gam, g2 = (gam - 2.0) / (gam - 1.0);
+    const double rho = 0.5 * (rhoL + rhoR);
+    const double vx = 0.5 * (v1L + v1R), vy = 0.5 * (v2L + v2R), vz = 0.5 * (v3L + v3R);
+    const double Bx = 0.5 * (B1L + B1R), By = 0.5 * (B2L + B2R), Bz = 0.5 * (B3L + B3R);
+    const double E = 0.5 * (EL + ER);
+    const double ri = 1.0 / rho;
+    const double r = sqrt(rho);
+    const double Bt2 = By * By + Bz * Bz;
+    const double B2 = Bx * Bx + Bt2;
+    const double v2 = vx * vx + vy * vy + vz * vz;
+    const double pg = (gam - 1.0) * (E - 0.5 * (rho * v2 + B2));
+    const double bbn2 = B2 * ri;
+    const double cs2 = fmax(0.0, gam * fabs(pg * ri));
+    const double bnx2 = Bx * Bx * ri;
+    const double a = sqrt(cs2);
+    const double s_ = bbn2 + cs2;
+    const double root = sqrt(fmax(0.0, s_ * s_ - 4.0 * bnx2 * cs2));
+    const double cf = sqrt(fmax(0.0, 0.5 * (s_ + root)));
+    const double cs = sqrt(fmax(0.0, 0.5 * (s_ - root)));
+    const double sg = (Bx < 0.0) ? -1.0 : 1.0;                    // sign(Bx), 0 -> 1
+    double bty = 0.70710678118654752440, btz = 0.70710678118654752440;
+    if (Bt2 > 1e-30) {
+        const double ib = 1.0 / sqrt(Bt2);
+        bty = By * ib; btz = Bz * ib;
+    }
+    const double dl2 = cf * cf - cs * cs;
+    double af = 1.0, as_ = 1.0;
+    if (dl2 >= 1e-30) {
+        const double id = 1.0 / dl2;
+        af = sqrt(fmax(0.0, cs2 - cs * cs) * id);
+        as_ = sqrt(fmax(0.0, cf * cf - cs2) * id);
+    }
+    const double sig = bty * vy + btz * vz;
+    const double ih = 0.5 / cs2;                                   // 1/(2 a^2)
+    const double afcf = af * cf, ascs = as_ * cs;
+
+    c.hv2 = 0.5 * v2; c.vx = vx; c.vy = vy; c.vz = vz; c.By = By; c.Bz = Bz;
+    c.bty = bty; c.btz = btz;
+    c.kf_n = g0 * af * ih;
+    c.kf_t = a * as_ * r * ih;
+    c.kf_1 = (afcf * vx - ascs * sig * sg) * ih;
+    c.kf_2 = -afcf * ih;
+    c.kf_u = ascs * sg * ih;
+    c.ks_n = g0 * as_ * ih;
+    c.ks_t = -a * af * r * ih;
+    c.ks_1 = (ascs * vx + afcf * sig * sg) * ih;
+    c.ks_2 = -ascs * ih;
+    c.ks_u = -afcf * sg * ih;
+    c.ka_1 = 0.5 * (btz * vy - bty * vz);
+    c.ka_3 = -0.5 * btz;
+    c.ka_4 = 0.5 * bty;
+    c.kb_5 = -0.5 * sg * r * btz;
+    c.kb_6 = 0.5 * sg * r * bty;
+    c.ke_n = -g0 / cs2;
+    const double rinv = r * ri;                                    // 1/sqrt(rho)
+    c.af = af; c.as_ = as_; c.afcf = afcf; c.ascs = ascs;
+    c.a_r = a * rinv; c.s_r = sg * rinv; c.sgn = sg; c.sig = sig;
+    const double h = 0.5 * v2 - g2 * cs2;
+    c.hf = af * (cf * cf + h);
+    c.hs = as_ * (cs * cs + h);
+    c.axy = bty * vz - btz * vy;
+}
+
+// characteristic projection of one 7-vector x = [rho,M1,M2,M3,B2,B3,E]-shaped quantity
+W5_HD void project(const FaceCoef &c, const double x[7], double w[7])
+{
+    const double n = fma(c.vx, x[1], fma(c.vy, x[2], fma(c.vz, x[3], fma(c.By, x[4], fma(c.Bz, x[5], fma(-c.hv2, x[0], -x[6]))))));
+    const double t = fma(c.bty, x[4], c.btz * x[5]);
+    const double u = fma(c.bty, x[2], c.btz * x[3]);
+    const double pf = fma(c.kf_n, n, c.kf_t * t);
+    const double mf = fma(c.kf_1, x[0], fma(c.kf_2, x[1], c.kf_u * u));
+    const double ps = fma(c.ks_n, n, c.ks_t * t);
+    const double ms = fma(c.ks_1, x[0], fma(c.ks_2, x[1], c.ks_u * u));
+    const double A = fma(c.ka_1, x[0], fma(c.ka_3, x[2], c.ka_4 * x[3]));
+    const double B = fma(c.kb_5, x[4], c.kb_6 * x[5]);
+    w[0] = pf + mf; w[6] = pf - mf;
+    w[2] = ps + ms; w[4] = ps - ms;
+    w[1] = A + B;   w[5] = A - B;
+    w[3] = fma(c.ke_n, n, x[0]);
+}
+
+// fhat = R . Fs without forming R (Weno5_2D.jl:1879-1888 with :1428-1486)
+W5_HD void back_project(const FaceCoef &c, const double Fs[7], double fh[7])
+{
+    const double Sf = Fs[0] + Fs[6], Df = Fs[6] - Fs[0];
+    const double Ss = Fs[2] + Fs[4], Ds = Fs[4] - Fs[2];
+    const double Sa = Fs[1] + Fs[5], Da = Fs[5] - Fs[1];
+    const double X = fma(c.afcf, Ds, -c.ascs * Df);
+    const double Y = fma(c.afcf, Df, c.ascs * Ds);
+    const double f1 = fma(c.af, Sf, fma(c.as_, Ss, Fs[3]));
+    const double sX = c.sgn * X;
+    const double Z = c.a_r * fma(c.as_, Sf, -c.af * Ss);
+    const double sDa = c.s_r * Da;
+    fh[0] = f1;
+    fh[1] = fma(c.vx, f1, Y);
+    fh[2] = fma(c.vy, f1, fma(c.bty, sX, -c.btz * Sa));
+    fh[3] = fma(c.vz, f1, fma(c.btz, sX, c.bty * Sa));
+    fh[4] = fma(c.bty, Z, c.btz * sDa);
+    fh[5] = fma(c.btz, Z, -c.bty * sDa);
+    fh[6] = fma(c.hf, Sf, fma(c.hs, Ss, fma(c.vx, Y, fma(c.sig, sX, fma(c.hv2, Fs[3], c.axy * Sa)))));
+}
+
+// One side of the Jiang & Wu correction (Weno5_2D.jl:1836-1853) for UNHALVED inputs
+// A = 2a, ... : the smoothness indicators scale by exactly 4 (power of two, no rounding
+// change), so eps4 = 4 eps gives bit-identical ratios; the returned value is 2 phi.
+// omega0 = al0/(al0+al1+al2) with al = (1,6,3)/d_k, d_k = (eps+IS_k)^2, rewritten over the
+// common denominator so that a single reciprocal is needed.
+W5_HD double weno_phi2(double A, double B, double C, double D, double eps4)
+{
+    double t1 = A - B, t2 = fma(-3.0, B, A);
+    const double IS0 = fma(13.0 * t1, t1, 3.0 * (t2 * t2));
+    t1 = B - C; t2 = B + C;
+    const double IS1 = fma(13.0 * t1, t1, 3.0 * (t2 * t2));
+    t1 = C - D; t2 = fma(3.0, C, -D);
+    const double IS2 = fma(13.0 * t1, t1, 3.0 * (t2 * t2));
+    double d0 = eps4 + IS0, d1 = eps4 + IS1, d2 = eps4 + IS2;
+    d0 *= d0; d1 *= d1; d2 *= d2;
+    const double p12 = d1 * d2, p02 = d0 * d2, p01 = d0 * d1;
+    const double inv = fast_rcp(fma(6.0, p02, fma(3.0, p01, p12)));
+    const double om0 = p12 * inv;
+    const double om2 = 3.0 * p01 * inv;
+    const double D1 = fma(-2.0, B, A) + C;
+    const double D2 = fma(-2.0, C, B) + D;
+    return fma(om0 * (1.0 / 3.0), D1, (om2 - 0.5) * (1.0 / 6.0) * D2);
+}
+
+// Numerical flux of one face.  load(k, F, q) fills the flux and conserved 7-vectors of
+// stencil cell k = 0..5 (cells f-2 .. f+3); amax[m] = max(|a_m(f)|, |a_m(f+1)|)
+// (Weno5_2D.jl:1834).  Streams over the stencil so that only the 8 Lax-Friedrichs split
+// differences per field are live, not the 84 stencil operands.
+template <class Loader>
+W5_HD void face_flux(const FaceCoef &c, const double amax[7], double eps, Loader load, double fh[7])
+{
+    double P[4][7], Q[4][7];       // P[k] = dw_k + amax dv_k (k=0..3), Q[k-1] = dw_k - amax dv_k (k=1..4)
+    double first[7];
+    double wp[7], vp[7];
+    {
+        double F[7], q[7];
+        load(0, F, q);
+        project(c, F, wp);
+        project(c, q, vp);
+    }
+#pragma unroll
+    for (int k = 1; k < 6; ++k) {
+        double F[7], q[7], w[7], v[7];
+        load(k, F, q);
+        project(c, F, w);
+        project(c, q, v);
+#pragma unroll
+        for (int m = 0; m < 7; ++m) {
+            const double dw = w[m] - wp[m], dv = v[m] - vp[m];
+            if (k <= 4) P[k - 1][m] = fma(amax[m], dv, dw);
+            if (k >= 2) Q[k - 2][m] = fma(-amax[m], dv, dw);
+            // first = (-w1 + 7 w2 + 7 w3 - w4)/12, Weno5_2D.jl:1827
+            if (k == 1) first[m] = -w[m];
+            if (k == 2 || k == 3) first[m] = fma(7.0, w[m], first[m]);
+            if (k == 4) first[m] -= w[m];
+            wp[m] = w[m]; vp[m] = v[m];
+        }
+    }
+    const double eps4 = 4.0 * eps;
+    double Fs[7];
+#pragma unroll
+    for (int m = 0; m < 7; ++m) {
+        const double second2 = weno_phi2(P[0][m], P[1][m], P[2][m], P[3][m], eps4);
+        const double third2 = weno_phi2(Q[3][m], Q[2][m], Q[1][m], Q[0][m], eps4);
+        Fs[m] = fma(first[m], 1.0 / 12.0, 0.5 * (third2 - second2));
+    }
+    back_project(c, Fs, fh);
+}
+
+W5_HD void face_amax(double v1L, double lfL, double laL, double lsL,
+                     double v1R, double lfR, double laR, double lsR, double amax[7])
+{
+    amax[0] = fmax(fabs(v1L - lfL), fabs(v1R - lfR));
+    amax[1] = fmax(fabs(v1L - laL), fabs(v1R - laR));
+    amax[2] = fmax(fabs(v1L - lsL), fabs(v1R - lsR));
+    amax[3] = fmax(fabs(v1L), fabs(v1R));
+    amax[4] = fmax(fabs(v1L + lsL), fabs(v1R + lsR));
+    amax[5] = fmax(fabs(v1L + laL), fabs(v1R + laR));
+    amax[6] = fmax(fabs(v1L + lfL), fabs(v1R + lfR));
+}
+
+// Weno5_2D.jl:1770-1793
+W5_HD double e2s(double rho, double m1, double m2, double m3, double b1, double b2, double b3, double E, double gam)
+{
+    const double mom2 = m1 * m1 + m2 * m2 + m3 * m3;
+    const double BB = b1 * b1 + b2 * b2 + b3 * b3;
+    return (E - 0.5 * mom2 / rho - 0.5 * BB) * (gam - 1.0) / pow(rho, gam - 1.0);
+}
+
+W5_HD double s2e(double rho, double m1, double m2, double m3, double b1, double b2, double b3, double S, double gam)
+{
+    const double mom2 = m1 * m1 + m2 * m2 + m3 * m3;
+    const double BB = b1 * b1 + b2 * b2 + b3 * b3;
+    return pow(rho, gam - 1.0) * S / (gam - 1.0) + 0.5 * BB + 0.5 * mom2 / rho;
+}
+
+}  // namespace w5
