@@ -15,38 +15,64 @@
 // entropy/vmax/dt   E2S/S2E (:1770-1793), compute_global_vmax/timestep (:1930-1984).
 #include "weno5_kernels.cuh"
 #include "weno5_math.cuh"
+#include <cstdlib>
+
+#ifndef W5_DEFAULT_VARIANT
+#define W5_DEFAULT_VARIANT 0
+#endif
 
 namespace w5 {
 
-constexpr int NTHREADS = 256;
+// A CTA of NT threads handles a chunk of NT faces per march step: DIR 0 (x sweep) NT/64 rows of
+// 64 faces, DIR 1 (y sweep) NT/32 face rows of 32 columns -- lanes always run along x so that
+// global accesses are coalesced in both sweeps.
+template <int DIR, int NT> struct Tile {
+    static constexpr int NS = DIR == 0 ? 64 : NT / 32;     // faces along the sweep per chunk
+    static constexpr int NPB = DIR == 0 ? NT / 64 : 32;    // lines across the sweep per CTA
+    static constexpr int CBS = (NS + 5) * NPB;             // cell-buffer entries per quantity
+    static constexpr int FBS = (NS + 1) * NPB;             // face-flux-buffer entries per component
+    static constexpr int SMEM = (CQ_COUNT * CBS + 7 * FBS) * (int)sizeof(double);
+    __device__ static __forceinline__ int cbi(int slot, int p) { return DIR == 0 ? p * (NS + 5) + slot : slot * NPB + p; }
+    __device__ static __forceinline__ int fbi(int slot, int p) { return DIR == 0 ? p * (NS + 1) + slot : slot * NPB + p; }
+};
 
-template <int DIR> struct Tile;
-template <> struct Tile<0> { static constexpr int NS = 64, NPB = 4; };   // 4 rows x 64 faces
-template <> struct Tile<1> { static constexpr int NS = 8, NPB = 32; };   // 8 face rows x 32 columns
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-template <int DIR> __device__ __forceinline__ int cbi(int slot, int p)
-{
-    return DIR == 0 ? p * (Tile<DIR>::NS + 5) + slot : slot * Tile<DIR>::NPB + p;
-}
-template <int DIR> __device__ __forceinline__ int fbi(int slot, int p)
-{
-    return DIR == 0 ? p * (Tile<DIR>::NS + 1) + slot : slot * Tile<DIR>::NPB + p;
-}
+// Thread-private column of shared memory for the operands that are cold while the stencil is
+// streamed (minus-side differences, central term, back-projection coefficients).  With 250+
+// registers per thread only one CTA fits on an SM, which leaves > 100 KB of shared memory idle:
+// parking ~50 doubles per thread there is what lets ptxas keep the streaming loop free of
+// spills at a lower register count.  Slot-major layout: consecutive lanes hit consecutive banks.
+constexpr int STASH_Q = 28, STASH_FIRST = 7, STASH_BACK = 17;
+template <int NT, int LEVEL> struct SmemStash {
+    volatile double *b;
+    __device__ __forceinline__ void put_q(int k, int m, double v) { b[(k * 7 + m) * NT] = v; }
+    __device__ __forceinline__ double get_q(int k, int m) const { return b[(k * 7 + m) * NT]; }
+    __device__ __forceinline__ void put_first(int m, double v) { b[(STASH_Q + m) * NT] = v; }
+    __device__ __forceinline__ double get_first(int m) const { return b[(STASH_Q + m) * NT]; }
+    __device__ __forceinline__ void put_back(const BackCoef &c)
+    {
+        const double *src = reinterpret_cast<const double *>(&c);
+#pragma unroll
+        for (int i = 0; i < STASH_BACK; ++i) b[(STASH_Q + STASH_FIRST + i) * NT] = src[i];
+    }
+    __device__ __forceinline__ void get_back(BackCoef &c) const
+    {
+        double *dst = reinterpret_cast<double *>(&c);
+#pragma unroll
+        for (int i = 0; i < STASH_BACK; ++i) dst[i] = b[(STASH_Q + STASH_FIRST + i) * NT];
+    }
+};
+static_assert(sizeof(BackCoef) == STASH_BACK * sizeof(double), "BackCoef layout");
 
-template <int DIR> __host__ __device__ constexpr int cb_size() { return (Tile<DIR>::NS + 5) * Tile<DIR>::NPB; }
-template <int DIR> __host__ __device__ constexpr int fb_size() { return (Tile<DIR>::NS + 1) * Tile<DIR>::NPB; }
-
-int flux_smem_bytes(int dir)
-{
-    return dir == 0 ? (CQ_COUNT * cb_size<0>() + 7 * fb_size<0>()) * (int)sizeof(double)
-                    : (CQ_COUNT * cb_size<1>() + 7 * fb_size<1>()) * (int)sizeof(double);
-}
+constexpr int stash_slots(int level) { return level == 0 ? 0 : (level == 1 ? STASH_Q + STASH_FIRST : STASH_Q + STASH_FIRST + STASH_BACK); }
 
 // cons->prim, eigenvalues, flux of one cell -> shared memory slot
-template <int DIR>
+template <int DIR, int NT>
 __device__ __forceinline__ void cell_phase(const FluxArgs &a, double *cb, int c, int line, int slot, int p)
 {
-    constexpr int CBS = cb_size<DIR>();
+    using T = Tile<DIR, NT>;
+    constexpr int CBS = T::CBS;
     // sweep-frame component c reads physical plane in[c]: (x,y,z) -> (y,z,x) for the y sweep
     constexpr int in[8] = {0, DIR ? 2 : 1, DIR ? 3 : 2, DIR ? 1 : 3, DIR ? 5 : 4, DIR ? 6 : 5, DIR ? 4 : 6, 7};
     const int cc = min(c, a.N - 1), ll = min(line, a.NP - 1);
@@ -56,7 +82,7 @@ __device__ __forceinline__ void cell_phase(const FluxArgs &a, double *cb, int c,
     for (int k = 0; k < 8; ++k) q[k] = __ldg(a.qc[in[k]] + g);
     CellOut o;
     cell_quantities(q, a.gam, o);
-    const int i = cbi<DIR>(slot, p);
+    const int i = T::cbi(slot, p);
 #pragma unroll
     for (int m = 0; m < 7; ++m) cb[(CQ_F0 + m) * CBS + i] = o.F[m];
     cb[(CQ_Q0 + 0) * CBS + i] = q[0];
@@ -75,14 +101,17 @@ __device__ __forceinline__ void cell_phase(const FluxArgs &a, double *cb, int c,
     cb[CQ_LS * CBS + i] = o.ls;
 }
 
-template <int DIR>
-__global__ void __launch_bounds__(NTHREADS, 1) flux_kernel(const FluxArgs a)
+template <int DIR, int NT, int MINB, int STASH>
+__global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a)
 {
-    constexpr int NS = Tile<DIR>::NS, NPB = Tile<DIR>::NPB;
-    constexpr int CBS = cb_size<DIR>(), FBS = fb_size<DIR>();
+    using T = Tile<DIR, NT>;
+    constexpr int NTHREADS = NT;
+    constexpr int NS = T::NS, NPB = T::NPB;
+    constexpr int CBS = T::CBS, FBS = T::FBS;
     extern __shared__ double sm[];
     double *cb = sm;
     double *fb = sm + CQ_COUNT * CBS;
+    double *stash_base = fb + 7 * FBS;
 
     const double dt = *a.dtp;
     if (dt == 0.0) return;                       // advance() past tmax: leave the state untouched
@@ -99,16 +128,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) flux_kernel(const FluxArgs a)
     const int fB = min(fA + a.seg_len, a.N - 2);
     const int fStart = seg == 0 ? fA : fA - 1;
 
-    if (s < 5) cell_phase<DIR>(a, cb, fStart - 2 + s, line, s, p);
+    const bool line_ok = a.is1d ? (line == 0) : (line >= G && line < a.NP - G);
+
+    if (s < 5) cell_phase<DIR, NT>(a, cb, fStart - 2 + s, line, s, p);
 
     for (int s0 = fStart; s0 < fB; s0 += NS) {
-        cell_phase<DIR>(a, cb, s0 + 3 + s, line, 5 + s, p);
+        cell_phase<DIR, NT>(a, cb, s0 + 3 + s, line, 5 + s, p);
         __syncthreads();
+
+        // pull what the next ~2000 instructions will need towards L2: the next chunk's cells and,
+        // in the y sweep, this chunk's RK operands
+        {
+            const int cn = min(s0 + NS + 3 + s, a.N - 1), ll = min(line, a.NP - 1);
+            const size_t gn = DIR == 0 ? (size_t)cn + (size_t)a.pitch * ll : (size_t)ll + (size_t)a.pitch * cn;
+            if (s0 + NS < fB) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) prefetch_l2(a.qc[k] + gn);
+            }
+            if constexpr (DIR == 1) {
+                const int cu = min(s0 + s, a.N - 1);
+                const size_t gu = (size_t)ll + (size_t)a.pitch * cu;
+#pragma unroll
+                for (int m = 0; m < 6; ++m) {
+                    prefetch_l2(a.rhs[m] + gu);
+                    if (a.stage <= 3) prefetch_l2(a.base[m] + gu);
+                    if (a.stage >= 3) prefetch_l2(a.acc[m] + gu);
+                }
+            }
+        }
 
         // ---------------- face phase: face f between cells f and f+1 (slots s+2, s+3)
         const int f = s0 + s;
         if (f < fB) {
-            const int iL = cbi<DIR>(s + 2, p), iR = cbi<DIR>(s + 3, p);
+            const int iL = T::cbi(s + 2, p), iR = T::cbi(s + 3, p);
             FaceCoef fc;
             face_coefficients(cb[CQ_Q0 * CBS + iL], cb[CQ_Q0 * CBS + iR], cb[CQ_V1 * CBS + iL], cb[CQ_V1 * CBS + iR],
                               cb[CQ_V2 * CBS + iL], cb[CQ_V2 * CBS + iR], cb[CQ_V3 * CBS + iL], cb[CQ_V3 * CBS + iR],
@@ -119,16 +171,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) flux_kernel(const FluxArgs a)
             face_amax(cb[CQ_V1 * CBS + iL], cb[CQ_LF * CBS + iL], cb[CQ_LA * CBS + iL], cb[CQ_LS * CBS + iL],
                       cb[CQ_V1 * CBS + iR], cb[CQ_LF * CBS + iR], cb[CQ_LA * CBS + iR], cb[CQ_LS * CBS + iR], amax);
             auto load = [&](int k, double F[7], double x[7]) {
-                const int ii = cbi<DIR>(s + k, p);
+                const int ii = T::cbi(s + k, p);
 #pragma unroll
                 for (int m = 0; m < 7; ++m) {
                     F[m] = cb[(CQ_F0 + m) * CBS + ii];
                     x[m] = cb[(CQ_Q0 + m) * CBS + ii];
                 }
             };
-            double fh[7];
-            face_flux(fc, amax, a.eps, load, fh);
-            const int io = fbi<DIR>(s + 1, p);
+            double fh[7], Fs[7];
+            BackCoef bc;
+            split_back(fc, bc);
+            if constexpr (STASH == 0) {
+                RegStash st;
+                face_flux(fc, amax, a.eps, load, st, Fs);
+            } else {
+                SmemStash<NT, STASH> st{stash_base + t};
+                if constexpr (STASH >= 2) st.put_back(bc);
+                face_flux(fc, amax, a.eps, load, st, Fs);
+                if constexpr (STASH >= 2) st.get_back(bc);
+            }
+            back_project(bc, Fs, fh);
+            const int io = T::fbi(s + 1, p);
 #pragma unroll
             for (int m = 0; m < 7; ++m) fb[m * FBS + io] = fh[m];
             // CT seed flux, Weno5_2D.jl:1005-1008: x sweep -> fsy (tangential comp 2),
@@ -145,9 +208,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) flux_kernel(const FluxArgs a)
         // ---------------- update phase: cell c with faces c-1 (slot s) and c (slot s+1)
         {
             const int c = s0 + s;
-            const bool line_ok = a.is1d ? (line == 0) : (line >= G && line < a.NP - G);
             if (c > fStart && c < fB && c >= G && c < a.N - G && line_ok) {
-                const int i0 = fbi<DIR>(s, p), i1 = fbi<DIR>(s + 1, p);
+                const int i0 = T::fbi(s, p), i1 = T::fbi(s + 1, p);
                 const size_t g = DIR == 0 ? (size_t)c + (size_t)a.pitch * line : (size_t)line + (size_t)a.pitch * c;
                 if constexpr (DIR == 0) {
                     constexpr int fi[6] = {0, 1, 2, 3, 5, 6};      // rho,Mx,My,Mz,Bz,E in fhat
@@ -157,21 +219,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) flux_kernel(const FluxArgs a)
                 } else {
                     // rotated frame (rho,My,Mz,Mx,Bz,Bx,E): physical rho,Mx,My,Mz,Bz,E
                     constexpr int fi[6] = {0, 3, 1, 2, 4, 6};
-                    const int ic = cbi<DIR>(s + 2, p);
+                    const int ic = T::cbi(s + 2, p);
                     const double cx = a.c_dx * dt, cy = a.c_dy * dt;
+                    // all global operands first (one exposed latency instead of twelve)
+                    double rx[6], bb[6], ac[6];
+#pragma unroll
+                    for (int m = 0; m < 6; ++m) {
+                        rx[m] = __ldcs(a.rhs[m] + g);
+                        bb[m] = a.stage <= 3 ? __ldg(a.base[m] + g) : 0.0;
+                        ac[m] = a.stage >= 3 ? __ldcs(a.acc[m] + g) : 0.0;
+                    }
 #pragma unroll
                     for (int m = 0; m < 6; ++m) {
                         const double dfy = fb[fi[m] * FBS + i1] - fb[fi[m] * FBS + i0];
                         const double qcen = cb[(CQ_Q0 + fi[m]) * CBS + ic];
-                        double b;
-                        if (a.stage <= 3) {
-                            b = a.base[m][g];
-                            if (a.stage == 2) a.acc[m][g] = qcen - b;                       // -q0 + q1
-                            if (a.stage == 3) a.acc[m][g] = fma(2.0, qcen, a.acc[m][g]);    // + 2 q2
-                        } else {
-                            b = (a.acc[m][g] + qcen) * (1.0 / 3.0);                         // Weno5_2D.jl:279
-                        }
-                        a.qn[m][g] = fma(-cx, a.rhs[m][g], fma(-cy, dfy, b));
+                        double b = bb[m];
+                        if (a.stage == 2) a.acc[m][g] = qcen - b;                       // -q0 + q1
+                        if (a.stage == 3) a.acc[m][g] = fma(2.0, qcen, ac[m]);          // + 2 q2
+                        if (a.stage == 4) b = (ac[m] + qcen) * (1.0 / 3.0);             // Weno5_2D.jl:279
+                        a.qn[m][g] = fma(-cx, rx[m], fma(-cy, dfy, b));
                     }
                 }
             }
@@ -183,41 +249,68 @@ __global__ void __launch_bounds__(NTHREADS, 1) flux_kernel(const FluxArgs a)
             const int qn_ = e / (5 * NPB), rem = e % (5 * NPB);
             const int sl = DIR == 0 ? rem % 5 : rem / NPB;
             const int pp = DIR == 0 ? rem / 5 : rem % NPB;
-            cb[qn_ * CBS + cbi<DIR>(sl, pp)] = cb[qn_ * CBS + cbi<DIR>(NS + sl, pp)];
+            cb[qn_ * CBS + T::cbi(sl, pp)] = cb[qn_ * CBS + T::cbi(NS + sl, pp)];
         }
         for (int e = t; e < 7 * NPB; e += NTHREADS) {
             const int m = e / NPB, pp = e % NPB;
-            fb[m * FBS + fbi<DIR>(0, pp)] = fb[m * FBS + fbi<DIR>(NS, pp)];
+            fb[m * FBS + T::fbi(0, pp)] = fb[m * FBS + T::fbi(NS, pp)];
         }
         __syncthreads();
     }
 }
 
-static void flux_grid(const FluxArgs &a, int NS, int NPB, dim3 &grid)
+// Launch variants (CTA size, resident CTAs per SM -> register budget, stash level); chosen once
+// per process by WENO5_FLUX_VARIANT (development knob; the default is the fastest measured on B200).
+//   0: 256 thr, 252 regs, no stash          1: 256 thr, stash Q+first+back
+//   2: 384 thr, 168 regs, stash Q+first      3: 320 thr, 204 regs, stash Q+first
+//   4: 256 thr, stash Q+first
+struct Variant { int nt, stash; };
+static const Variant kVariants[5] = {{256, 0}, {256, 2}, {384, 1}, {320, 1}, {256, 1}};
+
+static int flux_variant()
 {
-    grid = dim3((a.NP + NPB - 1) / NPB, a.nseg, 1);
-    (void)NS;
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("WENO5_FLUX_VARIANT");
+        v = e ? atoi(e) : W5_DEFAULT_VARIANT;
+        if (v < 0 || v > 4) v = W5_DEFAULT_VARIANT;
+    }
+    return v;
 }
 
-void launch_flux_x(const FluxArgs &a, cudaStream_t s)
+template <int DIR, int NT, int MINB, int STASH>
+static void launch_flux_t(const FluxArgs &a, cudaStream_t s)
 {
+    using T = Tile<DIR, NT>;
+    constexpr int smem = T::SMEM + stash_slots(STASH) * NT * (int)sizeof(double);
+    static_assert(smem <= 227 * 1024, "shared memory budget");
     static bool once = false;
-    const int smem = flux_smem_bytes(0);
-    if (!once) { cudaFuncSetAttribute(flux_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); once = true; }
-    dim3 grid;
-    flux_grid(a, Tile<0>::NS, Tile<0>::NPB, grid);
-    flux_kernel<0><<<grid, NTHREADS, smem, s>>>(a);
+    if (!once) {
+        cudaFuncSetAttribute(flux_kernel<DIR, NT, MINB, STASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        once = true;
+    }
+    dim3 grid((a.NP + T::NPB - 1) / T::NPB, a.nseg, 1);
+    flux_kernel<DIR, NT, MINB, STASH><<<grid, NT, smem, s>>>(a);
 }
 
-void launch_flux_y(const FluxArgs &a, cudaStream_t s)
+template <int DIR>
+static void launch_flux(const FluxArgs &a, cudaStream_t s)
 {
-    static bool once = false;
-    const int smem = flux_smem_bytes(1);
-    if (!once) { cudaFuncSetAttribute(flux_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); once = true; }
-    dim3 grid;
-    flux_grid(a, Tile<1>::NS, Tile<1>::NPB, grid);
-    flux_kernel<1><<<grid, NTHREADS, smem, s>>>(a);
+    switch (flux_variant()) {
+    case 0: launch_flux_t<DIR, 256, 1, 0>(a, s); break;
+    case 1: launch_flux_t<DIR, 256, 1, 2>(a, s); break;
+    case 2: launch_flux_t<DIR, 384, 1, 1>(a, s); break;
+    case 3: launch_flux_t<DIR, 320, 1, 1>(a, s); break;
+    default: launch_flux_t<DIR, 256, 1, 1>(a, s); break;
+    }
 }
+
+void launch_flux_x(const FluxArgs &a, cudaStream_t s) { launch_flux<0>(a, s); }
+void launch_flux_y(const FluxArgs &a, cudaStream_t s) { launch_flux<1>(a, s); }
+
+// faces per march step along the sweep / lines per CTA for the active variant (host-side planning)
+int flux_chunk(int dir) { return dir == 0 ? 64 : kVariants[flux_variant()].nt / 32; }
+int flux_lines_per_cta(int dir) { return dir == 0 ? kVariants[flux_variant()].nt / 64 : 32; }
 
 // ------------------------------------------------------------------ 1-D stage update
 // Weno5_1D.jl:152-205: q_{k+1} = base - c dt/dx Q for the 7 flux-advanced components

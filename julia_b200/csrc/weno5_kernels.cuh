@@ -81,6 +81,7 @@ void launch_center2face(const double *Bx, const double *By, double *bxb, double 
 void launch_divb(const double *bxb, const double *byb, double *divb, const Geom &g, double dx, double dy,
                  cudaStream_t s);
 void launch_totals(const double *const planes[], int nplanes, const Geom &g, double *sums, cudaStream_t s);
-int flux_smem_bytes(int dir);
+int flux_chunk(int dir);          // faces per march step of the active launch variant
+int flux_lines_per_cta(int dir);  // lines across the sweep per CTA
 
 }  // namespace w5

@@ -48,6 +48,8 @@ W5_HD double fast_rcp(double x)
 #if defined(__CUDA_ARCH__)
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    // Newton steps from the hardware seed (relative error ~2^-23 or better): 2^-46, 2^-92 -> full
+    // precision after the second; the third is insurance against a coarser seed
     double e = fma(-x, r, 1.0);
     r = fma(r, e, r);
     e = fma(-x, r, 1.0);
@@ -60,12 +62,47 @@ W5_HD double fast_rcp(double x)
 #endif
 }
 
+// 1/sqrt(x) for normal x > 0, branch-free: hardware seed + two Newton steps (e -> 1.5 e^2).
+// IEEE sqrt()/division compile to a ~10-deep dependent chain fenced by a slow-path branch, which
+// stops ptxas from interleaving the eleven of them a face needs; these versions are plain
+// straight-line FMA code, accurate to ~1 ulp (not correctly rounded -- within the parity tolerance).
+W5_HD double fast_rsqrt(double x)
+{
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    double e = fma(-(hx * y), y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-(hx * y), y, 0.5);
+    y = fma(y, e, y);
+    return y;
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+
+// sqrt(x) for x >= 0 (0 and denormals give 0), branch-free
+W5_HD double fast_sqrt(double x)
+{
+#if defined(__CUDA_ARCH__)
+    const double xs = fmax(x, 1e-300);
+    const double y = fast_rsqrt(xs);
+    double s = xs * y;
+    const double d = fma(-s, s, xs);          // one correction step: s + d/(2s)
+    s = fma(d, 0.5 * y, s);
+    return x > 1e-300 ? s : 0.0;
+#else
+    return sqrt(x);
+#endif
+}
+
 // cons -> prim, cell-centre wave speeds and flux in the sweep frame
 // (Weno5_2D.jl:1573-1606, :1608-1667, :1533-1555).  q = [rho,M1,M2,M3,B1,B2,B3,E].
 W5_HD void cell_quantities(const double q[8], double gam, CellOut &o)
 {
     const double rho = q[0];
-    const double ri = 1.0 / rho;
+    const double ri = fast_rcp(rho);
     const double v1 = q[1] * ri, v2 = q[2] * ri, v3 = q[3] * ri;
     const double B1 = q[4], B2 = q[5], B3 = q[6], E = q[7];
     const double vv = v1 * v1 + v2 * v2 + v3 * v3;
@@ -75,10 +112,10 @@ W5_HD void cell_quantities(const double q[8], double gam, CellOut &o)
     const double bnx2 = fmax(0.0, B1 * B1 * ri);
     const double bbn2 = BB * ri;
     const double s = bbn2 + cs2;
-    const double root = sqrt(fmax(0.0, s * s - 4.0 * bnx2 * cs2));
-    o.lf = sqrt(fmax(0.0, 0.5 * (s + root)));
-    o.ls = sqrt(fmax(0.0, 0.5 * (s - root)));
-    o.la = sqrt(bnx2);
+    const double root = fast_sqrt(fmax(0.0, s * s - 4.0 * bnx2 * cs2));
+    o.lf = fast_sqrt(fmax(0.0, 0.5 * (s + root)));
+    o.ls = fast_sqrt(fmax(0.0, 0.5 * (s - root)));
+    o.la = fast_sqrt(bnx2);
     o.v1 = v1; o.v2 = v2; o.v3 = v3;
     const double pt = P + 0.5 * BB;
     const double vB = v1 * B1 + v2 * B2 + v3 * B3;
@@ -120,8 +157,9 @@ W5_HD void face_coefficients(double rhoL, double rhoR, double v1L, double v1R, d
     const double vx = 0.5 * (v1L + v1R), vy = 0.5 * (v2L + v2R), vz = 0.5 * (v3L + v3R);
     const double Bx = 0.5 * (B1L + B1R), By = 0.5 * (B2L + B2R), Bz = 0.5 * (B3L + B3R);
     const double E = 0.5 * (EL + ER);
-    const double ri = 1.0 / rho;
-    const double r = sqrt(rho);
+    const double rinv = fast_rsqrt(rho);                          // 1/sqrt(rho)
+    const double r = rho * rinv;
+    const double ri = rinv * rinv;
     const double Bt2 = By * By + Bz * Bz;
     const double B2 = Bx * Bx + Bt2;
     const double v2 = vx * vx + vy * vy + vz * vz;
@@ -129,26 +167,24 @@ W5_HD void face_coefficients(double rhoL, double rhoR, double v1L, double v1R, d
     const double bbn2 = B2 * ri;
     const double cs2 = fmax(0.0, gam * fabs(pg * ri));
     const double bnx2 = Bx * Bx * ri;
-    const double a = sqrt(cs2);
+    const double a = fast_sqrt(cs2);
     const double s_ = bbn2 + cs2;
-    const double root = sqrt(fmax(0.0, s_ * s_ - 4.0 * bnx2 * cs2));
-    const double cf = sqrt(fmax(0.0, 0.5 * (s_ + root)));
-    const double cs = sqrt(fmax(0.0, 0.5 * (s_ - root)));
+    const double root = fast_sqrt(fmax(0.0, s_ * s_ - 4.0 * bnx2 * cs2));
+    const double cf = fast_sqrt(fmax(0.0, 0.5 * (s_ + root)));
+    const double cs = fast_sqrt(fmax(0.0, 0.5 * (s_ - root)));
     const double sg = (Bx < 0.0) ? -1.0 : 1.0;                    // sign(Bx), 0 -> 1
-    double bty = 0.70710678118654752440, btz = 0.70710678118654752440;
-    if (Bt2 > 1e-30) {
-        const double ib = 1.0 / sqrt(Bt2);
-        bty = By * ib; btz = Bz * ib;
-    }
+    // degenerate cases are resolved with selects, not branches (Weno5_2D.jl:1337-1359)
+    const bool tang = Bt2 > 1e-30;
+    const double ib = fast_rsqrt(tang ? Bt2 : 1.0);
+    const double bty = tang ? By * ib : 0.70710678118654752440;
+    const double btz = tang ? Bz * ib : 0.70710678118654752440;
     const double dl2 = cf * cf - cs * cs;
-    double af = 1.0, as_ = 1.0;
-    if (dl2 >= 1e-30) {
-        const double id = 1.0 / dl2;
-        af = sqrt(fmax(0.0, cs2 - cs * cs) * id);
-        as_ = sqrt(fmax(0.0, cf * cf - cs2) * id);
-    }
+    const bool split = dl2 >= 1e-30;
+    const double id = fast_rcp(split ? dl2 : 1.0);
+    const double af = split ? fast_sqrt(fmax(0.0, cs2 - cs * cs) * id) : 1.0;
+    const double as_ = split ? fast_sqrt(fmax(0.0, cf * cf - cs2) * id) : 1.0;
     const double sig = bty * vy + btz * vz;
-    const double ih = 0.5 / cs2;                                   // 1/(2 a^2)
+    const double ih = 0.5 * fast_rcp(cs2);                         // 1/(2 a^2)
     const double afcf = af * cf, ascs = as_ * cs;
 
     c.hv2 = 0.5 * v2; c.vx = vx; c.vy = vy; c.vz = vz; c.By = By; c.Bz = Bz;
@@ -168,8 +204,7 @@ W5_HD void face_coefficients(double rhoL, double rhoR, double v1L, double v1R, d
     c.ka_4 = 0.5 * bty;
     c.kb_5 = -0.5 * sg * r * btz;
     c.kb_6 = 0.5 * sg * r * bty;
-    c.ke_n = -g0 / cs2;
-    const double rinv = r * ri;                                    // 1/sqrt(rho)
+    c.ke_n = -2.0 * g0 * ih;
     c.af = af; c.as_ = as_; c.afcf = afcf; c.ascs = ascs;
     c.a_r = a * rinv; c.s_r = sg * rinv; c.sgn = sg; c.sig = sig;
     const double h = 0.5 * v2 - g2 * cs2;
@@ -196,8 +231,22 @@ W5_HD void project(const FaceCoef &c, const double x[7], double w[7])
     w[3] = fma(c.ke_n, n, x[0]);
 }
 
+// Back-projection coefficients only (the part of FaceCoef that is cold during the stencil
+// streaming); kept separate so that a kernel can park them in shared memory.
+struct BackCoef {
+    double vx, vy, vz, bty, btz, hv2;
+    double af, as_, afcf, ascs, a_r, s_r, sgn, sig, hf, hs, axy;
+};
+
+W5_HD void split_back(const FaceCoef &c, BackCoef &b)
+{
+    b.vx = c.vx; b.vy = c.vy; b.vz = c.vz; b.bty = c.bty; b.btz = c.btz; b.hv2 = c.hv2;
+    b.af = c.af; b.as_ = c.as_; b.afcf = c.afcf; b.ascs = c.ascs; b.a_r = c.a_r; b.s_r = c.s_r;
+    b.sgn = c.sgn; b.sig = c.sig; b.hf = c.hf; b.hs = c.hs; b.axy = c.axy;
+}
+
 // fhat = R . Fs without forming R (Weno5_2D.jl:1879-1888 with :1428-1486)
-W5_HD void back_project(const FaceCoef &c, const double Fs[7], double fh[7])
+W5_HD void back_project(const BackCoef &c, const double Fs[7], double fh[7])
 {
     const double Sf = Fs[0] + Fs[6], Df = Fs[6] - Fs[0];
     const double Ss = Fs[2] + Fs[4], Ds = Fs[4] - Fs[2];
@@ -241,15 +290,26 @@ W5_HD double weno_phi2(double A, double B, double C, double D, double eps4)
     return fma(om0 * (1.0 / 3.0), D1, (om2 - 0.5) * (1.0 / 6.0) * D2);
 }
 
+// No-op stash: everything stays in registers (host tests, and the reference point for the
+// kernel's shared-memory stash).
+struct RegStash {
+    double q[4][7], first[7];
+    W5_HD void put_q(int k, int m, double v) { q[k][m] = v; }
+    W5_HD double get_q(int k, int m) const { return q[k][m]; }
+    W5_HD void put_first(int m, double v) { first[m] = v; }
+    W5_HD double get_first(int m) const { return first[m]; }
+};
+
 // Numerical flux of one face.  load(k, F, q) fills the flux and conserved 7-vectors of
 // stencil cell k = 0..5 (cells f-2 .. f+3); amax[m] = max(|a_m(f)|, |a_m(f+1)|)
-// (Weno5_2D.jl:1834).  Streams over the stencil so that only the 8 Lax-Friedrichs split
-// differences per field are live, not the 84 stencil operands.
-template <class Loader>
-W5_HD void face_flux(const FaceCoef &c, const double amax[7], double eps, Loader load, double fh[7])
+// (Weno5_2D.jl:1834).  Streams over the stencil so that only the Lax-Friedrichs split
+// differences are live, not the 84 stencil operands.  The minus-side differences Q and the
+// central term `first` are only needed after the streaming loop; they go through `stash`
+// (registers, or thread-private shared memory in the kernel) to keep register pressure down.
+template <class Loader, class Stash>
+W5_HD void face_flux(const FaceCoef &c, const double amax[7], double eps, Loader load, Stash &stash, double Fs[7])
 {
-    double P[4][7], Q[4][7];       // P[k] = dw_k + amax dv_k (k=0..3), Q[k-1] = dw_k - amax dv_k (k=1..4)
-    double first[7];
+    double P[4][7];                // P[k-1] = dw_k + amax dv_k (k=1..4); stash.q[k-2] = dw_k - amax dv_k (k=2..5)
     double wp[7], vp[7];
     {
         double F[7], q[7];
@@ -267,23 +327,21 @@ W5_HD void face_flux(const FaceCoef &c, const double amax[7], double eps, Loader
         for (int m = 0; m < 7; ++m) {
             const double dw = w[m] - wp[m], dv = v[m] - vp[m];
             if (k <= 4) P[k - 1][m] = fma(amax[m], dv, dw);
-            if (k >= 2) Q[k - 2][m] = fma(-amax[m], dv, dw);
-            // first = (-w1 + 7 w2 + 7 w3 - w4)/12, Weno5_2D.jl:1827
-            if (k == 1) first[m] = -w[m];
-            if (k == 2 || k == 3) first[m] = fma(7.0, w[m], first[m]);
-            if (k == 4) first[m] -= w[m];
+            if (k >= 2) stash.put_q(k - 2, m, fma(-amax[m], dv, dw));
+            // first = (-w1 + 7 w2 + 7 w3 - w4)/12, Weno5_2D.jl:1827, accumulated as
+            // 7 (w2 + w3) - (w1 + w4)
+            if (k == 2) stash.put_first(m, fma(7.0, w[m], -wp[m]));                 // 7 w2 - w1
+            if (k == 4) stash.put_first(m, fma(7.0, wp[m], stash.get_first(m)) - w[m]);   // + 7 w3 - w4
             wp[m] = w[m]; vp[m] = v[m];
         }
     }
     const double eps4 = 4.0 * eps;
-    double Fs[7];
 #pragma unroll
     for (int m = 0; m < 7; ++m) {
         const double second2 = weno_phi2(P[0][m], P[1][m], P[2][m], P[3][m], eps4);
-        const double third2 = weno_phi2(Q[3][m], Q[2][m], Q[1][m], Q[0][m], eps4);
-        Fs[m] = fma(first[m], 1.0 / 12.0, 0.5 * (third2 - second2));
+        const double third2 = weno_phi2(stash.get_q(3, m), stash.get_q(2, m), stash.get_q(1, m), stash.get_q(0, m), eps4);
+        Fs[m] = fma(stash.get_first(m), 1.0 / 12.0, 0.5 * (third2 - second2));
     }
-    back_project(c, Fs, fh);
 }
 
 W5_HD void face_amax(double v1L, double lfL, double laL, double lsL,

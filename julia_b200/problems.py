@@ -138,6 +138,11 @@ def _assemble(g, rho, vx, vy, vz, Bz, P, Az_corner=None, Bx_uniform=0.0, By_unif
     q = np.zeros((Nx, Ny, 9), order="F")
     for c, f in enumerate(fields):
         q[:, :, c] = f
+    # ghost cells are exact copies of the cells the boundary condition maps them to
+    # (what boundaries! would produce), not the formula evaluated outside the domain
+    for c in range(9):
+        _wrap_fill(q[:, :, c], 0, g.bc_x)
+        _wrap_fill(q[:, :, c], 1, g.bc_y)
     return q, bxb, byb
 
 

@@ -1,0 +1,40 @@
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def built():
+    """Compile the product library (nvcc cross-compiles without a GPU) and the oracle."""
+    import __graft_entry__ as ge
+    ge.build()
+    return True
+
+
+@pytest.fixture(scope="session")
+def hostmath():
+    """Host build of the product's per-face arithmetic (julia_b200/csrc/weno5_math.cuh)."""
+    import ctypes as C
+    d = os.path.join(ROOT, "tests", "hostmath")
+    so, src = os.path.join(d, "libhostmath.so"), os.path.join(d, "hostmath.cpp")
+    hdr = os.path.join(ROOT, "julia_b200", "csrc", "weno5_math.cuh")
+    if (not os.path.exists(so)) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.check_call([cxx, "-std=c++17", "-O2", "-mfma", "-fPIC", "-shared", "-o", so, src])
+    lib = C.CDLL(so)
+    dp = C.POINTER(C.c_double)
+    lib.hm_sweep.argtypes = [C.c_int, C.c_int, dp, C.c_int, C.c_int, C.c_double, C.c_double, dp, dp]
+    for f in (lib.hm_e2s, lib.hm_s2e):
+        f.restype = C.c_double
+        f.argtypes = [C.c_double] * 9
+    return lib

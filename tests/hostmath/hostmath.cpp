@@ -53,7 +53,12 @@ int hm_sweep(int Nx, int Ny, const double *q, int dir, int bc, double gam, doubl
                 const double *cc = &cq[(size_t)s * w5::CQ_COUNT];
                 for (int m = 0; m < 7; ++m) { F[m] = cc[w5::CQ_F0 + m]; x[m] = cc[w5::CQ_Q0 + m]; }
             };
-            w5::face_flux(c, amax, eps, load, &fh[(size_t)f * 7]);
+            w5::RegStash stash;
+            double Fs[7];
+            w5::face_flux(c, amax, eps, load, stash, Fs);
+            w5::BackCoef bc_;
+            w5::split_back(c, bc_);
+            w5::back_project(bc_, Fs, &fh[(size_t)f * 7]);
             const double b = dir ? fh[(size_t)f * 7 + 5] + 0.5 * (L[w5::CQ_B1] * L[w5::CQ_V3] + R[w5::CQ_B1] * R[w5::CQ_V3])
                                  : fh[(size_t)f * 7 + 4] + 0.5 * (L[w5::CQ_B1] * L[w5::CQ_V2] + R[w5::CQ_B1] * R[w5::CQ_V2]);
             const size_t g = dir ? (size_t)p + (size_t)Nx * f : (size_t)f + (size_t)Nx * p;
