@@ -243,10 +243,10 @@ extern "C" int weno5_create(const weno5_params *P, int device, int ny_local, int
     CU(cudaMalloc(&c->sums, 16 * sizeof(double)));
     CU(cudaMallocHost(&c->h_ctl, 16 * sizeof(double)));
 
-    choose_segments(g.NXI - 4, flux_chunk(0), (g.NYI + flux_lines_per_cta(0) - 1) / flux_lines_per_cta(0),
+    choose_segments(g.NXI - 5, flux_chunk(0), (g.NYI + flux_lines_per_cta(0) - 1) / flux_lines_per_cta(0),
                     c->segx_len, c->nsegx);
     if (!is1d)
-        choose_segments(g.NYI - 4, flux_chunk(1), (g.NXI + flux_lines_per_cta(1) - 1) / flux_lines_per_cta(1),
+        choose_segments(g.NYI - 5, flux_chunk(1), (g.NXI + flux_lines_per_cta(1) - 1) / flux_lines_per_cta(1),
                         c->segy_len, c->nsegy);
     CU(cudaStreamSynchronize(c->stream));
     *out = c;

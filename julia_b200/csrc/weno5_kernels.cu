@@ -31,12 +31,22 @@ template <int DIR, int NT> struct Tile {
     static constexpr int NPB = DIR == 0 ? NT / 64 : 32;    // lines across the sweep per CTA
     static constexpr int CBS = (NS + 5) * NPB;             // cell-buffer entries per quantity
     static constexpr int FBS = (NS + 1) * NPB;             // face-flux-buffer entries per component
-    static constexpr int SMEM = (CQ_COUNT * CBS + 7 * FBS) * (int)sizeof(double);
+    static constexpr int STQ = 8 * NT;                     // staged raw state of the next chunk
+    static constexpr int STU = DIR == 0 ? 0 : 18 * NT;     // staged RK operands (rhs, base, acc)
+    static constexpr int SMEM = (CQ_COUNT * CBS + 7 * FBS + STQ + STU) * (int)sizeof(double);
     __device__ static __forceinline__ int cbi(int slot, int p) { return DIR == 0 ? p * (NS + 5) + slot : slot * NPB + p; }
     __device__ static __forceinline__ int fbi(int slot, int p) { return DIR == 0 ? p * (NS + 1) + slot : slot * NPB + p; }
 };
 
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// Ampere-style asynchronous copy global -> shared (LDGSTS): no register staging, so the loads of
+// the NEXT march step and of the RK operands fly while the FP64 pipe works on the current faces.
+__device__ __forceinline__ void cp_async8(double *smem, const double *gmem)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Thread-private column of shared memory for the operands that are cold while the stencil is
 // streamed (minus-side differences, central term, back-projection coefficients).  With 250+
@@ -67,19 +77,21 @@ static_assert(sizeof(BackCoef) == STASH_BACK * sizeof(double), "BackCoef layout"
 
 constexpr int stash_slots(int level) { return level == 0 ? 0 : (level == 1 ? STASH_Q + STASH_FIRST : STASH_Q + STASH_FIRST + STASH_BACK); }
 
-// cons->prim, eigenvalues, flux of one cell -> shared memory slot
+// global index of sweep cell c on line `line` (clamped: cells past the array are never used by an
+// owned face, they only have to be finite)
+template <int DIR>
+__device__ __forceinline__ size_t cell_index(const FluxArgs &a, int c, int line)
+{
+    const int cc = min(c, a.N - 1), ll = min(line, a.NP - 1);
+    return DIR == 0 ? (size_t)cc + (size_t)a.pitch * ll : (size_t)ll + (size_t)a.pitch * cc;
+}
+
+// cons->prim, eigenvalues, flux of one cell -> shared memory slot.  q is in the sweep frame.
 template <int DIR, int NT>
-__device__ __forceinline__ void cell_phase(const FluxArgs &a, double *cb, int c, int line, int slot, int p)
+__device__ __forceinline__ void cell_store(const FluxArgs &a, double *cb, const double q[8], int slot, int p)
 {
     using T = Tile<DIR, NT>;
     constexpr int CBS = T::CBS;
-    // sweep-frame component c reads physical plane in[c]: (x,y,z) -> (y,z,x) for the y sweep
-    constexpr int in[8] = {0, DIR ? 2 : 1, DIR ? 3 : 2, DIR ? 1 : 3, DIR ? 5 : 4, DIR ? 6 : 5, DIR ? 4 : 6, 7};
-    const int cc = min(c, a.N - 1), ll = min(line, a.NP - 1);
-    const size_t g = DIR == 0 ? (size_t)cc + (size_t)a.pitch * ll : (size_t)ll + (size_t)a.pitch * cc;
-    double q[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) q[k] = __ldg(a.qc[in[k]] + g);
     CellOut o;
     cell_quantities(q, a.gam, o);
     const int i = T::cbi(slot, p);
@@ -101,6 +113,23 @@ __device__ __forceinline__ void cell_phase(const FluxArgs &a, double *cb, int c,
     cb[CQ_LS * CBS + i] = o.ls;
 }
 
+// sweep-frame component k reads physical plane perm<DIR>(k): (x,y,z) -> (y,z,x) for the y sweep
+template <int DIR> __device__ __forceinline__ constexpr int perm(int k)
+{
+    constexpr int px[8] = {0, 1, 2, 3, 4, 5, 6, 7}, py[8] = {0, 2, 3, 1, 5, 6, 4, 7};
+    return DIR ? py[k] : px[k];
+}
+
+template <int DIR, int NT>
+__device__ __forceinline__ void cell_phase(const FluxArgs &a, double *cb, int c, int line, int slot, int p)
+{
+    const size_t g = cell_index<DIR>(a, c, line);
+    double q[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) q[k] = __ldg(a.qc[perm<DIR>(k)] + g);
+    cell_store<DIR, NT>(a, cb, q, slot, p);
+}
+
 template <int DIR, int NT, int MINB, int STASH>
 __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a)
 {
@@ -111,7 +140,9 @@ __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a)
     extern __shared__ double sm[];
     double *cb = sm;
     double *fb = sm + CQ_COUNT * CBS;
-    double *stash_base = fb + 7 * FBS;
+    double *stq = fb + 7 * FBS;                  // [8][NT]   raw state of the next chunk (cp.async)
+    double *stu = stq + T::STQ;                  // [18][NT]  rhs, base, acc of this chunk (y sweep)
+    double *stash_base = stu + T::STU;
 
     const double dt = *a.dtp;
     if (dt == 0.0) return;                       // advance() past tmax: leave the state untouched
@@ -125,37 +156,52 @@ __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a)
     // this CTA owns faces [fA, fB) of its lines; it starts one face early (seg > 0) so that the
     // first owned cell has both of its faces
     const int fA = 2 + seg * a.seg_len;
-    const int fB = min(fA + a.seg_len, a.N - 2);
+    const int fB = min(fA + a.seg_len, a.N - 3);           // last face N-4: its stencil ends at cell N-1
     const int fStart = seg == 0 ? fA : fA - 1;
 
     const bool line_ok = a.is1d ? (line == 0) : (line >= G && line < a.NP - G);
 
+    // stage the first chunk, then the 5 carry cells directly
+    {
+        const size_t g0 = cell_index<DIR>(a, fStart + 3 + s, line);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cp_async8(stq + k * NT + t, a.qc[perm<DIR>(k)] + g0);
+        cp_async_commit();
+    }
     if (s < 5) cell_phase<DIR, NT>(a, cb, fStart - 2 + s, line, s, p);
 
     for (int s0 = fStart; s0 < fB; s0 += NS) {
-        cell_phase<DIR, NT>(a, cb, s0 + 3 + s, line, 5 + s, p);
+        // ---------------- cell phase from the staged state (each thread reads back its own copies)
+        cp_async_wait<0>();
+        {
+            double q[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) q[k] = stq[k * NT + t];
+            cell_store<DIR, NT>(a, cb, q, 5 + s, p);
+        }
         __syncthreads();
 
-        // pull what the next ~2000 instructions will need towards L2: the next chunk's cells and,
-        // in the y sweep, this chunk's RK operands
-        {
-            const int cn = min(s0 + NS + 3 + s, a.N - 1), ll = min(line, a.NP - 1);
-            const size_t gn = DIR == 0 ? (size_t)cn + (size_t)a.pitch * ll : (size_t)ll + (size_t)a.pitch * cn;
-            if (s0 + NS < fB) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) prefetch_l2(a.qc[k] + gn);
-            }
-            if constexpr (DIR == 1) {
-                const int cu = min(s0 + s, a.N - 1);
-                const size_t gu = (size_t)ll + (size_t)a.pitch * cu;
+        // ---------------- asynchronous copies that fly under the face phase:
+        // group A = this chunk's RK operands (y sweep), group B = the next chunk's state
+        const bool upd_ok = (s0 + s > fStart) && (s0 + s < fB) && (s0 + s >= G) && (s0 + s < a.N - G) && line_ok;
+        if constexpr (DIR == 1) {
+            if (upd_ok) {
+                const size_t gu = (size_t)line + (size_t)a.pitch * (s0 + s);
 #pragma unroll
                 for (int m = 0; m < 6; ++m) {
-                    prefetch_l2(a.rhs[m] + gu);
-                    if (a.stage <= 3) prefetch_l2(a.base[m] + gu);
-                    if (a.stage >= 3) prefetch_l2(a.acc[m] + gu);
+                    cp_async8(stu + m * NT + t, a.rhs[m] + gu);
+                    if (a.stage <= 3) cp_async8(stu + (6 + m) * NT + t, a.base[m] + gu);
+                    if (a.stage >= 3) cp_async8(stu + (12 + m) * NT + t, a.acc[m] + gu);
                 }
             }
         }
+        cp_async_commit();
+        if (s0 + NS < fB) {
+            const size_t gn = cell_index<DIR>(a, s0 + NS + 3 + s, line);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cp_async8(stq + k * NT + t, a.qc[perm<DIR>(k)] + gn);
+        }
+        cp_async_commit();
 
         // ---------------- face phase: face f between cells f and f+1 (slots s+2, s+3)
         const int f = s0 + s;
@@ -208,7 +254,8 @@ __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a)
         // ---------------- update phase: cell c with faces c-1 (slot s) and c (slot s+1)
         {
             const int c = s0 + s;
-            if (c > fStart && c < fB && c >= G && c < a.N - G && line_ok) {
+            if constexpr (DIR == 1) cp_async_wait<1>();          // group A has landed
+            if (upd_ok) {
                 const int i0 = T::fbi(s, p), i1 = T::fbi(s + 1, p);
                 const size_t g = DIR == 0 ? (size_t)c + (size_t)a.pitch * line : (size_t)line + (size_t)a.pitch * c;
                 if constexpr (DIR == 0) {
@@ -221,23 +268,17 @@ __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a)
                     constexpr int fi[6] = {0, 3, 1, 2, 4, 6};
                     const int ic = T::cbi(s + 2, p);
                     const double cx = a.c_dx * dt, cy = a.c_dy * dt;
-                    // all global operands first (one exposed latency instead of twelve)
-                    double rx[6], bb[6], ac[6];
-#pragma unroll
-                    for (int m = 0; m < 6; ++m) {
-                        rx[m] = __ldcs(a.rhs[m] + g);
-                        bb[m] = a.stage <= 3 ? __ldg(a.base[m] + g) : 0.0;
-                        ac[m] = a.stage >= 3 ? __ldcs(a.acc[m] + g) : 0.0;
-                    }
 #pragma unroll
                     for (int m = 0; m < 6; ++m) {
                         const double dfy = fb[fi[m] * FBS + i1] - fb[fi[m] * FBS + i0];
                         const double qcen = cb[(CQ_Q0 + fi[m]) * CBS + ic];
-                        double b = bb[m];
+                        const double rxm = stu[m * NT + t];
+                        double b = a.stage <= 3 ? stu[(6 + m) * NT + t] : 0.0;
+                        const double acm = a.stage >= 3 ? stu[(12 + m) * NT + t] : 0.0;
                         if (a.stage == 2) a.acc[m][g] = qcen - b;                       // -q0 + q1
-                        if (a.stage == 3) a.acc[m][g] = fma(2.0, qcen, ac[m]);          // + 2 q2
-                        if (a.stage == 4) b = (ac[m] + qcen) * (1.0 / 3.0);             // Weno5_2D.jl:279
-                        a.qn[m][g] = fma(-cx, rx[m], fma(-cy, dfy, b));
+                        if (a.stage == 3) a.acc[m][g] = fma(2.0, qcen, acm);            // + 2 q2
+                        if (a.stage == 4) b = (acm + qcen) * (1.0 / 3.0);               // Weno5_2D.jl:279
+                        a.qn[m][g] = fma(-cx, rxm, fma(-cy, dfy, b));
                     }
                 }
             }
@@ -261,11 +302,9 @@ __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a)
 
 // Launch variants (CTA size, resident CTAs per SM -> register budget, stash level); chosen once
 // per process by WENO5_FLUX_VARIANT (development knob; the default is the fastest measured on B200).
-//   0: 256 thr, 252 regs, no stash          1: 256 thr, stash Q+first+back
-//   2: 384 thr, 168 regs, stash Q+first      3: 320 thr, 204 regs, stash Q+first
-//   4: 256 thr, stash Q+first
+//   0: 256 threads, everything in registers (252)   1: 256 threads, Q + first parked in shared memory
 struct Variant { int nt, stash; };
-static const Variant kVariants[5] = {{256, 0}, {256, 2}, {384, 1}, {320, 1}, {256, 1}};
+static const Variant kVariants[2] = {{256, 0}, {256, 1}};
 
 static int flux_variant()
 {
@@ -273,7 +312,7 @@ static int flux_variant()
     if (v < 0) {
         const char *e = getenv("WENO5_FLUX_VARIANT");
         v = e ? atoi(e) : W5_DEFAULT_VARIANT;
-        if (v < 0 || v > 4) v = W5_DEFAULT_VARIANT;
+        if (v < 0 || v > 1) v = W5_DEFAULT_VARIANT;
     }
     return v;
 }
@@ -297,11 +336,8 @@ template <int DIR>
 static void launch_flux(const FluxArgs &a, cudaStream_t s)
 {
     switch (flux_variant()) {
-    case 0: launch_flux_t<DIR, 256, 1, 0>(a, s); break;
-    case 1: launch_flux_t<DIR, 256, 1, 2>(a, s); break;
-    case 2: launch_flux_t<DIR, 384, 1, 1>(a, s); break;
-    case 3: launch_flux_t<DIR, 320, 1, 1>(a, s); break;
-    default: launch_flux_t<DIR, 256, 1, 1>(a, s); break;
+    case 1: launch_flux_t<DIR, 256, 1, 1>(a, s); break;
+    default: launch_flux_t<DIR, 256, 1, 0>(a, s); break;
     }
 }
 

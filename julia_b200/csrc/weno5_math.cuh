@@ -267,27 +267,31 @@ W5_HD void back_project(const BackCoef &c, const double Fs[7], double fh[7])
 }
 
 // One side of the Jiang & Wu correction (Weno5_2D.jl:1836-1853) for UNHALVED inputs
-// A = 2a, ... : the smoothness indicators scale by exactly 4 (power of two, no rounding
-// change), so eps4 = 4 eps gives bit-identical ratios; the returned value is 2 phi.
-// omega0 = al0/(al0+al1+al2) with al = (1,6,3)/d_k, d_k = (eps+IS_k)^2, rewritten over the
-// common denominator so that a single reciprocal is needed.
-W5_HD double weno_phi2(double A, double B, double C, double D, double eps4)
+// A = 2a, B = 2b, ...; returns 2 phi.
+//  * smoothness indicators as quadratic forms, scaled by 1/16:
+//      IS0 = 13(a-b)^2 + 3(a-3b)^2 = 16 a^2 - 44 ab + 40 b^2   ->  A(A - 2.75 B) + 2.5 B^2
+//      IS1 = 13(b-c)^2 + 3(b+c)^2  = 16 b^2 - 20 bc + 16 c^2   ->  B(B - 1.25 C) + C^2
+//      IS2 = 13(c-d)^2 + 3(3c-d)^2 = 40 c^2 - 44 cd + 16 d^2   ->  D(D - 2.75 C) + 2.5 C^2
+//    (10 operations instead of 18).  With unhalved inputs these are IS_k/4, so eps is passed as
+//    eps/4 and the weight ratios are unchanged.
+//  * omega0 = al0/(al0+al1+al2), al = (1,6,3)/d_k, d_k = (eps+IS_k)^2, written over the common
+//    denominator so that a single reciprocal replaces five divisions.
+// Algebraically identical to the reference; differs in round-off only.
+W5_HD double weno_phi2(double A, double B, double C, double D, double epsq)
 {
-    double t1 = A - B, t2 = fma(-3.0, B, A);
-    const double IS0 = fma(13.0 * t1, t1, 3.0 * (t2 * t2));
-    t1 = B - C; t2 = B + C;
-    const double IS1 = fma(13.0 * t1, t1, 3.0 * (t2 * t2));
-    t1 = C - D; t2 = fma(3.0, C, -D);
-    const double IS2 = fma(13.0 * t1, t1, 3.0 * (t2 * t2));
-    double d0 = eps4 + IS0, d1 = eps4 + IS1, d2 = eps4 + IS2;
+    const double BB = B * B, CC = C * C;
+    const double IS0 = fma(A, fma(-2.75, B, A), 2.5 * BB);
+    const double IS1 = fma(B, fma(-1.25, C, B), CC);
+    const double IS2 = fma(D, fma(-2.75, C, D), 2.5 * CC);
+    double d0 = epsq + IS0, d1 = epsq + IS1, d2 = epsq + IS2;
     d0 *= d0; d1 *= d1; d2 *= d2;
     const double p12 = d1 * d2, p02 = d0 * d2, p01 = d0 * d1;
     const double inv = fast_rcp(fma(6.0, p02, fma(3.0, p01, p12)));
-    const double om0 = p12 * inv;
-    const double om2 = 3.0 * p01 * inv;
+    const double om0_3 = p12 * inv * (1.0 / 3.0);                   // omega0 / 3
+    const double om2_6 = fma(p01 * inv, 0.5, -1.0 / 12.0);          // (omega2 - 1/2) / 6
     const double D1 = fma(-2.0, B, A) + C;
     const double D2 = fma(-2.0, C, B) + D;
-    return fma(om0 * (1.0 / 3.0), D1, (om2 - 0.5) * (1.0 / 6.0) * D2);
+    return fma(om0_3, D1, om2_6 * D2);
 }
 
 // No-op stash: everything stays in registers (host tests, and the reference point for the
@@ -335,11 +339,11 @@ W5_HD void face_flux(const FaceCoef &c, const double amax[7], double eps, Loader
             wp[m] = w[m]; vp[m] = v[m];
         }
     }
-    const double eps4 = 4.0 * eps;
+    const double epsq = 0.25 * eps;
 #pragma unroll
     for (int m = 0; m < 7; ++m) {
-        const double second2 = weno_phi2(P[0][m], P[1][m], P[2][m], P[3][m], eps4);
-        const double third2 = weno_phi2(stash.get_q(3, m), stash.get_q(2, m), stash.get_q(1, m), stash.get_q(0, m), eps4);
+        const double second2 = weno_phi2(P[0][m], P[1][m], P[2][m], P[3][m], epsq);
+        const double third2 = weno_phi2(stash.get_q(3, m), stash.get_q(2, m), stash.get_q(1, m), stash.get_q(0, m), epsq);
         Fs[m] = fma(stash.get_first(m), 1.0 / 12.0, 0.5 * (third2 - second2));
     }
 }
