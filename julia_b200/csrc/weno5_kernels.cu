@@ -18,23 +18,25 @@
 #include <cstdlib>
 
 #ifndef W5_DEFAULT_VARIANT
-#define W5_DEFAULT_VARIANT 0
+#define W5_DEFAULT_VARIANT 2
 #endif
 
 namespace w5 {
 
 // A CTA of NT threads handles a chunk of NT faces per march step: DIR 0 (x sweep) NT/64 rows of
-// 64 faces, DIR 1 (y sweep) NT/32 face rows of 32 columns -- lanes always run along x so that
-// global accesses are coalesced in both sweeps.
-template <int DIR, int NT> struct Tile {
-    static constexpr int NS = DIR == 0 ? 64 : NT / 32;     // faces along the sweep per chunk
-    static constexpr int NPB = DIR == 0 ? NT / 64 : 32;    // lines across the sweep per CTA
-    static constexpr int CBS = (NS + 5) * NPB;             // cell-buffer entries per quantity
+// 64 faces, DIR 1 (y sweep) NT/YW face rows of YW columns -- lanes always run along x so that
+// global accesses are coalesced in both sweeps.  Cell data lives in a ring of RS = NS + 5 slots
+// along the sweep (the 5 trailing stencil cells of a chunk stay where they are for the next one).
+template <int DIR, int NT, int YW> struct Tile {
+    static constexpr int NS = DIR == 0 ? 64 : NT / YW;     // faces along the sweep per chunk
+    static constexpr int NPB = DIR == 0 ? NT / 64 : YW;    // lines across the sweep per CTA
+    static constexpr int RS = NS + 5;                      // ring slots along the sweep
+    static constexpr int CBS = RS * NPB;                   // cell-buffer entries per quantity
     static constexpr int FBS = (NS + 1) * NPB;             // face-flux-buffer entries per component
     static constexpr int STQ = 8 * NT;                     // staged raw state of the next chunk
     static constexpr int STU = DIR == 0 ? 0 : 18 * NT;     // staged RK operands (rhs, base, acc)
     static constexpr int SMEM = (CQ_COUNT * CBS + 7 * FBS + STQ + STU) * (int)sizeof(double);
-    __device__ static __forceinline__ int cbi(int slot, int p) { return DIR == 0 ? p * (NS + 5) + slot : slot * NPB + p; }
+    __device__ static __forceinline__ int cbi(int slot, int p) { return DIR == 0 ? p * RS + slot : slot * NPB + p; }
     __device__ static __forceinline__ int fbi(int slot, int p) { return DIR == 0 ? p * (NS + 1) + slot : slot * NPB + p; }
 };
 
@@ -48,35 +50,6 @@ __device__ __forceinline__ void cp_async8(double *smem, const double *gmem)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Thread-private column of shared memory for the operands that are cold while the stencil is
-// streamed (minus-side differences, central term, back-projection coefficients).  With 250+
-// registers per thread only one CTA fits on an SM, which leaves > 100 KB of shared memory idle:
-// parking ~50 doubles per thread there is what lets ptxas keep the streaming loop free of
-// spills at a lower register count.  Slot-major layout: consecutive lanes hit consecutive banks.
-constexpr int STASH_Q = 28, STASH_FIRST = 7, STASH_BACK = 17;
-template <int NT, int LEVEL> struct SmemStash {
-    volatile double *b;
-    __device__ __forceinline__ void put_q(int k, int m, double v) { b[(k * 7 + m) * NT] = v; }
-    __device__ __forceinline__ double get_q(int k, int m) const { return b[(k * 7 + m) * NT]; }
-    __device__ __forceinline__ void put_first(int m, double v) { b[(STASH_Q + m) * NT] = v; }
-    __device__ __forceinline__ double get_first(int m) const { return b[(STASH_Q + m) * NT]; }
-    __device__ __forceinline__ void put_back(const BackCoef &c)
-    {
-        const double *src = reinterpret_cast<const double *>(&c);
-#pragma unroll
-        for (int i = 0; i < STASH_BACK; ++i) b[(STASH_Q + STASH_FIRST + i) * NT] = src[i];
-    }
-    __device__ __forceinline__ void get_back(BackCoef &c) const
-    {
-        double *dst = reinterpret_cast<double *>(&c);
-#pragma unroll
-        for (int i = 0; i < STASH_BACK; ++i) dst[i] = b[(STASH_Q + STASH_FIRST + i) * NT];
-    }
-};
-static_assert(sizeof(BackCoef) == STASH_BACK * sizeof(double), "BackCoef layout");
-
-constexpr int stash_slots(int level) { return level == 0 ? 0 : (level == 1 ? STASH_Q + STASH_FIRST : STASH_Q + STASH_FIRST + STASH_BACK); }
-
 // global index of sweep cell c on line `line` (clamped: cells past the array are never used by an
 // owned face, they only have to be finite)
 template <int DIR>
@@ -86,15 +59,12 @@ __device__ __forceinline__ size_t cell_index(const FluxArgs &a, int c, int line)
     return DIR == 0 ? (size_t)cc + (size_t)a.pitch * ll : (size_t)ll + (size_t)a.pitch * cc;
 }
 
-// cons->prim, eigenvalues, flux of one cell -> shared memory slot.  q is in the sweep frame.
-template <int DIR, int NT>
-__device__ __forceinline__ void cell_store(const FluxArgs &a, double *cb, const double q[8], int slot, int p)
+// cons->prim, eigenvalues, flux of one cell -> shared memory entry i.  q is in the sweep frame.
+template <int CBS>
+__device__ __forceinline__ void cell_store(const FluxArgs &a, double *cb, const double q[8], int i)
 {
-    using T = Tile<DIR, NT>;
-    constexpr int CBS = T::CBS;
     CellOut o;
     cell_quantities(q, a.gam, o);
-    const int i = T::cbi(slot, p);
 #pragma unroll
     for (int m = 0; m < 7; ++m) cb[(CQ_F0 + m) * CBS + i] = o.F[m];
     cb[(CQ_Q0 + 0) * CBS + i] = q[0];
@@ -120,29 +90,17 @@ template <int DIR> __device__ __forceinline__ constexpr int perm(int k)
     return DIR ? py[k] : px[k];
 }
 
-template <int DIR, int NT>
-__device__ __forceinline__ void cell_phase(const FluxArgs &a, double *cb, int c, int line, int slot, int p)
-{
-    const size_t g = cell_index<DIR>(a, c, line);
-    double q[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) q[k] = __ldg(a.qc[perm<DIR>(k)] + g);
-    cell_store<DIR, NT>(a, cb, q, slot, p);
-}
-
-template <int DIR, int NT, int MINB, int STASH>
+template <int DIR, int NT, int YW, int MINB>
 __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a)
 {
-    using T = Tile<DIR, NT>;
-    constexpr int NTHREADS = NT;
-    constexpr int NS = T::NS, NPB = T::NPB;
+    using T = Tile<DIR, NT, YW>;
+    constexpr int NS = T::NS, NPB = T::NPB, RS = T::RS;
     constexpr int CBS = T::CBS, FBS = T::FBS;
     extern __shared__ double sm[];
     double *cb = sm;
     double *fb = sm + CQ_COUNT * CBS;
     double *stq = fb + 7 * FBS;                  // [8][NT]   raw state of the next chunk (cp.async)
     double *stu = stq + T::STQ;                  // [18][NT]  rhs, base, acc of this chunk (y sweep)
-    double *stash_base = stu + T::STU;
 
     const double dt = *a.dtp;
     if (dt == 0.0) return;                       // advance() past tmax: leave the state untouched
@@ -161,23 +119,42 @@ __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a)
 
     const bool line_ok = a.is1d ? (line == 0) : (line >= G && line < a.NP - G);
 
-    // stage the first chunk, then the 5 carry cells directly
+    // stage the first chunk asynchronously, meanwhile compute the 5 leading stencil cells directly.
+    // Ring slot of sweep cell c is (c - (fStart - 2)) mod RS.
     {
         const size_t g0 = cell_index<DIR>(a, fStart + 3 + s, line);
 #pragma unroll
         for (int k = 0; k < 8; ++k) cp_async8(stq + k * NT + t, a.qc[perm<DIR>(k)] + g0);
         cp_async_commit();
     }
-    if (s < 5) cell_phase<DIR, NT>(a, cb, fStart - 2 + s, line, s, p);
+    for (int e = t; e < 5 * NPB; e += NT) {
+        const int sl = DIR == 0 ? e % 5 : e / NPB;
+        const int pp = DIR == 0 ? e / 5 : e % NPB;
+        const size_t g = cell_index<DIR>(a, fStart - 2 + sl, blockIdx.x * NPB + pp);
+        double q[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) q[k] = __ldg(a.qc[perm<DIR>(k)] + g);
+        cell_store<CBS>(a, cb, q, T::cbi(sl, pp));
+    }
 
+    int r0 = 0;                                  // ring slot of cell s0 - 2
     for (int s0 = fStart; s0 < fB; s0 += NS) {
-        // ---------------- cell phase from the staged state (each thread reads back its own copies)
+        // ring slots of the six stencil cells f-2 .. f+3 of this thread's face f = s0 + s
+        int sl[6];
+        {
+            int r = r0 + s;
+            if (r >= RS) r -= RS;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { sl[k] = r; r = (r + 1 == RS) ? 0 : r + 1; }
+        }
+        // ---------------- cell phase: cell s0 + 3 + s from the staged state (each thread reads back
+        // its own copies, no barrier needed for the staging buffer)
         cp_async_wait<0>();
         {
             double q[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) q[k] = stq[k * NT + t];
-            cell_store<DIR, NT>(a, cb, q, 5 + s, p);
+            cell_store<CBS>(a, cb, q, T::cbi(sl[5], p));
         }
         __syncthreads();
 
@@ -203,10 +180,10 @@ __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a)
         }
         cp_async_commit();
 
-        // ---------------- face phase: face f between cells f and f+1 (slots s+2, s+3)
+        // ---------------- face phase: face f between cells f (stencil slot 2) and f+1 (slot 3)
         const int f = s0 + s;
         if (f < fB) {
-            const int iL = T::cbi(s + 2, p), iR = T::cbi(s + 3, p);
+            const int iL = T::cbi(sl[2], p), iR = T::cbi(sl[3], p);
             FaceCoef fc;
             face_coefficients(cb[CQ_Q0 * CBS + iL], cb[CQ_Q0 * CBS + iR], cb[CQ_V1 * CBS + iL], cb[CQ_V1 * CBS + iR],
                               cb[CQ_V2 * CBS + iL], cb[CQ_V2 * CBS + iR], cb[CQ_V3 * CBS + iL], cb[CQ_V3 * CBS + iR],
@@ -217,7 +194,7 @@ __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a)
             face_amax(cb[CQ_V1 * CBS + iL], cb[CQ_LF * CBS + iL], cb[CQ_LA * CBS + iL], cb[CQ_LS * CBS + iL],
                       cb[CQ_V1 * CBS + iR], cb[CQ_LF * CBS + iR], cb[CQ_LA * CBS + iR], cb[CQ_LS * CBS + iR], amax);
             auto load = [&](int k, double F[7], double x[7]) {
-                const int ii = T::cbi(s + k, p);
+                const int ii = T::cbi(sl[k], p);
 #pragma unroll
                 for (int m = 0; m < 7; ++m) {
                     F[m] = cb[(CQ_F0 + m) * CBS + ii];
@@ -227,15 +204,8 @@ __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a)
             double fh[7], Fs[7];
             BackCoef bc;
             split_back(fc, bc);
-            if constexpr (STASH == 0) {
-                RegStash st;
-                face_flux(fc, amax, a.eps, load, st, Fs);
-            } else {
-                SmemStash<NT, STASH> st{stash_base + t};
-                if constexpr (STASH >= 2) st.put_back(bc);
-                face_flux(fc, amax, a.eps, load, st, Fs);
-                if constexpr (STASH >= 2) st.get_back(bc);
-            }
+            RegStash st;
+            face_flux(fc, amax, a.eps, load, st, Fs);
             back_project(bc, Fs, fh);
             const int io = T::fbi(s + 1, p);
 #pragma unroll
@@ -251,7 +221,7 @@ __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a)
         }
         __syncthreads();
 
-        // ---------------- update phase: cell c with faces c-1 (slot s) and c (slot s+1)
+        // ---------------- update phase: cell c = s0 + s with faces c-1 (fb slot s) and c (slot s+1)
         {
             const int c = s0 + s;
             if constexpr (DIR == 1) cp_async_wait<1>();          // group A has landed
@@ -266,7 +236,7 @@ __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a)
                 } else {
                     // rotated frame (rho,My,Mz,Mx,Bz,Bx,E): physical rho,Mx,My,Mz,Bz,E
                     constexpr int fi[6] = {0, 3, 1, 2, 4, 6};
-                    const int ic = T::cbi(s + 2, p);
+                    const int ic = T::cbi(sl[2], p);
                     const double cx = a.c_dx * dt, cy = a.c_dy * dt;
 #pragma unroll
                     for (int m = 0; m < 6; ++m) {
@@ -285,26 +255,22 @@ __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a)
         }
         __syncthreads();
 
-        // ---------------- carry the 5 trailing cells and the last face to the front
-        for (int e = t; e < 5 * NPB * CQ_COUNT; e += NTHREADS) {
-            const int qn_ = e / (5 * NPB), rem = e % (5 * NPB);
-            const int sl = DIR == 0 ? rem % 5 : rem / NPB;
-            const int pp = DIR == 0 ? rem / 5 : rem % NPB;
-            cb[qn_ * CBS + T::cbi(sl, pp)] = cb[qn_ * CBS + T::cbi(NS + sl, pp)];
-        }
-        for (int e = t; e < 7 * NPB; e += NTHREADS) {
+        // the last face of this chunk is the left face of the next chunk's first cell; no barrier
+        // needed after this: the next writes to fb happen behind the next cell-phase barrier
+        for (int e = t; e < 7 * NPB; e += NT) {
             const int m = e / NPB, pp = e % NPB;
             fb[m * FBS + T::fbi(0, pp)] = fb[m * FBS + T::fbi(NS, pp)];
         }
-        __syncthreads();
+        r0 += NS;
+        while (r0 >= RS) r0 -= RS;
     }
 }
 
-// Launch variants (CTA size, resident CTAs per SM -> register budget, stash level); chosen once
-// per process by WENO5_FLUX_VARIANT (development knob; the default is the fastest measured on B200).
-//   0: 256 threads, everything in registers (252)   1: 256 threads, Q + first parked in shared memory
-struct Variant { int nt, stash; };
-static const Variant kVariants[2] = {{256, 0}, {256, 1}};
+// Launch variants (CTA size x resident CTAs per SM; always 8 warps of ~252 registers per SM);
+// chosen once per process by WENO5_FLUX_VARIANT (development knob; the default is the fastest
+// measured on B200).  Smaller CTAs decouple the barriers of the march steps.
+struct Variant { int nt, yw; };
+static const Variant kVariants[4] = {{256, 32}, {128, 32}, {128, 16}, {64, 16}};
 
 static int flux_variant()
 {
@@ -312,32 +278,33 @@ static int flux_variant()
     if (v < 0) {
         const char *e = getenv("WENO5_FLUX_VARIANT");
         v = e ? atoi(e) : W5_DEFAULT_VARIANT;
-        if (v < 0 || v > 1) v = W5_DEFAULT_VARIANT;
+        if (v < 0 || v > 3) v = W5_DEFAULT_VARIANT;
     }
     return v;
 }
 
-template <int DIR, int NT, int MINB, int STASH>
+template <int DIR, int NT, int YW, int MINB>
 static void launch_flux_t(const FluxArgs &a, cudaStream_t s)
 {
-    using T = Tile<DIR, NT>;
-    constexpr int smem = T::SMEM + stash_slots(STASH) * NT * (int)sizeof(double);
-    static_assert(smem <= 227 * 1024, "shared memory budget");
+    using T = Tile<DIR, NT, YW>;
+    static_assert(T::SMEM * MINB <= 227 * 1024, "shared memory budget");
     static bool once = false;
     if (!once) {
-        cudaFuncSetAttribute(flux_kernel<DIR, NT, MINB, STASH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(flux_kernel<DIR, NT, YW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM);
         once = true;
     }
     dim3 grid((a.NP + T::NPB - 1) / T::NPB, a.nseg, 1);
-    flux_kernel<DIR, NT, MINB, STASH><<<grid, NT, smem, s>>>(a);
+    flux_kernel<DIR, NT, YW, MINB><<<grid, NT, T::SMEM, s>>>(a);
 }
 
 template <int DIR>
 static void launch_flux(const FluxArgs &a, cudaStream_t s)
 {
     switch (flux_variant()) {
-    case 1: launch_flux_t<DIR, 256, 1, 1>(a, s); break;
-    default: launch_flux_t<DIR, 256, 1, 0>(a, s); break;
+    case 1: launch_flux_t<DIR, 128, 32, 2>(a, s); break;
+    case 2: launch_flux_t<DIR, 128, 16, 2>(a, s); break;
+    case 3: launch_flux_t<DIR, 64, 16, 4>(a, s); break;
+    default: launch_flux_t<DIR, 256, 32, 1>(a, s); break;
     }
 }
 
@@ -345,8 +312,8 @@ void launch_flux_x(const FluxArgs &a, cudaStream_t s) { launch_flux<0>(a, s); }
 void launch_flux_y(const FluxArgs &a, cudaStream_t s) { launch_flux<1>(a, s); }
 
 // faces per march step along the sweep / lines per CTA for the active variant (host-side planning)
-int flux_chunk(int dir) { return dir == 0 ? 64 : kVariants[flux_variant()].nt / 32; }
-int flux_lines_per_cta(int dir) { return dir == 0 ? kVariants[flux_variant()].nt / 64 : 32; }
+int flux_chunk(int dir) { const Variant v = kVariants[flux_variant()]; return dir == 0 ? 64 : v.nt / v.yw; }
+int flux_lines_per_cta(int dir) { const Variant v = kVariants[flux_variant()]; return dir == 0 ? v.nt / 64 : v.yw; }
 
 // ------------------------------------------------------------------ 1-D stage update
 // Weno5_1D.jl:152-205: q_{k+1} = base - c dt/dx Q for the 7 flux-advanced components
