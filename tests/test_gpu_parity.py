@@ -156,7 +156,7 @@ def test_one_shot_call_equals_handle_path():
     b = run_gpu(g, q, bx, by, 1, dt=dt)[:3]
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
-    g1, q1 = pr.brio_wu(64)
+    g1, q1 = pr.rj95_2a(64)                  # (Brio-Wu starts with a degenerate face)
     q4 = S.classical_RK4_step(g1, q1, dt=1e-3)
     assert rel_linf(q4, O.rk4_step_1d(g1, q1, 1e-3)) <= 1e-12
 
