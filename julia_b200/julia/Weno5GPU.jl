@@ -1,0 +1,171 @@
+# Weno5GPU.jl -- Julia host side of libweno5mhd (B200 / sm_100a).
+#
+# Drop-in for the hot path of jdonnert/julia's Weno5_2D.jl / Weno5_1D.jl: the functions below
+# keep the reference's names, argument meaning and array layout
+#     q   :: Array{Float64,3} (Nx,Ny,9)  [rho,Mx,My,Mz,Bx,By,Bz,S,E]      (Weno5_2D.jl:35,2006)
+#     bxb, byb :: Array{Float64,2} (Nx,Ny)  face-centred Bx / By            (Weno5_2D.jl:37,1669)
+#     1-D: q :: Array{Float64,2} (N,9)                                        (Weno5_1D.jl:37)
+# and forward to the C ABI of include/weno5mhd.h with `ccall`.  Julia arrays are column-major
+# Float64, which is exactly the layout the library expects, so pointers are passed unchanged.
+#
+# The reference reads its configuration from module-level constants (Weno5_2D.jl:7-29); here it
+# is an explicit `Weno5Params` value.  Written for Julia >= 1.0 (the reference itself is Julia 0.6
+# and does not parse on a current Julia).  There is no `julia` binary in the build container, so
+# this file is exercised only where Julia exists; its Python twin julia_b200/solver.py binds the
+# same entry points and is what the test-suite drives.
+module Weno5GPU
+
+export Weno5Params, Solver, upload!, download, boundaries!, timestep, classical_RK4_step,
+       classical_RK4_step!, advance!, compute_divB, compute_global_vmax, interpolateB_center2face,
+       state2conserved, WENO5_2D, WENO5_1D
+
+const NBnd = 3                                    # Weno5_2D.jl:9
+const BC_OUTFLOW, BC_PERIODIC = Cint(0), Cint(1)
+
+const libweno5 = get(ENV, "WENO5MHD_LIB", joinpath(@__DIR__, "..", "libweno5mhd.so"))
+
+# mirrors `weno5_params` (include/weno5mhd.h)
+struct Weno5Params
+    nx::Cint; ny::Cint
+    dx::Cdouble; dy::Cdouble
+    gamma::Cdouble; cfl::Cdouble; eps::Cdouble
+    bc_x::Cint; bc_y::Cint
+    es_roundtrip::Cint
+end
+
+"Reference defaults: gam = 5/3, courFac = 0.8, eps = 1e-6 (Weno5_2D.jl:25-29), outflow boundaries."
+Weno5Params(nx, ny; xsize=1.0, ysize=1.0, gamma=5/3, cfl=0.8, eps=1e-6,
+            bc_x=BC_OUTFLOW, bc_y=BC_OUTFLOW, es_roundtrip=true) =
+    Weno5Params(nx, ny, xsize/nx, ny > 1 ? ysize/ny : 1.0, gamma, cfl, eps, bc_x, bc_y, es_roundtrip ? 1 : 0)
+
+struct Weno5Error <: Exception
+    code::Int
+    msg::String
+end
+
+function check(rc::Integer)
+    rc == 0 && return nothing
+    throw(Weno5Error(rc, unsafe_string(ccall((:weno5_last_error, libweno5), Cstring, ()))))
+end
+
+"One GPU, one y-slab; the state stays resident in HBM between calls."
+mutable struct Solver
+    h::Ptr{Cvoid}
+    p::Weno5Params
+    ny_local::Int
+    function Solver(p::Weno5Params; device::Integer=0, ny_local::Integer=p.ny, j_offset::Integer=0)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:weno5_create, libweno5), Cint, (Ref{Weno5Params}, Cint, Cint, Cint, Ref{Ptr{Cvoid}}),
+                    p, device, ny_local, j_offset, h))
+        s = new(h[], p, ny_local)
+        finalizer(x -> (x.h != C_NULL && ccall((:weno5_destroy, libweno5), Cint, (Ptr{Cvoid},), x.h); x.h = C_NULL), s)
+        return s
+    end
+end
+
+is1d(s::Solver) = s.p.ny == 1
+dims(s::Solver) = (Int(s.p.nx) + 2NBnd, is1d(s) ? 1 : s.ny_local + 2NBnd)
+
+# ---- multi-GPU (one Julia process per GPU; ship the id with Distributed / MPI)
+function comm_unique_id()
+    id = Vector{UInt8}(undef, 128)
+    check(ccall((:weno5_comm_unique_id, libweno5), Cint, (Ptr{UInt8},), id))
+    return id
+end
+comm_init!(s::Solver, rank::Integer, nranks::Integer, id::Vector{UInt8}) =
+    check(ccall((:weno5_comm_init, libweno5), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), s.h, rank, nranks, id))
+
+# ---- state transfer
+function upload!(s::Solver, q::Array{Float64,3}, bxb::Array{Float64,2}, byb::Array{Float64,2})
+    @assert size(q) == (dims(s)..., 9) && size(bxb) == dims(s) && size(byb) == dims(s)
+    check(ccall((:weno5_upload, libweno5), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), s.h, q, bxb, byb))
+end
+"q only: the face fields are derived on the device as interpolateB_center2face does (Weno5_2D.jl:1669)."
+upload!(s::Solver, q::Array{Float64,3}) =
+    check(ccall((:weno5_upload, libweno5), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), s.h, q, C_NULL, C_NULL))
+upload!(s::Solver, q::Array{Float64,2}) =
+    check(ccall((:weno5_upload_1d, libweno5), Cint, (Ptr{Cvoid}, Ptr{Float64}), s.h, q))
+
+function download(s::Solver)
+    Nx, Ny = dims(s)
+    if is1d(s)
+        q = Array{Float64}(undef, Nx, 9)
+        check(ccall((:weno5_download_1d, libweno5), Cint, (Ptr{Cvoid}, Ptr{Float64}), s.h, q))
+        return q
+    end
+    q = Array{Float64}(undef, Nx, Ny, 9); bxb = Array{Float64}(undef, Nx, Ny); byb = similar(bxb)
+    check(ccall((:weno5_download, libweno5), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), s.h, q, bxb, byb))
+    return q, bxb, byb
+end
+
+# ---- the hot path (reference names)
+"boundaries!(q, bxb, byb) on the resident state (Weno5_2D.jl:1684)."
+boundaries!(s::Solver) = check(ccall((:weno5_boundaries, libweno5), Cint, (Ptr{Cvoid},), s.h))
+
+"timestep(q) -> (dt, vxmax, vymax) (Weno5_2D.jl:1930); 1-D: dt = courFac*dx/vmax (Weno5_1D.jl:55)."
+function timestep(s::Solver)
+    dt = Ref(0.0); vx = Ref(0.0); vy = Ref(0.0)
+    check(ccall((:weno5_timestep, libweno5), Cint, (Ptr{Cvoid}, Ref{Float64}, Ref{Float64}, Ref{Float64}), s.h, dt, vx, vy))
+    return dt[], vx[], vy[]
+end
+compute_global_vmax(s::Solver) = (r = timestep(s); is1d(s) ? r[2] : (r[2], r[3]))
+
+"classical_RK4_step on the resident state (Weno5_2D.jl:125 / Weno5_1D.jl:152)."
+classical_RK4_step!(s::Solver, dt::Real) = check(ccall((:weno5_rk4_step, libweno5), Cint, (Ptr{Cvoid}, Cdouble), s.h, dt))
+
+"The driver loop of WENO5_2D()/WENO5_1D() kept on the device; returns (t, steps_done)."
+function advance!(s::Solver, nsteps::Integer; tmax::Real=0.0, t::Real=0.0)
+    tt = Ref(Float64(t)); nd = Ref{Cint}(0)
+    check(ccall((:weno5_advance, libweno5), Cint, (Ptr{Cvoid}, Cint, Cdouble, Ref{Float64}, Ref{Cint}), s.h, nsteps, tmax, tt, nd))
+    return tt[], Int(nd[])
+end
+
+function compute_divB(s::Solver)
+    d = Array{Float64}(undef, dims(s)...)
+    check(ccall((:weno5_divb, libweno5), Cint, (Ptr{Cvoid}, Ptr{Float64}), s.h, d))
+    return d
+end
+
+# ---- reference-shaped functional forms: host arrays in, fresh host arrays out
+"(q4, bxb4, byb4) = classical_RK4_step(p, q, bxb, byb, dt)   -- Weno5_2D.jl:125-317"
+function classical_RK4_step(p::Weno5Params, q::Array{Float64,3}, bxb::Array{Float64,2}, byb::Array{Float64,2}, dt::Float64)
+    q4 = similar(q); bxb4 = similar(bxb); byb4 = similar(byb)
+    check(ccall((:weno5_classical_rk4_step_2d, libweno5), Cint,
+                (Ref{Weno5Params}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cdouble, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                p, q, bxb, byb, dt, q4, bxb4, byb4))
+    return q4, bxb4, byb4
+end
+"q4 = classical_RK4_step(p, q, dt)   -- Weno5_1D.jl:152-236 (first return value)"
+function classical_RK4_step(p::Weno5Params, q::Array{Float64,2}, dt::Float64)
+    q4 = similar(q)
+    check(ccall((:weno5_classical_rk4_step_1d, libweno5), Cint, (Ref{Weno5Params}, Ptr{Float64}, Cdouble, Ptr{Float64}), p, q, dt, q4))
+    return q4
+end
+
+function interpolateB_center2face(p::Weno5Params, q::Array{Float64,3})
+    s = Solver(p); upload!(s, q); _, bxb, byb = download(s); return bxb, byb
+end
+
+"state2conserved(rho,vx,vy,vz,Bx,By,Bz,P) -> 9-vector (Weno5_2D.jl:2043-2053); host arithmetic."
+function state2conserved(rho, vx, vy, vz, Bx, By, Bz, P; gam=5/3)
+    v2 = vx^2 + vy^2 + vz^2; B2 = Bx^2 + By^2 + Bz^2
+    E = P/(gam-1) + 0.5*(rho*v2 + B2); S = P/rho^(gam-1)
+    return [rho, rho*vx, rho*vy, rho*vz, Bx, By, Bz, S, E]
+end
+
+"Driver loop of Weno5_2D.jl:33-110: upload, advance, report t / dt / max divB, download."
+function WENO5_2D(p::Weno5Params, q, bxb, byb; nstep::Integer=typemax(Int32), tmax::Real=0.1)
+    s = Solver(p); upload!(s, q, bxb, byb)
+    t, n = advance!(s, nstep; tmax=tmax)
+    println("t = $t after $n steps; Max DivB = ", maximum(abs.(compute_divB(s))))
+    return download(s)..., t
+end
+
+"Driver loop of Weno5_1D.jl:33-148 (without the plotting)."
+function WENO5_1D(p::Weno5Params, q; tmax::Real=0.2)
+    s = Solver(p); upload!(s, q)
+    t, n = advance!(s, typemax(Int32); tmax=tmax)
+    return download(s), t, n
+end
+
+end # module
