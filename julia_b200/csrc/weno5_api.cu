@@ -135,7 +135,36 @@ struct weno5_ctx {
     unsigned long long prof_launches = 0;
     // launch decomposition
     int segx_len, nsegx, segy_len, nsegy;
+    // TMA: one 3-D tensor map (x, y, plane) over the whole pool per sweep direction (box shapes differ)
+    CUtensorMap tmap_x[4], tmap_y[4];        // boxes of 8, 6, 4, 2 planes
+    bool have_tmap = false;
+    size_t nplanes = 0;
 };
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point: no link-time libcuda dependency
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static bool make_tensor_map(CUtensorMap *tm, double *pool, const Geom &g, size_t nplanes, const int box[2], int zbox)
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) {
+            cudaGetLastError();
+            return false;
+        }
+        fn = (EncodeTiledFn)p;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)g.pitch, (cuuint64_t)g.NYI, (cuuint64_t)nplanes};
+    const cuuint64_t strides[2] = {(cuuint64_t)g.pitch * sizeof(double), (cuuint64_t)g.plane * sizeof(double)};
+    const cuuint32_t bx[3] = {(cuuint32_t)box[0], (cuuint32_t)box[1], (cuuint32_t)zbox};
+    const cuuint32_t es[3] = {1, 1, 1};
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, pool, dims, strides, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 static void choose_segments(int nfaces, int NS, int strips, int &seg_len, int &nseg)
 {
@@ -217,13 +246,14 @@ extern "C" int weno5_create(const weno5_params *P, int device, int ny_local, int
 
     // planes: 3 states x 11 + acc 6+2+1 + rhs 7 + fsy,gsx + scratch
     const size_t nplanes = 3 * 11 + 9 + 7 + 2 + 1;
-    if (cudaMalloc(&c->pool, nplanes * g.plane * sizeof(double)) != cudaSuccess) {
+    // + slack: a TMA row segment of the x sweep may run up to 66 cells past the end of the last row
+    if (cudaMalloc(&c->pool, (nplanes * g.plane + 1024) * sizeof(double)) != cudaSuccess) {
         cudaGetLastError();
         delete c;
         return fail(WENO5_ERR_CUDA, "cudaMalloc of %.2f GB failed", nplanes * g.plane * 8.0 / 1e9);
     }
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CU(cudaMemsetAsync(c->pool, 0, nplanes * g.plane * sizeof(double), c->stream));
+    CU(cudaMemsetAsync(c->pool, 0, (nplanes * g.plane + 1024) * sizeof(double), c->stream));
     double *cur = c->pool;
     c->Q0 = carve_state(cur, g.plane);
     c->QA = carve_state(cur, g.plane);
@@ -236,6 +266,18 @@ extern "C" int weno5_create(const weno5_params *P, int device, int ny_local, int
     c->fsy = cur; cur += g.plane;
     c->gsx = cur; cur += g.plane;
     c->scratch = cur; cur += g.plane;
+
+    c->nplanes = nplanes;
+    if (!is1d && flux_uses_tma()) {
+        int bx[2], by[2];
+        flux_box(0, bx);
+        flux_box(1, by);
+        static const int zs[4] = {8, 6, 4, 2};
+        c->have_tmap = true;
+        for (int k = 0; k < 4; ++k)
+            c->have_tmap = c->have_tmap && make_tensor_map(&c->tmap_x[k], c->pool, g, nplanes, bx, zs[k]) &&
+                           make_tensor_map(&c->tmap_y[k], c->pool, g, nplanes, by, zs[k]);
+    }
 
     CU(cudaMalloc(&c->ctl, 8 * sizeof(double)));
     CU(cudaMemsetAsync(c->ctl, 0, 8 * sizeof(double), c->stream));
@@ -492,6 +534,11 @@ static int enqueue_stage(weno5_ctx *c, int stage, State &cur, State &nxt)
     a.gam = P.gamma; a.eps = P.eps;
     a.is1d = g.is1d;
     a.pitch = g.pitch;
+    a.tmap_x = c->have_tmap ? c->tmap_x : nullptr;
+    a.tmap_y = c->have_tmap ? c->tmap_y : nullptr;
+    auto plane_of = [&](const double *p) { return (int)((p - c->pool) / (ptrdiff_t)g.plane); };
+    for (int k = 0; k < 8; ++k) a.qc_plane[k] = plane_of(cur.q[k]);
+    for (int k = 0; k < 7; ++k) a.rhs_plane[k] = plane_of(c->rhs[k]);
 
     // x sweep
     a.N = g.NXI; a.NP = g.NYI; a.bs = c->fsy;
@@ -523,7 +570,10 @@ static int enqueue_stage(weno5_ctx *c, int stage, State &cur, State &nxt)
     // y sweep + RK update
     a.N = g.NYI; a.NP = g.NXI; a.bs = c->gsx;
     a.seg_len = c->segy_len; a.nseg = c->nsegy;
-    for (int k = 0; k < 6; ++k) { a.base[k] = c->Q0.q[six[k]]; a.acc[k] = c->acc[k]; a.qn[k] = nxt.q[six[k]]; }
+    for (int k = 0; k < 6; ++k) {
+        a.base[k] = c->Q0.q[six[k]]; a.acc[k] = c->acc[k]; a.qn[k] = nxt.q[six[k]];
+        a.base_plane[k] = plane_of(a.base[k]); a.acc_plane[k] = plane_of(a.acc[k]);
+    }
     { ProfScope ps(c); launch_flux_y(a, c->stream); }
     c->launches++; c->prof_launches += c->profiling;
 

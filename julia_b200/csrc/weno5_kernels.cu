@@ -18,7 +18,7 @@
 #include <cstdlib>
 
 #ifndef W5_DEFAULT_VARIANT
-#define W5_DEFAULT_VARIANT 2
+#define W5_DEFAULT_VARIANT 4
 #endif
 
 namespace w5 {
@@ -33,9 +33,18 @@ template <int DIR, int NT, int YW> struct Tile {
     static constexpr int RS = NS + 5;                      // ring slots along the sweep
     static constexpr int CBS = RS * NPB;                   // cell-buffer entries per quantity
     static constexpr int FBS = (NS + 1) * NPB;             // face-flux-buffer entries per component
-    static constexpr int STQ = 8 * NT;                     // staged raw state of the next chunk
-    static constexpr int STU = DIR == 0 ? 0 : 18 * NT;     // staged RK operands (rhs, base, acc)
-    static constexpr int SMEM = (CQ_COUNT * CBS + 7 * FBS + STQ + STU) * (int)sizeof(double);
+    // staging: [field][NT], thread t's element at t.  A TMA box (x: NS cells x NPB rows, y: NPB
+    // columns x NS rows) lands in exactly this layout because t = row-major index inside the box.
+    // The start address of a TMA box must be 16-byte aligned, i.e. an even cell index: the x-sweep
+    // box is 2 cells wider and starts at c0 - (c0 & 1); threads read at offset +(c0 & 1).
+    static constexpr int BOX_X = DIR == 0 ? NS + 2 : NPB, BOX_Y = DIR == 0 ? NPB : NS;
+    static constexpr int FST = BOX_X * BOX_Y;              // staging stride per field (one multi-plane TMA box is contiguous)
+    static constexpr int OFFQ = (CQ_COUNT * CBS + 7 * FBS + 15) / 16 * 16;   // 128-byte aligned (TMA destination)
+    static constexpr int STQ = 8 * FST;                    // staged raw state of the next chunk
+    static constexpr int STU = DIR == 0 ? 0 : 18 * FST;    // staged RK operands (rhs, base, acc)
+    static constexpr int SMEM = (OFFQ + (STQ + 15) / 16 * 16 + STU) * (int)sizeof(double) + 16;
+    // staging index of the thread at (sweep position s, line p); e = even-start shift (x sweep, TMA)
+    __device__ static __forceinline__ int sti(int s, int p, int e) { return DIR == 0 ? p * BOX_X + s + e : s * NPB + p; }
     __device__ static __forceinline__ int cbi(int slot, int p) { return DIR == 0 ? p * RS + slot : slot * NPB + p; }
     __device__ static __forceinline__ int fbi(int slot, int p) { return DIR == 0 ? p * (NS + 1) + slot : slot * NPB + p; }
 };
@@ -49,6 +58,37 @@ __device__ __forceinline__ void cp_async8(double *smem, const double *gmem)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// TMA bulk copies (cp.async.bulk, SASS UBLKCP) with mbarrier transaction counting: one warp issues
+// whole row segments global -> shared; the consumers wait on the barrier's phase parity.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// one box of the 3-D tensor map (x, y, plane) -> shared memory; out-of-bounds elements are zero-filled
+__device__ __forceinline__ void tma_load_box(double *dst, const CUtensorMap *tm, int x, int y, int z, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(tm), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok = 0;
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    }
+}
 
 // global index of sweep cell c on line `line` (clamped: cells past the array are never used by an
 // owned face, they only have to be finite)
@@ -90,17 +130,51 @@ template <int DIR> __device__ __forceinline__ constexpr int perm(int k)
     return DIR ? py[k] : px[k];
 }
 
-template <int DIR, int NT, int YW, int MINB>
-__global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a)
+// The tensor maps of one sweep direction: the same 3-D view (x, y, plane) of the plane pool with
+// boxes of 8, 6, 4 and 2 planes (the box shape is part of a tensor map).
+struct FluxMaps { CUtensorMap m8, m6, m4, m2; };
+
+// TMA path, executed by one thread: stage the raw state of the chunk whose first new cell is c0.
+// The 8 state planes are consecutive in the pool, so ONE box carries all of them.
+template <int DIR, int NT, int YW>
+__device__ __forceinline__ void tma_issue_state(const FluxArgs &a, const FluxMaps *tm, double *stq, unsigned long long *bar, int c0)
+{
+    using T = Tile<DIR, NT, YW>;
+    mbar_expect_tx(bar, 8 * T::FST * (unsigned)sizeof(double));
+    const int bx = DIR == 0 ? c0 - (c0 & 1) : (int)blockIdx.x * T::NPB;
+    const int by = DIR == 0 ? (int)blockIdx.x * T::NPB : c0;
+    tma_load_box(stq, &tm->m8, bx, by, a.qc_plane[0], bar);
+}
+
+// TMA path: stage the RK operands of the cells s0 .. s0+NS-1 of the y sweep: rhs (6 consecutive
+// planes), base (rho,Mx,My,Mz | Bz,E: planes 0-3 and 6-7 of the base state), acc (6 consecutive)
+template <int NT, int YW>
+__device__ __forceinline__ void tma_issue_operands(const FluxArgs &a, const FluxMaps *tm, double *stu, unsigned long long *bar, int s0)
+{
+    using T = Tile<1, NT, YW>;
+    const int nf = a.stage == 3 ? 18 : 12;
+    mbar_expect_tx(bar, nf * T::FST * (unsigned)sizeof(double));
+    const int bx = (int)blockIdx.x * T::NPB;
+    tma_load_box(stu, &tm->m6, bx, s0, a.rhs_plane[0], bar);
+    if (a.stage <= 3) {
+        tma_load_box(stu + 6 * T::FST, &tm->m4, bx, s0, a.base_plane[0], bar);
+        tma_load_box(stu + 10 * T::FST, &tm->m2, bx, s0, a.base_plane[4], bar);
+    }
+    if (a.stage >= 3) tma_load_box(stu + 12 * T::FST, &tm->m6, bx, s0, a.acc_plane[0], bar);
+}
+
+template <int DIR, int NT, int YW, int MINB, bool TMA>
+__global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a, const __grid_constant__ FluxMaps tmap)
 {
     using T = Tile<DIR, NT, YW>;
     constexpr int NS = T::NS, NPB = T::NPB, RS = T::RS;
     constexpr int CBS = T::CBS, FBS = T::FBS;
-    extern __shared__ double sm[];
+    extern __shared__ __align__(128) double sm[];
     double *cb = sm;
     double *fb = sm + CQ_COUNT * CBS;
-    double *stq = fb + 7 * FBS;                  // [8][NT]   raw state of the next chunk (cp.async)
-    double *stu = stq + T::STQ;                  // [18][NT]  rhs, base, acc of this chunk (y sweep)
+    double *stq = sm + T::OFFQ;                  // [8][NT]   raw state of the next chunk
+    double *stu = stq + (T::STQ + 15) / 16 * 16; // [18][NT]  rhs, base, acc of this chunk (y sweep)
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(stu + T::STU);   // [0] state, [1] operands
 
     const double dt = *a.dtp;
     if (dt == 0.0) return;                       // advance() past tmax: leave the state untouched
@@ -119,12 +193,20 @@ __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a)
 
     const bool line_ok = a.is1d ? (line == 0) : (line >= G && line < a.NP - G);
 
+    unsigned phq = 0, phu = 0;                   // mbarrier phase parities
+    if constexpr (TMA) {
+        if (t == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+        __syncthreads();
+    }
+
     // stage the first chunk asynchronously, meanwhile compute the 5 leading stencil cells directly.
     // Ring slot of sweep cell c is (c - (fStart - 2)) mod RS.
-    {
+    if constexpr (TMA) {
+        if (t == 0) tma_issue_state<DIR, NT, YW>(a, &tmap, stq, &bars[0], fStart + 3);
+    } else {
         const size_t g0 = cell_index<DIR>(a, fStart + 3 + s, line);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) cp_async8(stq + k * NT + t, a.qc[perm<DIR>(k)] + g0);
+        for (int k = 0; k < 8; ++k) cp_async8(stq + k * T::FST + T::sti(s, p, 0), a.qc[k] + g0);
         cp_async_commit();
     }
     for (int e = t; e < 5 * NPB; e += NT) {
@@ -149,11 +231,12 @@ __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a)
         }
         // ---------------- cell phase: cell s0 + 3 + s from the staged state (each thread reads back
         // its own copies, no barrier needed for the staging buffer)
-        cp_async_wait<0>();
+        if constexpr (TMA) { mbar_wait(&bars[0], phq); phq ^= 1u; } else cp_async_wait<0>();
         {
+            const int si = T::sti(s, p, TMA ? ((s0 + 3) & 1) : 0);
             double q[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) q[k] = stq[k * NT + t];
+            for (int k = 0; k < 8; ++k) q[k] = stq[perm<DIR>(k) * T::FST + si];     // staged in physical plane order
             cell_store<CBS>(a, cb, q, T::cbi(sl[5], p));
         }
         __syncthreads();
@@ -161,24 +244,31 @@ __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a)
         // ---------------- asynchronous copies that fly under the face phase:
         // group A = this chunk's RK operands (y sweep), group B = the next chunk's state
         const bool upd_ok = (s0 + s > fStart) && (s0 + s < fB) && (s0 + s >= G) && (s0 + s < a.N - G) && line_ok;
-        if constexpr (DIR == 1) {
-            if (upd_ok) {
-                const size_t gu = (size_t)line + (size_t)a.pitch * (s0 + s);
+        if constexpr (TMA) {
+            if (t == 0) {
+                if constexpr (DIR == 1) tma_issue_operands<NT, YW>(a, &tmap, stu, &bars[1], s0);
+                if (s0 + NS < fB) tma_issue_state<DIR, NT, YW>(a, &tmap, stq, &bars[0], s0 + NS + 3);
+            }
+        } else {
+            if constexpr (DIR == 1) {
+                if (upd_ok) {
+                    const size_t gu = (size_t)line + (size_t)a.pitch * (s0 + s);
 #pragma unroll
-                for (int m = 0; m < 6; ++m) {
-                    cp_async8(stu + m * NT + t, a.rhs[m] + gu);
-                    if (a.stage <= 3) cp_async8(stu + (6 + m) * NT + t, a.base[m] + gu);
-                    if (a.stage >= 3) cp_async8(stu + (12 + m) * NT + t, a.acc[m] + gu);
+                    for (int m = 0; m < 6; ++m) {
+                        cp_async8(stu + m * T::FST + t, a.rhs[m] + gu);
+                        if (a.stage <= 3) cp_async8(stu + (6 + m) * T::FST + t, a.base[m] + gu);
+                        if (a.stage >= 3) cp_async8(stu + (12 + m) * T::FST + t, a.acc[m] + gu);
+                    }
                 }
             }
-        }
-        cp_async_commit();
-        if (s0 + NS < fB) {
-            const size_t gn = cell_index<DIR>(a, s0 + NS + 3 + s, line);
+            cp_async_commit();
+            if (s0 + NS < fB) {
+                const size_t gn = cell_index<DIR>(a, s0 + NS + 3 + s, line);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) cp_async8(stq + k * NT + t, a.qc[perm<DIR>(k)] + gn);
+                for (int k = 0; k < 8; ++k) cp_async8(stq + k * T::FST + T::sti(s, p, 0), a.qc[k] + gn);
+            }
+            cp_async_commit();
         }
-        cp_async_commit();
 
         // ---------------- face phase: face f between cells f (stencil slot 2) and f+1 (slot 3)
         const int f = s0 + s;
@@ -224,7 +314,9 @@ __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a)
         // ---------------- update phase: cell c = s0 + s with faces c-1 (fb slot s) and c (slot s+1)
         {
             const int c = s0 + s;
-            if constexpr (DIR == 1) cp_async_wait<1>();          // group A has landed
+            if constexpr (DIR == 1) {                            // the RK operands have landed
+                if constexpr (TMA) { mbar_wait(&bars[1], phu); phu ^= 1u; } else cp_async_wait<1>();
+            }
             if (upd_ok) {
                 const int i0 = T::fbi(s, p), i1 = T::fbi(s + 1, p);
                 const size_t g = DIR == 0 ? (size_t)c + (size_t)a.pitch * line : (size_t)line + (size_t)a.pitch * c;
@@ -242,9 +334,9 @@ __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a)
                     for (int m = 0; m < 6; ++m) {
                         const double dfy = fb[fi[m] * FBS + i1] - fb[fi[m] * FBS + i0];
                         const double qcen = cb[(CQ_Q0 + fi[m]) * CBS + ic];
-                        const double rxm = stu[m * NT + t];
-                        double b = a.stage <= 3 ? stu[(6 + m) * NT + t] : 0.0;
-                        const double acm = a.stage >= 3 ? stu[(12 + m) * NT + t] : 0.0;
+                        const double rxm = stu[m * T::FST + t];
+                        double b = a.stage <= 3 ? stu[(6 + m) * T::FST + t] : 0.0;
+                        const double acm = a.stage >= 3 ? stu[(12 + m) * T::FST + t] : 0.0;
                         if (a.stage == 2) a.acc[m][g] = qcen - b;                       // -q0 + q1
                         if (a.stage == 3) a.acc[m][g] = fma(2.0, qcen, acm);            // + 2 q2
                         if (a.stage == 4) b = (acm + qcen) * (1.0 / 3.0);               // Weno5_2D.jl:279
@@ -269,8 +361,10 @@ __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a)
 // Launch variants (CTA size x resident CTAs per SM; always 8 warps of ~252 registers per SM);
 // chosen once per process by WENO5_FLUX_VARIANT (development knob; the default is the fastest
 // measured on B200).  Smaller CTAs decouple the barriers of the march steps.
+//   0: 256 thr x1, y tile 8x32    1: 128 x2, 4x32    2: 128 x2, 8x16 (LDGSTS staging)
+//   3: 64 x4, 4x16                4: 128 x2, 8x16 with TMA bulk-copy staging (default)
 struct Variant { int nt, yw; };
-static const Variant kVariants[4] = {{256, 32}, {128, 32}, {128, 16}, {64, 16}};
+static const Variant kVariants[5] = {{256, 32}, {128, 32}, {128, 16}, {64, 16}, {128, 16}};
 
 static int flux_variant()
 {
@@ -278,33 +372,38 @@ static int flux_variant()
     if (v < 0) {
         const char *e = getenv("WENO5_FLUX_VARIANT");
         v = e ? atoi(e) : W5_DEFAULT_VARIANT;
-        if (v < 0 || v > 3) v = W5_DEFAULT_VARIANT;
+        if (v < 0 || v > 4) v = W5_DEFAULT_VARIANT;
     }
     return v;
 }
 
-template <int DIR, int NT, int YW, int MINB>
+template <int DIR, int NT, int YW, int MINB, bool TMA>
 static void launch_flux_t(const FluxArgs &a, cudaStream_t s)
 {
     using T = Tile<DIR, NT, YW>;
     static_assert(T::SMEM * MINB <= 227 * 1024, "shared memory budget");
     static bool once = false;
     if (!once) {
-        cudaFuncSetAttribute(flux_kernel<DIR, NT, YW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM);
+        cudaFuncSetAttribute(flux_kernel<DIR, NT, YW, MINB, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM);
         once = true;
     }
     dim3 grid((a.NP + T::NPB - 1) / T::NPB, a.nseg, 1);
-    flux_kernel<DIR, NT, YW, MINB><<<grid, NT, T::SMEM, s>>>(a);
+    static const FluxMaps dummy = {};
+    const FluxMaps *tm = reinterpret_cast<const FluxMaps *>(DIR == 0 ? a.tmap_x : a.tmap_y);
+    flux_kernel<DIR, NT, YW, MINB, TMA><<<grid, NT, T::SMEM, s>>>(a, TMA && tm ? *tm : dummy);
 }
 
 template <int DIR>
 static void launch_flux(const FluxArgs &a, cudaStream_t s)
 {
-    switch (flux_variant()) {
-    case 1: launch_flux_t<DIR, 128, 32, 2>(a, s); break;
-    case 2: launch_flux_t<DIR, 128, 16, 2>(a, s); break;
-    case 3: launch_flux_t<DIR, 64, 16, 4>(a, s); break;
-    default: launch_flux_t<DIR, 256, 32, 1>(a, s); break;
+    const bool tma_ok = a.tmap_x != nullptr && a.tmap_y != nullptr && !a.is1d;
+    const int v = flux_variant();
+    switch (tma_ok || v < 4 ? v : 2) {
+    case 0: launch_flux_t<DIR, 256, 32, 1, false>(a, s); break;
+    case 1: launch_flux_t<DIR, 128, 32, 2, false>(a, s); break;
+    case 2: launch_flux_t<DIR, 128, 16, 2, false>(a, s); break;
+    case 3: launch_flux_t<DIR, 64, 16, 4, false>(a, s); break;
+    default: launch_flux_t<DIR, 128, 16, 2, true>(a, s); break;
     }
 }
 
@@ -314,6 +413,12 @@ void launch_flux_y(const FluxArgs &a, cudaStream_t s) { launch_flux<1>(a, s); }
 // faces per march step along the sweep / lines per CTA for the active variant (host-side planning)
 int flux_chunk(int dir) { const Variant v = kVariants[flux_variant()]; return dir == 0 ? 64 : v.nt / v.yw; }
 int flux_lines_per_cta(int dir) { const Variant v = kVariants[flux_variant()]; return dir == 0 ? v.nt / 64 : v.yw; }
+int flux_uses_tma() { return flux_variant() == 4; }
+void flux_box(int dir, int box[2])
+{
+    const Variant v = kVariants[flux_variant()];
+    if (dir == 0) { box[0] = 64 + 2; box[1] = v.nt / 64; } else { box[0] = v.yw; box[1] = v.nt / v.yw; }
+}
 
 // ------------------------------------------------------------------ 1-D stage update
 // Weno5_1D.jl:152-205: q_{k+1} = base - c dt/dx Q for the 7 flux-advanced components

@@ -6,6 +6,7 @@
 // and y-slabs need a single exchange per stage).  With G = 4 the internal 0-based index
 // equals the reference's 1-based public index: internal (i,j) == public (i,j).
 #pragma once
+#include <cuda.h>          // CUtensorMap (types only; the encoder is fetched through the runtime)
 #include <cuda_runtime.h>
 
 namespace w5 {
@@ -41,6 +42,10 @@ struct FluxArgs {
     int seg_len, nseg;       // faces per segment, segments per line
     double gam, eps;
     int is1d;
+    // TMA staging: plane indices into the pool (z coordinate of the 3-D tensor maps) and the maps
+    // themselves (host pointers; copied into the kernel's parameter space at launch)
+    int qc_plane[8], rhs_plane[7], base_plane[6], acc_plane[6];
+    const CUtensorMap *tmap_x, *tmap_y;      // each points at 4 maps: boxes of 8, 6, 4, 2 planes
 };
 
 struct CtArgs {
@@ -83,5 +88,7 @@ void launch_divb(const double *bxb, const double *byb, double *divb, const Geom 
 void launch_totals(const double *const planes[], int nplanes, const Geom &g, double *sums, cudaStream_t s);
 int flux_chunk(int dir);          // faces per march step of the active launch variant
 int flux_lines_per_cta(int dir);  // lines across the sweep per CTA
+int flux_uses_tma();              // 1 if the active variant stages through TMA tensor maps
+void flux_box(int dir, int box[2]);   // TMA box (cells along x, rows along y) of one march step
 
 }  // namespace w5

@@ -2,7 +2,7 @@
 # development aid: time every flux-kernel launch variant on one B200 and check it against the oracle
 mkdir -p gpurun_out
 N=${1:-2048}
-for v in 0 1 2 3; do
+for v in 2 4; do
   export WENO5_FLUX_VARIANT=$v
   python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_v$v.log 2>&1 || { echo "variant $v: SMOKE FAILED"; tail -3 gpurun_out/smoke_v$v.log; continue; }
   python bench.py --nx $N --ny $N --steps 10 --warmup 3 --e2e-steps 1 --no-cpu > gpurun_out/bench_v$v.log 2>&1
