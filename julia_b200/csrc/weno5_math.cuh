@@ -41,31 +41,24 @@ struct CellOut {
     double lf, la, ls;
 };
 
-// 1/x good to ~1 ulp without the slow-path branch of IEEE division (x is a sum of
-// positive terms here, never 0/inf/denormal)
+// 1/x for normal x > 0, branch-free: hardware seed (measured relative error 9.4e-7 on B200,
+// scripts/microbench/seed_accuracy.cu) and one cubic step r(1 + e + e^2), e = 1 - x r, which leaves
+// e^3 ~ 1e-18: 1 ulp (measured 2.2e-16) for MUFU + 3 FMA.  IEEE division costs ~10 dependent
+// operations and a slow-path branch that stops ptxas from interleaving independent chains.
 W5_HD double fast_rcp(double x)
 {
 #if defined(__CUDA_ARCH__)
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    // Newton steps from the hardware seed (relative error ~2^-23 or better): 2^-46, 2^-92 -> full
-    // precision after the second; the third is insurance against a coarser seed
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    return r;
+    const double e = fma(-x, r, 1.0);
+    return fma(r, fma(e, e, e), r);
 #else
     return 1.0 / x;
 #endif
 }
 
-// 1/sqrt(x) for normal x > 0, branch-free: hardware seed + two Newton steps (e -> 1.5 e^2).
-// IEEE sqrt()/division compile to a ~10-deep dependent chain fenced by a slow-path branch, which
-// stops ptxas from interleaving the eleven of them a face needs; these versions are plain
-// straight-line FMA code, accurate to ~1 ulp (not correctly rounded -- within the parity tolerance).
+// 1/sqrt(x) for normal x > 0, branch-free: hardware seed + two Newton steps (e -> 1.5 e^2;
+// measured 2.7e-16).
 W5_HD double fast_rsqrt(double x)
 {
 #if defined(__CUDA_ARCH__)
@@ -82,14 +75,18 @@ W5_HD double fast_rsqrt(double x)
 #endif
 }
 
-// sqrt(x) for x >= 0 (0 and denormals give 0), branch-free
+// sqrt(x) for x >= 0 (0 and denormals give 0), branch-free: one Newton step on the rsqrt seed
+// (1.3e-12) and one correction step s + (x - s^2) y/2 on the product, which squares that error.
 W5_HD double fast_sqrt(double x)
 {
 #if defined(__CUDA_ARCH__)
     const double xs = fmax(x, 1e-300);
-    const double y = fast_rsqrt(xs);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(xs));
+    const double e = fma(-(0.5 * xs * y), y, 0.5);
+    y = fma(y, e, y);
     double s = xs * y;
-    const double d = fma(-s, s, xs);          // one correction step: s + d/(2s)
+    const double d = fma(-s, s, xs);
     s = fma(d, 0.5 * y, s);
     return x > 1e-300 ? s : 0.0;
 #else

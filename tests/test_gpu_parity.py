@@ -170,7 +170,8 @@ def test_reference_named_helpers():
     bxo, byo = O.center2face(g, q)
     qo = q.copy(order="F")
     O.boundaries_2d(g, qo, bxo, byo)
-    assert np.array_equal(bx2, bxo) and np.array_equal(by2, byo) and np.array_equal(q2, qo)
+    # the device contracts the 4th-order stencil into FMAs: last-bit differences are allowed
+    assert rel_linf(bx2, bxo) <= 4e-16 and rel_linf(by2, byo) <= 4e-16 and np.array_equal(q2, qo)
     d = S.compute_divB(g, bx, by)
     assert np.abs(d - O.divb(g, bx, by)).max() <= 1e-12 * max(1.0, np.abs(d).max())
 
