@@ -30,7 +30,8 @@ namespace w5 {
 template <int DIR, int NT, int YW> struct Tile {
     static constexpr int NS = DIR == 0 ? 64 : NT / YW;     // faces along the sweep per chunk
     static constexpr int NPB = DIR == 0 ? NT / 64 : YW;    // lines across the sweep per CTA
-    static constexpr int RS = NS + 5;                      // ring slots along the sweep
+    static constexpr int RS = (NS + 5 + 15) / 16 * 16;     // ring slots along the sweep (>= NS + 5; a multiple of
+                                                           // 16 keeps the wrapped x-sweep accesses bank-conflict free)
     static constexpr int CBS = RS * NPB;                   // cell-buffer entries per quantity
     static constexpr int FBS = (NS + 1) * NPB;             // face-flux-buffer entries per component
     // staging: [field][NT], thread t's element at t.  A TMA box (x: NS cells x NPB rows, y: NPB
@@ -361,10 +362,11 @@ __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a, const 
 // Launch variants (CTA size x resident CTAs per SM; always 8 warps of ~252 registers per SM);
 // chosen once per process by WENO5_FLUX_VARIANT (development knob; the default is the fastest
 // measured on B200).  Smaller CTAs decouple the barriers of the march steps.
-//   0: 256 thr x1, y tile 8x32    1: 128 x2, 4x32    2: 128 x2, 8x16 (LDGSTS staging)
-//   3: 64 x4, 4x16                4: 128 x2, 8x16 with TMA bulk-copy staging (default)
+//   2: cp.async (LDGSTS) staging        4: TMA tensor-map staging (default)
+// Both: 128 threads x 2 CTAs per SM, x tile 2 rows x 64 faces, y tile 8 face rows x 16 columns.
+// (256x1, 64x4, 4x32-tile and 128/168-register variants were measured and dropped)
 struct Variant { int nt, yw; };
-static const Variant kVariants[5] = {{256, 32}, {128, 32}, {128, 16}, {64, 16}, {128, 16}};
+static const Variant kVariants[5] = {{128, 16}, {128, 16}, {128, 16}, {128, 16}, {128, 16}};
 
 static int flux_variant()
 {
@@ -398,13 +400,8 @@ static void launch_flux(const FluxArgs &a, cudaStream_t s)
 {
     const bool tma_ok = a.tmap_x != nullptr && a.tmap_y != nullptr && !a.is1d;
     const int v = flux_variant();
-    switch (tma_ok || v < 4 ? v : 2) {
-    case 0: launch_flux_t<DIR, 256, 32, 1, false>(a, s); break;
-    case 1: launch_flux_t<DIR, 128, 32, 2, false>(a, s); break;
-    case 2: launch_flux_t<DIR, 128, 16, 2, false>(a, s); break;
-    case 3: launch_flux_t<DIR, 64, 16, 4, false>(a, s); break;
-    default: launch_flux_t<DIR, 128, 16, 2, true>(a, s); break;
-    }
+    if (tma_ok && v == 4) launch_flux_t<DIR, 128, 16, 2, true>(a, s);
+    else launch_flux_t<DIR, 128, 16, 2, false>(a, s);
 }
 
 void launch_flux_x(const FluxArgs &a, cudaStream_t s) { launch_flux<0>(a, s); }
