@@ -702,22 +702,26 @@ __global__ void vmax_kernel(const VmaxArgs a)
     double vxm = 0.0, vym = 0.0;
     if (i < a.NXI - G && (a.NYI == 1 || j < a.NYI - G)) {
         const size_t g = (size_t)i + (size_t)a.pitch * j;
+        // same quantities as the reference loop (Weno5_2D.jl:1950-1979); the six divisions by the face
+        // density share one branch-free reciprocal and the square roots are branch-free (~1 ulp)
         const double rho = (a.q[C_RHO][g] + a.q[C_RHO][g + 1]) / 2;
-        const double vx = (a.q[C_MX][g] + a.q[C_MX][g + 1]) / 2 / rho;
-        const double vy = (a.q[C_MY][g] + a.q[C_MY][g + 1]) / 2 / rho;
+        const double ri = fast_rcp(rho);
+        const double vx = (a.q[C_MX][g] + a.q[C_MX][g + 1]) / 2 * ri;
+        const double vy = (a.q[C_MY][g] + a.q[C_MY][g + 1]) / 2 * ri;
         const double Bx = (a.q[C_BX][g] + a.q[C_BX][g + 1]) / 2;
         const double By = (a.q[C_BY][g] + a.q[C_BY][g + 1]) / 2;
         const double Bz = (a.q[C_BZ][g] + a.q[C_BZ][g + 1]) / 2;
         const double S = (a.q[C_S][g] + a.q[C_S][g + 1]) / 2;
         const double pres = S * pow(rho, a.gam - 1.0);
-        const double cs2 = a.gam * fabs(pres / rho);
+        const double cs2 = a.gam * fabs(pres * ri);
         const double B2 = Bx * Bx + By * By + Bz * Bz;
-        const double bbn2 = B2 / rho, bnx2 = Bx * Bx / rho, bny2 = By * By / rho;
+        const double bbn2 = B2 * ri, bnx2 = Bx * Bx * ri, bny2 = By * By * ri;
         const double sm = bbn2 + cs2;
-        const double rootx = sqrt(fmax(0.0, sm * sm - 4 * bnx2 * cs2));
-        const double rooty = sqrt(fmax(0.0, sm * sm - 4 * bny2 * cs2));
-        vxm = fabs(vx) + sqrt(0.5 * (sm + rootx));
-        vym = fabs(vy) + sqrt(0.5 * (sm + rooty));
+        const double rootx = fast_sqrt(fmax(0.0, sm * sm - 4 * bnx2 * cs2));
+        const double rooty = fast_sqrt(fmax(0.0, sm * sm - 4 * bny2 * cs2));
+        vxm = fabs(vx) + fast_sqrt(0.5 * (sm + rootx));
+        vym = fabs(vy) + fast_sqrt(0.5 * (sm + rooty));
+        if (sm != sm) { vxm = sm; vym = sm; }          // fast_sqrt maps NaN to 0: keep the NaN visible
     }
     unsigned long long bx_ = (unsigned long long)__double_as_longlong(vxm);
     unsigned long long by_ = (unsigned long long)__double_as_longlong(vym);
