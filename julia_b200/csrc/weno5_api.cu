@@ -122,7 +122,12 @@ struct weno5_ctx {
     double *h_ctl = nullptr;         // pinned mirror
     int side[4];                     // SideBC of x-lo, x-hi, y-lo, y-hi for this slab
     bool uploaded = false;
-    // multi-GPU
+    // multi-GPU: NCCL runs on its own stream so that the ghost-row exchange of stage k overlaps the
+    // interior x sweep of stage k+1
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_comm = nullptr;
+    bool xchg_pending = false;
+    double *halo = nullptr;          // 4 message buffers: send up, send down, recv from up, recv from down
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
     int up = -1, down = -1;          // neighbour ranks (-1: none)
@@ -166,13 +171,21 @@ static bool make_tensor_map(CUtensorMap *tm, double *pool, const Geom &g, size_t
               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// Cut every line of a sweep into segments (one CTA marches one segment of one strip of lines).
+// Measured on B200 (scripts/wave_sweep.sh): the step time is flat between 4 and 12 waves of the 296
+// resident CTAs and rises below 4 (tail) and for very short segments (prologue: 5 leading cells,
+// one redundant face, pipeline start-up) -- wave quantisation itself costs little because the CTAs
+// of a partial last wave have the FP64 pipe of their SM to themselves.
 static void choose_segments(int nfaces, int NS, int strips, int &seg_len, int &nseg)
 {
     const int chunks = (nfaces + NS - 1) / NS;
-    int want = (8 * 148 + strips - 1) / strips;          // aim at >= 8 waves of one CTA per SM
+    static const int waves = getenv("WENO5_WAVES") ? atoi(getenv("WENO5_WAVES")) : 4;
+    static const int minper = getenv("WENO5_MINPER") ? atoi(getenv("WENO5_MINPER")) : 4;
+    int want = (waves * 296 + strips - 1) / strips;
     if (want < 1) want = 1;
-    if (want > chunks) want = chunks;
-    const int per = (chunks + want - 1) / want;
+    int per = (chunks + want - 1) / want;
+    if (per < minper) per = minper;
+    if (per > chunks) per = chunks;
     seg_len = per * NS;
     nseg = (nfaces + seg_len - 1) / seg_len;
 }
@@ -300,7 +313,12 @@ extern "C" int weno5_destroy(weno5_ctx *c)
     if (!c) return 0;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    if (c->ev_main) cudaEventDestroy(c->ev_main);
+    if (c->ev_comm) cudaEventDestroy(c->ev_comm);
+    if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+    cudaFree(c->halo);
     for (auto &e : c->ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     cudaFree(c->pool); cudaFree(c->ctl); cudaFree(c->vmax_bits); cudaFree(c->sums);
     cudaFreeHost(c->h_ctl);
@@ -329,6 +347,10 @@ extern "C" int weno5_comm_init(weno5_ctx *c, int rank, int nranks, const unsigne
     ncclUniqueId u;
     memcpy(u.internal, id, 128);
     NC(g_nccl.CommInitRank(&c->comm, nranks, u, rank));
+    CU(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+    CU(cudaMalloc(&c->halo, 4 * (size_t)NCELL * G * c->g.pitch * sizeof(double)));
+    CU(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
     c->rank = rank;
     c->nranks = nranks;
     const bool per = c->P.bc_y == WENO5_BC_PERIODIC;
@@ -337,28 +359,49 @@ extern "C" int weno5_comm_init(weno5_ctx *c, int rank, int nranks, const unsigne
     return 0;
 }
 
-// send the 4 outermost interior rows, receive the 4 ghost rows, for each plane
-static int exchange_rows(weno5_ctx *c, double *const planes[], int n)
+// make the main stream wait for an exchange that is still in flight on the NCCL stream
+static int wait_exchange(weno5_ctx *c)
+{
+    if (c->xchg_pending) {
+        CU(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
+        c->xchg_pending = false;
+    }
+    return 0;
+}
+
+// send the 4 outermost interior rows, receive the 4 ghost rows, for each plane.  Runs on the NCCL
+// stream after everything queued so far on the main stream; with `async` the main stream does not
+// wait (the caller overlaps independent work and calls wait_exchange before touching ghost rows).
+static int exchange_rows(weno5_ctx *c, double *const planes[], int n, bool async = false)
 {
     if (!c->comm || (c->up < 0 && c->down < 0)) return 0;
+    // The overlap of the exchange with the interior x sweep is implemented (async) but OFF by default:
+    // on B200 the NCCL kernel running beside flux_x cost more (0.5 ms/step) than the 0.23 ms/step the
+    // serialized packed exchange takes.  WENO5_OVERLAP_XCHG=1 turns it on.
+    static const bool overlap = getenv("WENO5_OVERLAP_XCHG") != nullptr;
+    if (!overlap) async = false;
     const Geom &g = c->g;
     const size_t cnt = (size_t)G * g.pitch;
+    CU(cudaEventRecord(c->ev_main, c->stream));
+    CU(cudaStreamWaitEvent(c->comm_stream, c->ev_main, 0));
+    // one packed message per neighbour: [plane][4 rows][pitch]
+    const size_t msg = (size_t)NCELL * G * g.pitch;
+    double *s_up = c->halo, *s_down = c->halo + msg, *r_up = c->halo + 2 * msg, *r_down = c->halo + 3 * msg;
+    launch_halo_pack(planes, n, g, s_up, s_down, c->up >= 0, c->down >= 0, 0, c->comm_stream);
     NC(g_nccl.GroupStart());
-    for (int k = 0; k < n; ++k) {
-        double *p = planes[k];
-        if (c->up >= 0) {
-            NC(g_nccl.Send(p + (size_t)(g.NYI - 2 * G) * g.pitch, cnt, ncclFloat64, c->up, c->comm, c->stream));
-        }
-        if (c->down >= 0) {
-            NC(g_nccl.Recv(p, cnt, ncclFloat64, c->down, c->comm, c->stream));
-            NC(g_nccl.Send(p + (size_t)G * g.pitch, cnt, ncclFloat64, c->down, c->comm, c->stream));
-        }
-        if (c->up >= 0) {
-            NC(g_nccl.Recv(p + (size_t)(g.NYI - G) * g.pitch, cnt, ncclFloat64, c->up, c->comm, c->stream));
-        }
+    if (c->up >= 0) NC(g_nccl.Send(s_up, cnt * n, ncclFloat64, c->up, c->comm, c->comm_stream));
+    if (c->down >= 0) {
+        NC(g_nccl.Recv(r_down, cnt * n, ncclFloat64, c->down, c->comm, c->comm_stream));
+        NC(g_nccl.Send(s_down, cnt * n, ncclFloat64, c->down, c->comm, c->comm_stream));
     }
+    if (c->up >= 0) NC(g_nccl.Recv(r_up, cnt * n, ncclFloat64, c->up, c->comm, c->comm_stream));
     NC(g_nccl.GroupEnd());
+    launch_halo_pack(planes, n, g, r_up, r_down, c->up >= 0, c->down >= 0, 1, c->comm_stream);
+    c->launches += 2;
+    CU(cudaEventRecord(c->ev_comm, c->comm_stream));
+    c->xchg_pending = true;
     c->launches += 1;
+    if (!async) return wait_exchange(c);
     return 0;
 }
 
@@ -468,7 +511,13 @@ static int enqueue_timestep(weno5_ctx *c)
     launch_vmax(c->Q0.q, c->g, c->P.gamma, c->vmax_bits, c->stream);
     c->launches += 1;
     if (c->comm && c->nranks > 1) {
-        NC(g_nccl.AllReduce(c->vmax_bits, c->vmax_bits, 2, ncclUint64, ncclMax, c->comm, c->stream));
+        // all NCCL work of a handle is ordered on the NCCL stream (after a still-running exchange)
+        CU(cudaEventRecord(c->ev_main, c->stream));
+        CU(cudaStreamWaitEvent(c->comm_stream, c->ev_main, 0));
+        NC(g_nccl.AllReduce(c->vmax_bits, c->vmax_bits, 2, ncclUint64, ncclMax, c->comm, c->comm_stream));
+        CU(cudaEventRecord(c->ev_comm, c->comm_stream));
+        c->xchg_pending = true;
+        if (int r = wait_exchange(c)) return r;
         c->launches += 1;
     }
     launch_dt_from_vmax(c->vmax_bits, c->ctl, c->P.dx, c->P.dy, c->P.cfl, c->g.is1d, c->stream);
@@ -543,8 +592,24 @@ static int enqueue_stage(weno5_ctx *c, int stage, State &cur, State &nxt)
     // x sweep
     a.N = g.NXI; a.NP = g.NYI; a.bs = c->fsy;
     a.seg_len = c->segx_len; a.nseg = c->nsegx;
-    { ProfScope ps(c); launch_flux_x(a, c->stream); }
-    c->launches++; c->prof_launches += c->profiling;
+    if (c->xchg_pending && !g.is1d) {
+        // ghost rows of `cur` are still arriving: sweep the interior rows now, the ghost rows after
+        a.row_mode = 1;
+        { ProfScope ps(c); launch_flux_x(a, c->stream); }
+        if (int r = wait_exchange(c)) return r;
+        // only 8 rows are left: cut them into single-chunk segments so that they fill the machine
+        // instead of 4 CTAs marching the whole row length
+        a.row_mode = 2;
+        a.seg_len = flux_chunk(0);
+        a.nseg = (g.NXI - 5 + a.seg_len - 1) / a.seg_len;
+        launch_flux_x(a, c->stream);
+        a.row_mode = 0;
+        a.seg_len = c->segx_len; a.nseg = c->nsegx;
+        c->launches += 2; c->prof_launches += c->profiling;
+    } else {
+        { ProfScope ps(c); launch_flux_x(a, c->stream); }
+        c->launches++; c->prof_launches += c->profiling;
+    }
 
     if (g.is1d) {
         double *qn7[7]; const double *base7[7]; double *acc7[7];
@@ -607,7 +672,7 @@ static int enqueue_stage(weno5_ctx *c, int stage, State &cur, State &nxt)
     const int nfill = ent ? NCELL : 8;
     launch_bc_fill(nxt.q, nfill, g, c->side, dtp, c->stream);
     c->launches++;
-    if (c->comm) { if (int r = exchange_rows(c, nxt.q, nfill)) return r; }
+    if (c->comm) { if (int r = exchange_rows(c, nxt.q, nfill, true)) return r; }
     CU(cudaGetLastError());
     return 0;
 }
@@ -630,6 +695,7 @@ extern "C" int weno5_rk4_step(weno5_ctx *c, double dt)
     c->h_ctl[8] = dt;
     CU(cudaMemcpyAsync(c->ctl, c->h_ctl + 8, sizeof(double), cudaMemcpyHostToDevice, c->stream));
     if (int r = enqueue_step(c)) return r;
+    if (int r = wait_exchange(c)) return r;
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());
     return 0;
@@ -655,6 +721,7 @@ extern "C" int weno5_advance(weno5_ctx *c, int nsteps, double tmax, double *t, i
             if (c->h_ctl[1] >= tmax || c->h_ctl[6] != 0.0) break;
         }
     }
+    if (int r = wait_exchange(c)) return r;
     CU(cudaMemcpyAsync(c->h_ctl, c->ctl, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());

@@ -193,6 +193,16 @@ __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a, const 
     const int fStart = seg == 0 ? fA : fA - 1;
 
     const bool line_ok = a.is1d ? (line == 0) : (line >= G && line < a.NP - G);
+    // halo-exchange overlap (x sweep on y-slabs): interior rows are swept while the ghost rows are
+    // still in flight, the 2 x 4 ghost rows in a second launch
+    bool row_sel = true;
+    if (DIR == 0 && a.row_mode != 0) {
+        const int l0 = blockIdx.x * NPB, l1 = min(l0 + NPB, a.NP) - 1;
+        const bool any_interior = l1 >= G && l0 < a.NP - G;
+        const bool any_ghost = l0 < G || l1 >= a.NP - G;
+        if (a.row_mode == 1 ? !any_interior : !any_ghost) return;
+        row_sel = (line >= G && line < a.NP - G) == (a.row_mode == 1);
+    }
 
     unsigned phq = 0, phu = 0;                   // mbarrier phase parities
     if constexpr (TMA) {
@@ -244,7 +254,7 @@ __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a, const 
 
         // ---------------- asynchronous copies that fly under the face phase:
         // group A = this chunk's RK operands (y sweep), group B = the next chunk's state
-        const bool upd_ok = (s0 + s > fStart) && (s0 + s < fB) && (s0 + s >= G) && (s0 + s < a.N - G) && line_ok;
+        const bool upd_ok = (s0 + s > fStart) && (s0 + s < fB) && (s0 + s >= G) && (s0 + s < a.N - G) && line_ok && row_sel;
         if constexpr (TMA) {
             if (t == 0) {
                 if constexpr (DIR == 1) tma_issue_operands<NT, YW>(a, &tmap, stu, &bars[1], s0);
@@ -303,7 +313,7 @@ __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a, const 
             for (int m = 0; m < 7; ++m) fb[m * FBS + io] = fh[m];
             // CT seed flux, Weno5_2D.jl:1005-1008: x sweep -> fsy (tangential comp 2),
             // y sweep -> gsx (tangential comp 3 of the rotated frame)
-            if (!a.is1d && line < a.NP && (seg == 0 || f >= fA)) {
+            if (!a.is1d && line < a.NP && row_sel && (seg == 0 || f >= fA)) {
                 constexpr int TV = DIR == 0 ? CQ_V2 : CQ_V3;
                 const double bv = cb[CQ_B1 * CBS + iL] * cb[TV * CBS + iL] + cb[CQ_B1 * CBS + iR] * cb[TV * CBS + iR];
                 const size_t g = DIR == 0 ? (size_t)f + (size_t)a.pitch * line : (size_t)line + (size_t)a.pitch * f;
@@ -656,6 +666,39 @@ void launch_bc_fill(double *const planes[], int nplanes, const Geom &g, const in
     const int nyg = g.NYI > 1 ? 2 * G : 0;
     const long total = (long)nyg * g.NXI + (long)(g.NYI - nyg) * 2 * G;
     bc_fill_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a);
+}
+
+// ------------------------------------------------------------------ halo packing for the slab exchange
+// One contiguous message per neighbour and stage instead of one per plane: rows [NYI-2G, NYI-G) of
+// every plane -> up buffer, rows [G, 2G) -> down buffer (pack); received rows -> ghost rows (unpack).
+struct PackArgs { double *pl[NCELL]; int n; int NYI, pitch; double *up, *down; int has_up, has_down; };
+
+__global__ void halo_pack_kernel(const PackArgs a, int unpack)
+{
+    const size_t per = (size_t)G * a.pitch;                 // doubles per plane and direction
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= per * a.n) return;
+    const int k = (int)(e / per);
+    const size_t r = e % per;
+    double *p = a.pl[k];
+    if (!unpack) {
+        if (a.has_up) a.up[e] = p[(size_t)(a.NYI - 2 * G) * a.pitch + r];
+        if (a.has_down) a.down[e] = p[(size_t)G * a.pitch + r];
+    } else {
+        if (a.has_up) p[(size_t)(a.NYI - G) * a.pitch + r] = a.up[e];
+        if (a.has_down) p[r] = a.down[e];
+    }
+}
+
+void launch_halo_pack(double *const planes[], int n, const Geom &g, double *up, double *down, int has_up, int has_down,
+                      int unpack, cudaStream_t s)
+{
+    PackArgs a;
+    a.n = n;
+    for (int k = 0; k < n; ++k) a.pl[k] = planes[k];
+    a.NYI = g.NYI; a.pitch = g.pitch; a.up = up; a.down = down; a.has_up = has_up; a.has_down = has_down;
+    const size_t total = (size_t)G * g.pitch * n;
+    halo_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a, unpack);
 }
 
 // ------------------------------------------------------------------ entropy variable

@@ -42,6 +42,7 @@ struct FluxArgs {
     int seg_len, nseg;       // faces per segment, segments per line
     double gam, eps;
     int is1d;
+    int row_mode;            // x sweep: 0 all rows, 1 interior rows only, 2 ghost rows only (halo-exchange overlap)
     // TMA staging: plane indices into the pool (z coordinate of the 3-D tensor maps) and the maps
     // themselves (host pointers; copied into the kernel's parameter space at launch)
     int qc_plane[8], rhs_plane[7], base_plane[6], acc_plane[6];
@@ -73,6 +74,8 @@ void launch_ct_centers(const double *bxn, const double *byn, double *Bx, double 
 void launch_face_bc(double *bx, double *by, const Geom &g, const int side[4], const double *dtp, cudaStream_t s);
 void launch_bc_fill(double *const planes[], int nplanes, const Geom &g, const int side[4],
                     const double *dtp, cudaStream_t s);
+void launch_halo_pack(double *const planes[], int n, const Geom &g, double *up, double *down, int has_up, int has_down,
+                      int unpack, cudaStream_t s);
 void launch_entropy(double *const q9[9], const Geom &g, double gam, int roundtrip, int all_cells,
                     const double *dtp, cudaStream_t s);
 void launch_vmax(const double *const q9[9], const Geom &g, double gam, unsigned long long *vmax_bits,
