@@ -751,7 +751,7 @@ extern "C" int weno5_totals(weno5_ctx *c, double sums[11])
     if (!c->uploaded) return fail(WENO5_ERR_STATE, "no state on the device yet");
     CU(cudaSetDevice(c->device));
     const double *pl[11];
-    for (int k = 0; k < NCELL; ++k) pl[k] = c->Q0.q[k];
+    for (int k = 0; k < NCELL; ++k) pl[host_comp(k)] = c->Q0.q[k];     // report in the reference's order (S, then E)
     pl[9] = c->Q0.bx; pl[10] = c->Q0.by;
     launch_totals(pl, c->g.is1d ? 9 : 11, c->g, c->sums, c->stream);
     c->launches++;
