@@ -278,10 +278,44 @@ def run_gpu(args):
         tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
-    e2e_value = cells_global * e2e_steps / e2e_s
     bytes_dir = 11 * q.shape[0] * q.shape[1] * 8
+    e2e_seq = {"value": cells_global * e2e_steps / e2e_s, "unit": "cell-updates/s", "h2d_bytes_per_step": bytes_dir,
+               "d2h_bytes_per_step": bytes_dir, "steps": e2e_steps,
+               "calls": "weno5_upload -> weno5_timestep -> weno5_rk4_step -> weno5_download, pinned host arrays"}
+    e2e = e2e_seq
+
+    # single GPU: the pipelined host step (y-slabs with overlap rows; H2D, compute and D2H overlap)
+    if world == 1 and nyl >= 1024:
+        from julia_b200.solver import Pipe
+        rows = 512
+        oq, poq = pinned_array(lib, q.shape)
+        obx, pobx = pinned_array(lib, bx.shape)
+        oby, poby = pinned_array(lib, by.shape)
+        dt0 = s.timestep()[0]                             # time step of the state in hq (it is the resident one)
+        with Pipe(gglob, device=local, rows_per_slab=rows, es_roundtrip=bool(args.es_roundtrip)) as pipe:
+            a_in, a_out = (hq, hbx, hby), (oq, obx, oby)
+            _, _, _, dtn = pipe.step(*a_in, dt0, out=a_out)          # warm-up
+            a_in, a_out = a_out, a_in
+            psteps = max(1, min(args.steps, 2 * args.e2e_steps))
+            torch.cuda.synchronize()
+            t0 = time.time()
+            for _ in range(psteps):
+                _, _, _, dtn = pipe.step(*a_in, dtn, out=a_out)
+                a_in, a_out = a_out, a_in
+            torch.cuda.synchronize()
+            pipe_s = time.time() - t0
+        nslab = (nyl + rows - 1) // rows
+        up_rows = nslab * (rows + 2 * 16 + 8)
+        e2e = {"value": cells_global * psteps / pipe_s, "unit": "cell-updates/s",
+               "h2d_bytes_per_step": 11 * q.shape[0] * up_rows * 8, "d2h_bytes_per_step": bytes_dir, "steps": psteps,
+               "calls": "weno5_pipe_step(q0,bxb0,byb0,dt) -> (q4,bxb4,byb4,dt_next): host arrays in, host arrays out, "
+                        f"{nslab} y-slabs of {rows}+32 rows on 3 streams (copies and compute overlap), pinned host arrays",
+               "sequential": e2e_seq}
+        for p_ in (poq, pobx, poby):
+            lib.weno5_host_free(p_)
     for p in (pq, pbx, pby):
         lib.weno5_host_free(p)
+    e2e_value = e2e["value"]
 
     if rank == 0:
         sampler.stop()
@@ -303,9 +337,7 @@ def run_gpu(args):
             "config": workload_config(world) if (nx, nyl) == (NX_PER_GPU, NY_PER_GPU) else
             {"workload": f"orszag_tang {nx}x{nyl} per GPU (non-default size)", "nx": nx, "ny_global": nyl * world},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": bytes_dir,
-                    "d2h_bytes_per_step": bytes_dir, "steps": e2e_steps,
-                    "calls": "weno5_upload -> weno5_timestep -> weno5_rk4_step -> weno5_download, pinned host arrays"},
+            "e2e": e2e,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": how, "kernel": "flux_kernel<0|1> (x and y sweeps)",

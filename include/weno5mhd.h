@@ -110,6 +110,19 @@ int weno5_classical_rk4_step_1d(const weno5_params *params, const double *q0, do
 int weno5_step_host(weno5_ctx *ctx, const double *q0, const double *bxb0, const double *byb0,
                     double dt, double *q4, double *bxb4, double *byb4);
 
+/* ---- pipelined host -> host step (2-D): the same classical_RK4_step(q0,bxb0,byb0,dt) -> (q4,bxb4,byb4)
+ * (Weno5_2D.jl:125-317), streamed through the GPU in y-slabs of `rows_per_slab` rows that carry the
+ * domain of dependence of one step as overlap, so that the host->device copy of the next slab, the
+ * step of the current one and the device->host copy of the previous one overlap.  Results are
+ * bit-identical to weno5_step_host.  Output arrays must not alias the inputs; page-locked host
+ * arrays (weno5_host_alloc) are needed for the copies to overlap.  *dt_next receives
+ * timestep(q4) (Weno5_2D.jl:1930), computed on the fly from the result. */
+typedef struct weno5_pipe weno5_pipe;
+int weno5_pipe_create(const weno5_params *params, int device, int rows_per_slab, weno5_pipe **out);
+int weno5_pipe_step(weno5_pipe *pipe, const double *q0, const double *bxb0, const double *byb0, double dt,
+                    double *q4, double *bxb4, double *byb4, double *dt_next);
+int weno5_pipe_destroy(weno5_pipe *pipe);
+
 /* ---- host memory helpers (page-locked buffers make upload/download asynchronous-capable) */
 int weno5_host_alloc(void **ptr, unsigned long long bytes);
 int weno5_host_free(void *ptr);

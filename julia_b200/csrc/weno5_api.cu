@@ -214,14 +214,16 @@ static State carve_state(double *&cur, size_t plane)
     return s;
 }
 
-extern "C" int weno5_create(const weno5_params *P, int device, int ny_local, int j_offset, weno5_ctx **out)
+// side_lo/side_hi >= 0 override the y sides derived from (j_offset, ny_local) -- used by the
+// pipelined host step, whose slabs are cut at arbitrary rows
+static int create_ctx(const weno5_params *P, int device, int ny_local, int j_offset, int side_lo, int side_hi, weno5_ctx **out)
 {
     if (!P || !out) return fail(WENO5_ERR_ARG, "null argument");
     const bool is1d = P->ny == 1;
     if (P->nx < 8 || (!is1d && (P->ny < 8 || ny_local < 8)))
         return fail(WENO5_ERR_ARG, "grid too small: nx=%d ny=%d ny_local=%d (need >= 8, or ny = 1)", P->nx, P->ny, ny_local);
     if (is1d && (ny_local != 1 || j_offset != 0)) return fail(WENO5_ERR_ARG, "1-D grids cannot be decomposed");
-    if (!is1d && (j_offset < 0 || j_offset + ny_local > P->ny)) return fail(WENO5_ERR_ARG, "slab outside the grid");
+    if (!is1d && side_lo < 0 && (j_offset < 0 || j_offset + ny_local > P->ny)) return fail(WENO5_ERR_ARG, "slab outside the grid");
     if (!(P->dx > 0) || (!is1d && !(P->dy > 0)) || !(P->gamma > 1.0)) return fail(WENO5_ERR_ARG, "bad dx/dy/gamma");
     for (int b : {P->bc_x, P->bc_y})
         if (b != WENO5_BC_OUTFLOW && b != WENO5_BC_PERIODIC) return fail(WENO5_ERR_ARG, "unknown boundary condition %d", b);
@@ -256,6 +258,8 @@ extern "C" int weno5_create(const weno5_params *P, int device, int ny_local, int
     c->side[2] = (j_offset == 0) ? (whole || ybc == SIDE_OUTFLOW ? ybc : SIDE_NONE) : SIDE_NONE;
     c->side[3] = (j_offset + ny_local == P->ny) ? (whole || ybc == SIDE_OUTFLOW ? ybc : SIDE_NONE) : SIDE_NONE;
     if (is1d) c->side[2] = c->side[3] = SIDE_NONE;
+    if (side_lo >= 0) c->side[2] = side_lo;
+    if (side_hi >= 0) c->side[3] = side_hi;
 
     // planes: 3 states x 11 + acc 6+2+1 + rhs 7 + fsy,gsx + scratch
     const size_t nplanes = 3 * 11 + 9 + 7 + 2 + 1;
@@ -306,6 +310,11 @@ extern "C" int weno5_create(const weno5_params *P, int device, int ny_local, int
     CU(cudaStreamSynchronize(c->stream));
     *out = c;
     return 0;
+}
+
+extern "C" int weno5_create(const weno5_params *P, int device, int ny_local, int j_offset, weno5_ctx **out)
+{
+    return create_ctx(P, device, ny_local, j_offset, -1, -1, out);
 }
 
 extern "C" int weno5_destroy(weno5_ctx *c)
@@ -802,6 +811,177 @@ extern "C" int weno5_classical_rk4_step_1d(const weno5_params *P, const double *
     const int r = weno5_step_host(c, q0, nullptr, nullptr, dt, q4, nullptr, nullptr);
     weno5_destroy(c);
     return r;
+}
+
+// ------------------------------------------------------------------ pipelined host -> host step
+// classical_RK4_step for host-resident arrays, streamed through the GPU in y-slabs.  One explicit RK4
+// step has a finite domain of dependence: a row of the result depends on the 4 stages x 4 rows of the
+// input around it (3 for the WENO stencil of the y faces + 1 for the constrained-transport
+// centring).  A slab that carries PIPE_H >= 16 extra rows on each cut side therefore reproduces its
+// owned rows bit for bit without talking to its neighbours.  Three slab contexts on three streams
+// rotate, so the H2D copy of slab k+1, the RK4 step of slab k and the D2H copy of slab k-1 overlap:
+// the call is bound by the PCIe transfer of the state (once in, once out) instead of
+// upload + compute + download in sequence.
+constexpr int PIPE_H = 16;
+constexpr int PIPE_NCTX = 3;
+
+struct weno5_pipe {
+    weno5_params P;
+    int device;
+    int R;                    // owned rows per slab
+    int W;                    // interior rows of a slab window = R + 2 PIPE_H
+    weno5_ctx *ctx[PIPE_NCTX];
+};
+
+extern "C" int weno5_pipe_destroy(weno5_pipe *p)
+{
+    if (!p) return 0;
+    for (int k = 0; k < PIPE_NCTX; ++k) weno5_destroy(p->ctx[k]);
+    delete p;
+    return 0;
+}
+
+extern "C" int weno5_pipe_create(const weno5_params *P, int device, int rows_per_slab, weno5_pipe **out)
+{
+    if (!P || !out) return fail(WENO5_ERR_ARG, "null argument");
+    if (P->ny == 1) return fail(WENO5_ERR_ARG, "the pipelined step is 2-D only");
+    if (rows_per_slab < 2 * PIPE_H + 8) return fail(WENO5_ERR_ARG, "rows_per_slab must be >= %d", 2 * PIPE_H + 8);
+    if (P->ny < rows_per_slab + 2 * PIPE_H)
+        return fail(WENO5_ERR_ARG, "grid of %d rows is too small for slabs of %d rows (+%d overlap); use weno5_step_host", P->ny,
+                    rows_per_slab, 2 * PIPE_H);
+    weno5_pipe *p = new weno5_pipe();
+    p->P = *P;
+    p->device = device;
+    p->R = rows_per_slab;
+    p->W = rows_per_slab + 2 * PIPE_H;
+    for (int k = 0; k < PIPE_NCTX; ++k) p->ctx[k] = nullptr;
+    for (int k = 0; k < PIPE_NCTX; ++k) {
+        if (int r = create_ctx(P, device, p->W, 0, SIDE_NONE, SIDE_NONE, &p->ctx[k])) {
+            weno5_pipe_destroy(p);
+            return r;
+        }
+    }
+    *out = p;
+    return 0;
+}
+
+// copy `nrows` rows starting at host public row hj <-> internal row ij of one plane
+static int copy_rows(weno5_ctx *c, double *dev, const double *host_in, double *host_out, int Ny_host, int hj, int ij, int nrows)
+{
+    if (nrows <= 0) return 0;
+    const Geom &g = c->g;
+    (void)Ny_host;
+    double *d = dev + 1 + (size_t)g.pitch * ij;
+    const size_t w = (size_t)g.Nx * sizeof(double);
+    if (host_in)
+        CU(cudaMemcpy2DAsync(d, g.pitch * sizeof(double), host_in + (size_t)g.Nx * hj, w, w, nrows, cudaMemcpyHostToDevice, c->stream));
+    if (host_out)
+        CU(cudaMemcpy2DAsync(host_out + (size_t)g.Nx * hj, w, d, g.pitch * sizeof(double), w, nrows, cudaMemcpyDeviceToHost, c->stream));
+    return 0;
+}
+
+extern "C" int weno5_pipe_step(weno5_pipe *p, const double *q0, const double *bxb0, const double *byb0, double dt, double *q4,
+                               double *bxb4, double *byb4, double *dt_next)
+{
+    if (!p || !q0 || !bxb0 || !byb0 || !q4 || !bxb4 || !byb4) return fail(WENO5_ERR_ARG, "null argument");
+    if (q0 == q4 || bxb0 == bxb4 || byb0 == byb4) return fail(WENO5_ERR_ARG, "the pipelined step cannot run in place");
+    if (!(dt > 0.0) || !std::isfinite(dt)) return fail(WENO5_ERR_ARG, "dt must be positive and finite (got %g)", dt);
+    CU(cudaSetDevice(p->device));
+    const weno5_params &P = p->P;
+    const int ny = P.ny, Ny = ny + 2 * WENO5_NBND, Nx = P.nx + 2 * WENO5_NBND;
+    const bool periodic = P.bc_y == WENO5_BC_PERIODIC;
+    const size_t hp = (size_t)Nx * Ny;
+    const int nslab = (ny + p->R - 1) / p->R;
+
+    for (int k = 0; k < PIPE_NCTX; ++k) {
+        weno5_ctx *c = p->ctx[k];
+        c->h_ctl[8] = dt;
+        CU(cudaMemcpyAsync(c->ctl, c->h_ctl + 8, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemsetAsync(c->vmax_bits, 0, 2 * sizeof(unsigned long long), c->stream));
+    }
+
+    for (int k = 0; k < nslab; ++k) {
+        weno5_ctx *c = p->ctx[k % PIPE_NCTX];
+        const Geom &g = c->g;
+        const int r0 = k * p->R, r1 = r0 + p->R < ny ? r0 + p->R : ny;       // owned interior rows
+        // window of W interior rows around the owned rows
+        int w0 = r0 - PIPE_H;
+        if (!periodic) { if (w0 < 0) w0 = 0; if (w0 > ny - p->W) w0 = ny - p->W; }
+        const bool phys_lo = !periodic && w0 == 0, phys_hi = !periodic && w0 + p->W == ny;
+        c->side[2] = phys_lo ? SIDE_OUTFLOW : SIDE_NONE;
+        c->side[3] = phys_hi ? SIDE_OUTFLOW : SIDE_NONE;
+
+        // ---- upload: internal row ii holds interior row w0 - 4 + ii, i.e. public row w0 - 1 + ii
+        for (int ii = 0; ii < g.NYI;) {
+            int src = w0 - 1 + ii;                        // public row
+            int run;
+            if (periodic) {
+                int rr = ((w0 - 4 + ii) % ny + ny) % ny;   // interior row, wrapped
+                src = rr + WENO5_NBND;
+                run = ny - rr;                             // rows until the wrap
+            } else {
+                if (src < 0) { ++ii; continue; }           // beyond the public ghosts: filled by bc_fill
+                if (src >= Ny) break;
+                run = Ny - src;
+            }
+            if (run > g.NYI - ii) run = g.NYI - ii;
+            for (int f = 0; f < NCELL; ++f)
+                if (int r = copy_rows(c, c->Q0.q[f], q0 + host_comp(f) * hp, nullptr, Ny, src, ii, run)) return r;
+            if (int r = copy_rows(c, c->Q0.bx, bxb0, nullptr, Ny, src, ii, run)) return r;
+            if (int r = copy_rows(c, c->Q0.by, byb0, nullptr, Ny, src, ii, run)) return r;
+            ii += run;
+        }
+        c->uploaded = true;
+        if (int r = apply_boundaries(c, c->Q0, true)) return r;
+
+        // ---- one RK4 step of the window, wave speeds of the owned rows for the next dt
+        if (int r = enqueue_step(c)) return r;
+        const int io0 = r0 - w0 + G, io1 = r1 - w0 + G;       // owned rows, internal
+        launch_vmax_rows(c->Q0.q, g, P.gamma, c->vmax_bits, io0, io1, 0, c->stream);
+        c->launches++;
+
+        // ---- download the owned rows (and the physical ghost rows next to them)
+        int d0 = io0, d1 = io1;
+        if (phys_lo && r0 == 0) d0 = 1;                        // public ghost rows 0..2 = internal 1..3
+        if (phys_hi && r1 == ny) d1 = g.NYI - 1;
+        const int hj = w0 - 1 + d0;                            // public row of internal row d0
+        for (int f = 0; f < NCELL; ++f)
+            if (int r = copy_rows(c, c->Q0.q[f], nullptr, q4 + host_comp(f) * hp, Ny, hj, d0, d1 - d0)) return r;
+        if (int r = copy_rows(c, c->Q0.bx, nullptr, bxb4, Ny, hj, d0, d1 - d0)) return r;
+        if (int r = copy_rows(c, c->Q0.by, nullptr, byb4, Ny, hj, d0, d1 - d0)) return r;
+    }
+
+    unsigned long long vb[2] = {0ull, 0ull};
+    for (int k = 0; k < PIPE_NCTX; ++k) {
+        weno5_ctx *c = p->ctx[k];
+        unsigned long long *hv = reinterpret_cast<unsigned long long *>(c->h_ctl + 12);
+        CU(cudaMemcpyAsync(hv, c->vmax_bits, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaGetLastError());
+        if (hv[0] > vb[0]) vb[0] = hv[0];
+        if (hv[1] > vb[1]) vb[1] = hv[1];
+    }
+    if (periodic) {
+        // boundaries! of the result (Weno5_2D.jl:313, periodic addition): ghost rows are images
+        double *arrs[3] = {q4, bxb4, byb4};
+        const int nplanes[3] = {NCELL, 1, 1};
+        for (int a = 0; a < 3; ++a)
+            for (int f = 0; f < nplanes[a]; ++f) {
+                double *pl = arrs[a] + (size_t)f * hp;
+                memcpy(pl, pl + (size_t)Nx * ny, sizeof(double) * Nx * WENO5_NBND);
+                memcpy(pl + (size_t)Nx * (ny + WENO5_NBND), pl + (size_t)Nx * WENO5_NBND, sizeof(double) * Nx * WENO5_NBND);
+            }
+    }
+    if (dt_next) {
+        double vx, vy;
+        memcpy(&vx, &vb[0], 8);
+        memcpy(&vy, &vb[1], 8);
+        const double dtx = P.dx / vx, dty = P.dy / vy;               // timestep(), Weno5_2D.jl:1930-1940
+        *dt_next = P.cfl / (1 / dtx + 1 / dty);
+        if (!(*dt_next > 0.0) || !std::isfinite(*dt_next))
+            return fail(WENO5_ERR_NUMERIC, "non-finite wave speed in the result (vxmax=%g vymax=%g)", vx, vy);
+    }
+    return 0;
 }
 
 // ------------------------------------------------------------------ host memory, instrumentation

@@ -736,14 +736,14 @@ void launch_entropy(double *const q9[9], const Geom &g, double gam, int roundtri
 // from S); 1-D twin Weno5_1D.jl:1038-1074.  Non-negative doubles order like their bit
 // patterns, so the grid-wide maximum is an integer atomicMax; NaN maps to the largest
 // pattern and is caught by dt_kernel.
-struct VmaxArgs { const double *q[9]; int NXI, NYI, pitch; double gam; unsigned long long *out; };
+struct VmaxArgs { const double *q[9]; int NXI, NYI, pitch; double gam; unsigned long long *out; int j0, j1; };
 
 __global__ void vmax_kernel(const VmaxArgs a)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x + G;
-    const int j = a.NYI > 1 ? blockIdx.y * blockDim.y + threadIdx.y + G : 0;
+    const int j = a.NYI > 1 ? blockIdx.y * blockDim.y + threadIdx.y + a.j0 : 0;
     double vxm = 0.0, vym = 0.0;
-    if (i < a.NXI - G && (a.NYI == 1 || j < a.NYI - G)) {
+    if (i < a.NXI - G && (a.NYI == 1 || j < a.j1)) {
         const size_t g = (size_t)i + (size_t)a.pitch * j;
         // same quantities as the reference loop (Weno5_2D.jl:1950-1979); the six divisions by the face
         // density share one branch-free reciprocal and the square roots are branch-free (~1 ulp)
@@ -790,11 +790,19 @@ __global__ void vmax_kernel(const VmaxArgs a)
 void launch_vmax(const double *const q9[9], const Geom &g, double gam, unsigned long long *vmax_bits,
                  cudaStream_t s)
 {
+    launch_vmax_rows(q9, g, gam, vmax_bits, G, g.NYI - G, 1, s);
+}
+
+// rows [j0, j1) (internal indices) only; with zero_first == 0 the maxima accumulate into vmax_bits
+void launch_vmax_rows(const double *const q9[9], const Geom &g, double gam, unsigned long long *vmax_bits, int j0, int j1,
+                      int zero_first, cudaStream_t s)
+{
     VmaxArgs a;
     for (int k = 0; k < 9; ++k) a.q[k] = q9[k];
     a.NXI = g.NXI; a.NYI = g.NYI; a.pitch = g.pitch; a.gam = gam; a.out = vmax_bits;
-    cudaMemsetAsync(vmax_bits, 0, 2 * sizeof(unsigned long long), s);
-    dim3 block(64, 4), grid((g.NXI - 2 * G + 63) / 64, g.NYI > 1 ? (g.NYI - 2 * G + 3) / 4 : 1);
+    a.j0 = g.NYI > 1 ? j0 : 0; a.j1 = g.NYI > 1 ? j1 : 1;
+    if (zero_first) cudaMemsetAsync(vmax_bits, 0, 2 * sizeof(unsigned long long), s);
+    dim3 block(64, 4), grid((g.NXI - 2 * G + 63) / 64, g.NYI > 1 ? (a.j1 - a.j0 + 3) / 4 : 1);
     vmax_kernel<<<grid, block, 0, s>>>(a);
 }
 

@@ -80,6 +80,8 @@ void launch_entropy(double *const q9[9], const Geom &g, double gam, int roundtri
                     const double *dtp, cudaStream_t s);
 void launch_vmax(const double *const q9[9], const Geom &g, double gam, unsigned long long *vmax_bits,
                  cudaStream_t s);
+void launch_vmax_rows(const double *const q9[9], const Geom &g, double gam, unsigned long long *vmax_bits, int j0, int j1,
+                      int zero_first, cudaStream_t s);
 // ctl[0]=dt ctl[1]=t ctl[2]=vxmax ctl[3]=vymax ctl[4]=tmax ctl[5]=steps_done ctl[6]=bad-flag
 void launch_dt_from_vmax(const unsigned long long *vmax_bits, double *ctl, double dx, double dy,
                          double cfl, int is1d, cudaStream_t s);

@@ -17,7 +17,7 @@ module Weno5GPU
 
 export Weno5Params, Solver, upload!, download, boundaries!, timestep, classical_RK4_step,
        classical_RK4_step!, advance!, compute_divB, compute_global_vmax, interpolateB_center2face,
-       state2conserved, WENO5_2D, WENO5_1D
+       state2conserved, WENO5_2D, WENO5_1D, Pipe, pipe_step!
 
 const NBnd = 3                                    # Weno5_2D.jl:9
 const BC_OUTFLOW, BC_PERIODIC = Cint(0), Cint(1)
@@ -140,6 +140,31 @@ function classical_RK4_step(p::Weno5Params, q::Array{Float64,2}, dt::Float64)
     q4 = similar(q)
     check(ccall((:weno5_classical_rk4_step_1d, libweno5), Cint, (Ref{Weno5Params}, Ptr{Float64}, Cdouble, Ptr{Float64}), p, q, dt, q4))
     return q4
+end
+
+"""
+Pipelined host -> host classical_RK4_step (weno5_pipe_*): the grid streams through the GPU in y-slabs
+so that upload, compute and download overlap.  `pipe_step!(pipe, q, bxb, byb, dt, q4, bxb4, byb4)`
+fills the preallocated outputs (which must not alias the inputs) and returns timestep(q4).
+"""
+mutable struct Pipe
+    h::Ptr{Cvoid}
+    function Pipe(p::Weno5Params; device::Integer=0, rows_per_slab::Integer=512)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:weno5_pipe_create, libweno5), Cint, (Ref{Weno5Params}, Cint, Cint, Ref{Ptr{Cvoid}}), p, device, rows_per_slab, h))
+        s = new(h[])
+        finalizer(x -> (x.h != C_NULL && ccall((:weno5_pipe_destroy, libweno5), Cint, (Ptr{Cvoid},), x.h); x.h = C_NULL), s)
+        return s
+    end
+end
+
+function pipe_step!(p::Pipe, q::Array{Float64,3}, bxb::Array{Float64,2}, byb::Array{Float64,2}, dt::Real,
+                    q4::Array{Float64,3}, bxb4::Array{Float64,2}, byb4::Array{Float64,2})
+    dtn = Ref(0.0)
+    check(ccall((:weno5_pipe_step, libweno5), Cint,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cdouble, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}),
+                p.h, q, bxb, byb, dt, q4, bxb4, byb4, dtn))
+    return dtn[]
 end
 
 function interpolateB_center2face(p::Weno5Params, q::Array{Float64,3})

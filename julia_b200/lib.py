@@ -54,6 +54,9 @@ SIGNATURES = {
     "weno5_classical_rk4_step_2d": (C.c_int, [C.POINTER(Params), _dp, _dp, _dp, C.c_double, _dp, _dp, _dp]),
     "weno5_classical_rk4_step_1d": (C.c_int, [C.POINTER(Params), _dp, C.c_double, _dp]),
     "weno5_step_host": (C.c_int, [_vp, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp]),
+    "weno5_pipe_create": (C.c_int, [C.POINTER(Params), C.c_int, C.c_int, C.POINTER(_vp)]),
+    "weno5_pipe_step": (C.c_int, [_vp, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp, _dp]),
+    "weno5_pipe_destroy": (C.c_int, [_vp]),
     "weno5_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_ulonglong]),
     "weno5_host_free": (C.c_int, [_vp]),
     "weno5_launch_count": (C.c_ulonglong, [_vp]),

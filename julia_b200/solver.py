@@ -157,6 +157,43 @@ class Solver:
         return d
 
 
+class Pipe:
+    """Pipelined host -> host classical_RK4_step: y-slabs with overlap rows stream through the GPU so
+    that upload, compute and download overlap (weno5_pipe_* in include/weno5mhd.h)."""
+
+    def __init__(self, g, device=0, rows_per_slab=512, es_roundtrip=True):
+        self.lib = L.load()
+        self.g = g
+        self.params = make_params(g, es_roundtrip)
+        h = C.c_void_p()
+        L.check(self.lib.weno5_pipe_create(C.byref(self.params), device, int(rows_per_slab), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.weno5_pipe_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def step(self, q, bxb, byb, dt, out=None):
+        """(q4, bxb4, byb4, dt_next); `out` = preallocated (q4, bxb4, byb4), must not alias the inputs."""
+        g = self.g
+        q, bxb, byb = _farr(q, (g.Nx, g.Ny, 9)), _farr(bxb, (g.Nx, g.Ny)), _farr(byb, (g.Nx, g.Ny))
+        if out is None:
+            out = (np.zeros_like(q, order="F"), np.zeros_like(bxb, order="F"), np.zeros_like(byb, order="F"))
+        dtn = C.c_double()
+        L.check(self.lib.weno5_pipe_step(self.h, L.dptr(q), L.dptr(bxb), L.dptr(byb), float(dt),
+                                         L.dptr(out[0]), L.dptr(out[1]), L.dptr(out[2]), C.byref(dtn)))
+        return out[0], out[1], out[2], dtn.value
+
+
 # ----------------------------------------------------------------------------- reference-shaped API
 def classical_RK4_step(g, q, bxb=None, byb=None, dt=None, es_roundtrip=True):
     """Weno5_2D.jl:125 ``classical_RK4_step(q,bxb,byb,dt) -> (q4,bxb4,byb4)``;
