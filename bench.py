@@ -185,6 +185,73 @@ def pinned_array(lib, shape):
     return a, p
 
 
+def run_e2e(args, lib, L, s, q, bx, by, gglob, local, world, cells_global, nyl, sync_all, torch, dist):
+    """End-to-end arm: host arrays in, host arrays out, every step (see module docstring)."""
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    hq, pq = pinned_array(lib, q.shape)
+    hbx, pbx = pinned_array(lib, bx.shape)
+    hby, pby = pinned_array(lib, by.shape)
+    hq[...] = q
+    hbx[...] = bx
+    hby[...] = by
+    for _ in range(1):                                   # warm the path once
+        s.upload(hq, hbx, hby)
+        dt = s.timestep()[0]
+        s.rk4_step(dt)
+        L.check(lib.weno5_download(s.h, L.dptr(hq), L.dptr(hbx), L.dptr(hby)))
+    sync_all()
+    t0 = time.time()
+    for _ in range(e2e_steps):
+        s.upload(hq, hbx, hby)
+        dt = s.timestep()[0]
+        s.rk4_step(dt)
+        L.check(lib.weno5_download(s.h, L.dptr(hq), L.dptr(hbx), L.dptr(hby)))
+    sync_all()
+    e2e_s = time.time() - t0
+    if world > 1:
+        tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    bytes_dir = 11 * q.shape[0] * q.shape[1] * 8
+    e2e_seq = {"value": cells_global * e2e_steps / e2e_s, "unit": "cell-updates/s", "h2d_bytes_per_step": bytes_dir,
+               "d2h_bytes_per_step": bytes_dir, "steps": e2e_steps,
+               "calls": "weno5_upload -> weno5_timestep -> weno5_rk4_step -> weno5_download, pinned host arrays"}
+    e2e = e2e_seq
+
+    # single GPU: the pipelined host step (y-slabs with overlap rows; H2D, compute and D2H overlap)
+    if world == 1 and nyl >= 1024:
+        from julia_b200.solver import Pipe
+        rows = 512
+        oq, poq = pinned_array(lib, q.shape)
+        obx, pobx = pinned_array(lib, bx.shape)
+        oby, poby = pinned_array(lib, by.shape)
+        dt0 = s.timestep()[0]                             # time step of the state in hq (it is the resident one)
+        with Pipe(gglob, device=local, rows_per_slab=rows, es_roundtrip=bool(args.es_roundtrip)) as pipe:
+            a_in, a_out = (hq, hbx, hby), (oq, obx, oby)
+            _, _, _, dtn = pipe.step(*a_in, dt0, out=a_out)          # warm-up
+            a_in, a_out = a_out, a_in
+            psteps = max(1, min(args.steps, 2 * args.e2e_steps))
+            torch.cuda.synchronize()
+            t0 = time.time()
+            for _ in range(psteps):
+                _, _, _, dtn = pipe.step(*a_in, dtn, out=a_out)
+                a_in, a_out = a_out, a_in
+            torch.cuda.synchronize()
+            pipe_s = time.time() - t0
+        nslab = (nyl + rows - 1) // rows
+        up_rows = nslab * (rows + 2 * 16 + 8)
+        e2e = {"value": cells_global * psteps / pipe_s, "unit": "cell-updates/s",
+               "h2d_bytes_per_step": 11 * q.shape[0] * up_rows * 8, "d2h_bytes_per_step": bytes_dir, "steps": psteps,
+               "calls": "weno5_pipe_step(q0,bxb0,byb0,dt) -> (q4,bxb4,byb4,dt_next): host arrays in, host arrays out, "
+                        f"{nslab} y-slabs of {rows}+32 rows on 3 streams (copies and compute overlap), pinned host arrays",
+               "sequential": e2e_seq}
+        for p_ in (poq, pobx, poby):
+            lib.weno5_host_free(p_)
+    for p in (pq, pbx, pby):
+        lib.weno5_host_free(p)
+    return e2e
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -253,69 +320,10 @@ def run_gpu(args):
     value = cells_global * args.steps / (ms * 1e-3)
 
     # ---- end to end through host buffers (reference-shaped call sequence)
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    hq, pq = pinned_array(lib, q.shape)
-    hbx, pbx = pinned_array(lib, bx.shape)
-    hby, pby = pinned_array(lib, by.shape)
-    hq[...] = q
-    hbx[...] = bx
-    hby[...] = by
-    for _ in range(1):                                   # warm the path once
-        s.upload(hq, hbx, hby)
-        dt = s.timestep()[0]
-        s.rk4_step(dt)
-        L.check(lib.weno5_download(s.h, L.dptr(hq), L.dptr(hbx), L.dptr(hby)))
-    sync_all()
-    t0 = time.time()
-    for _ in range(e2e_steps):
-        s.upload(hq, hbx, hby)
-        dt = s.timestep()[0]
-        s.rk4_step(dt)
-        L.check(lib.weno5_download(s.h, L.dptr(hq), L.dptr(hbx), L.dptr(hby)))
-    sync_all()
-    e2e_s = time.time() - t0
-    if world > 1:
-        tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_s = float(tt.item())
-    bytes_dir = 11 * q.shape[0] * q.shape[1] * 8
-    e2e_seq = {"value": cells_global * e2e_steps / e2e_s, "unit": "cell-updates/s", "h2d_bytes_per_step": bytes_dir,
-               "d2h_bytes_per_step": bytes_dir, "steps": e2e_steps,
-               "calls": "weno5_upload -> weno5_timestep -> weno5_rk4_step -> weno5_download, pinned host arrays"}
-    e2e = e2e_seq
+    e2e = None
+    if args.e2e_steps > 0:
+        e2e = run_e2e(args, lib, L, s, q, bx, by, gglob, local, world, cells_global, nyl, sync_all, torch, dist)
 
-    # single GPU: the pipelined host step (y-slabs with overlap rows; H2D, compute and D2H overlap)
-    if world == 1 and nyl >= 1024:
-        from julia_b200.solver import Pipe
-        rows = 512
-        oq, poq = pinned_array(lib, q.shape)
-        obx, pobx = pinned_array(lib, bx.shape)
-        oby, poby = pinned_array(lib, by.shape)
-        dt0 = s.timestep()[0]                             # time step of the state in hq (it is the resident one)
-        with Pipe(gglob, device=local, rows_per_slab=rows, es_roundtrip=bool(args.es_roundtrip)) as pipe:
-            a_in, a_out = (hq, hbx, hby), (oq, obx, oby)
-            _, _, _, dtn = pipe.step(*a_in, dt0, out=a_out)          # warm-up
-            a_in, a_out = a_out, a_in
-            psteps = max(1, min(args.steps, 2 * args.e2e_steps))
-            torch.cuda.synchronize()
-            t0 = time.time()
-            for _ in range(psteps):
-                _, _, _, dtn = pipe.step(*a_in, dtn, out=a_out)
-                a_in, a_out = a_out, a_in
-            torch.cuda.synchronize()
-            pipe_s = time.time() - t0
-        nslab = (nyl + rows - 1) // rows
-        up_rows = nslab * (rows + 2 * 16 + 8)
-        e2e = {"value": cells_global * psteps / pipe_s, "unit": "cell-updates/s",
-               "h2d_bytes_per_step": 11 * q.shape[0] * up_rows * 8, "d2h_bytes_per_step": bytes_dir, "steps": psteps,
-               "calls": "weno5_pipe_step(q0,bxb0,byb0,dt) -> (q4,bxb4,byb4,dt_next): host arrays in, host arrays out, "
-                        f"{nslab} y-slabs of {rows}+32 rows on 3 streams (copies and compute overlap), pinned host arrays",
-               "sequential": e2e_seq}
-        for p_ in (poq, pobx, poby):
-            lib.weno5_host_free(p_)
-    for p in (pq, pbx, pby):
-        lib.weno5_host_free(p)
-    e2e_value = e2e["value"]
 
     if rank == 0:
         sampler.stop()
