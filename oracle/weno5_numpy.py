@@ -7,10 +7,13 @@ This file is one of two independent CPU restatements (the other is the C oracle 
 (whole-grid temporaries, transposed copy for the y sweep) and is only ever imported
 by ``tests/`` -- never by the product path.
 
-PARITY UNPINNED: the reference ships no golden vectors / tests for this path and
-cannot be executed here (Julia 0.6 source, no ``julia`` binary).  What pins this file:
-algebraic identities (L.R = I, R diag(a) L = dF/dq), invariants, and agreement with the
-independently written C oracle (see tests/test_oracle_*.py).
+PARITY PINNED against outputs of the reference itself: the Julia 0.6 source is translated
+mechanically (oracle/jl2py.py) and its own functions are executed unmodified by
+scripts/make_reference_golden.py; tests/test_reference_pin.py checks this file against the
+committed vectors tests/golden/ref_*.npz (bit-identical functions, sweeps and full RK4
+step; the only deviation is quirk Q3 below).  Further pins: algebraic identities
+(L.R = I, R diag(a) L = dF/dq), invariants, and agreement with the independently written
+C oracle (tests/test_oracle.py).
 
 Index convention: arrays are numpy (Nx, Ny, C) with 0-based indices; a reference
 1-based index ``i`` is ``i-1`` here.  NBnd = 3 ghost cells on every side.

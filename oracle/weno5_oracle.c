@@ -6,9 +6,16 @@
  * CUDA path (tests/, __graft_entry__.smoke()) and the timed CPU baseline of bench.py;
  * nothing in the product (julia_b200/, libweno5mhd.so) may call, link or load it.
  *
- * PARITY UNPINNED: the reference has no golden vectors, known-answer tests or fixtures
- * for this path and cannot be run here (Julia 0.6 source; no julia binary).  This file
- * is pinned by (i) algebraic identities of the eigen-system, (ii) invariants
+ * PARITY PINNED against outputs of the reference itself: the reference (Julia 0.6 source;
+ * no julia binary here) is translated mechanically by oracle/jl2py.py and its own functions
+ * are executed unmodified by scripts/make_reference_golden.py; the resulting vectors are
+ * committed as tests/golden/ref_*.npz and checked by tests/test_reference_pin.py: every
+ * cell-local function, both sweeps (on all cells whose faces the reference computes in
+ * bounds), the constrained-transport pieces, boundaries!, timestep, the full 2-D RK4 step
+ * (periodic ghosts) and the 1-D RK4 step are BIT-IDENTICAL to the reference (E2S/S2E to
+ * 2 ulp of libm pow); with the reference's outflow boundaries! the step differs by the
+ * documented quirk Q3 (<= 1e-8 of the field scale on the reference's shock-cloud problem).
+ * Further pins: (i) algebraic identities of the eigen-system, (ii) invariants
  * (conservation, div B, uniform-state preservation), (iii) agreement to round-off with
  * the independently written numpy restatement oracle/weno5_numpy.py, which is
  * array-at-a-time and uses the reference's transpose/rotate formulation, while this file
