@@ -169,9 +169,9 @@ def workload_config(ngpu):
                         "periodic, gamma=5/3, CFL 0.8, dt recomputed every step",
             "nx": NX_PER_GPU, "ny_global": NY_PER_GPU * ngpu, "partition": f"y-slabs x{ngpu}",
             "l2": "no flush needed: ~6.5 GB of resident planes per GPU >> 126 MB L2",
-            "es_roundtrip": 0,
-            "note": "E is not round-tripped through S after each stage (the 1-D reference's form, Weno5_1D.jl:252-254); "
-                    "the 2-D reference's round trip changes results at the 1e-13 level (tests/test_gpu_parity.py)"}
+            "es_roundtrip": 1,
+            "note": "E <- S2E(E2S(E)) after every stage, exactly as the 2-D reference's ES_Switch does "
+                    "(Weno5_2D.jl:1738,1765); --es-roundtrip 0 selects the 1-D reference's form (keeps E, ~3% faster)"}
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -379,7 +379,7 @@ def main():
     ap.add_argument("--ny", type=int, default=NY_PER_GPU, help="rows per GPU")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--es-roundtrip", type=int, default=0, help="1: E <- S2E(E2S(E)) after every stage (2-D reference form)")
+    ap.add_argument("--es-roundtrip", type=int, default=1, help="1: E <- S2E(E2S(E)) after every stage (2-D reference form)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -220,8 +220,10 @@ static int create_ctx(const weno5_params *P, int device, int ny_local, int j_off
 {
     if (!P || !out) return fail(WENO5_ERR_ARG, "null argument");
     const bool is1d = P->ny == 1;
-    if (P->nx < 8 || (!is1d && (P->ny < 8 || ny_local < 8)))
-        return fail(WENO5_ERR_ARG, "grid too small: nx=%d ny=%d ny_local=%d (need >= 8, or ny = 1)", P->nx, P->ny, ny_local);
+    // a periodic ghost layer (4 cells internally) must map onto interior cells; the reference's own
+    // configuration is 16 x 4 cells (Weno5_2D.jl:11-12)
+    if (P->nx < 4 || (!is1d && (P->ny < 4 || ny_local < 4)))
+        return fail(WENO5_ERR_ARG, "grid too small: nx=%d ny=%d ny_local=%d (need >= 4, or ny = 1)", P->nx, P->ny, ny_local);
     if (is1d && (ny_local != 1 || j_offset != 0)) return fail(WENO5_ERR_ARG, "1-D grids cannot be decomposed");
     if (!is1d && side_lo < 0 && (j_offset < 0 || j_offset + ny_local > P->ny)) return fail(WENO5_ERR_ARG, "slab outside the grid");
     if (!(P->dx > 0) || (!is1d && !(P->dy > 0)) || !(P->gamma > 1.0)) return fail(WENO5_ERR_ARG, "bad dx/dy/gamma");
@@ -670,14 +672,16 @@ static int enqueue_stage(weno5_ctx *c, int stage, State &cur, State &nxt)
     // (a fused corner/face/centre kernel with halo recomputation in shared memory was measured 1.6 %
     // slower than these two launches and removed)
     launch_ct_faces(t, c->stream);
-    launch_ct_centers(nxt.bx, nxt.by, nxt.q[C_BX], nxt.q[C_BY], g, dtp, c->stream);
+    // cell-centred B from the new faces and, when this stage derives S (every stage with the 2-D
+    // reference's E -> S -> E round trip, else stage 4 only), the ES_Switch residue in the same pass
+    const bool ent = P.es_roundtrip || stage == 4;
+    if (ent) launch_ct_centers_entropy(nxt.bx, nxt.by, nxt.q, g, P.gamma, P.es_roundtrip, dtp, c->stream);
+    else launch_ct_centers(nxt.bx, nxt.by, nxt.q[C_BX], nxt.q[C_BY], g, dtp, c->stream);
     c->launches += 2;
     if (stage == 4) {                                   // boundaries!(q4, bxb4, byb4), Weno5_2D.jl:313
         launch_face_bc(nxt.bx, nxt.by, g, c->side, dtp, c->stream);
         c->launches++;
     }
-    const bool ent = P.es_roundtrip || stage == 4;
-    if (ent) { launch_entropy(nxt.q, g, P.gamma, P.es_roundtrip, 0, dtp, c->stream); c->launches++; }
     const int nfill = ent ? NCELL : 8;
     launch_bc_fill(nxt.q, nfill, g, c->side, dtp, c->stream);
     c->launches++;

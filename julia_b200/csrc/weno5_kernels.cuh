@@ -76,6 +76,8 @@ void launch_bc_fill(double *const planes[], int nplanes, const Geom &g, const in
                     const double *dtp, cudaStream_t s);
 void launch_halo_pack(double *const planes[], int n, const Geom &g, double *up, double *down, int has_up, int has_down,
                       int unpack, cudaStream_t s);
+void launch_ct_centers_entropy(const double *bxn, const double *byn, double *const q9[9], const Geom &g, double gam,
+                               int roundtrip, const double *dtp, cudaStream_t s);
 void launch_entropy(double *const q9[9], const Geom &g, double gam, int roundtrip, int all_cells,
                     const double *dtp, cudaStream_t s);
 void launch_vmax(const double *const q9[9], const Geom &g, double gam, unsigned long long *vmax_bits,

@@ -372,4 +372,18 @@ W5_HD double s2e(double rho, double m1, double m2, double m3, double b1, double 
     return pow(rho, gam - 1.0) * S / (gam - 1.0) + 0.5 * BB + 0.5 * mom2 / rho;
 }
 
+// E2S followed by S2E on the same cell (the residue of ES_Switch, Weno5_2D.jl:1738 and :1765): the two
+// functions above evaluate the same pow(rho, gam-1) and mom2/rho, so one evaluation serves both;
+// the results are bit-identical to calling e2s() and then s2e().
+W5_HD void e2s_s2e(double rho, double m1, double m2, double m3, double b1, double b2, double b3, double E, double gam,
+                   double &S, double &E2)
+{
+    const double mom2 = m1 * m1 + m2 * m2 + m3 * m3;
+    const double BB = b1 * b1 + b2 * b2 + b3 * b3;
+    const double pr = pow(rho, gam - 1.0);
+    const double kin = 0.5 * mom2 / rho;
+    S = (E - kin - 0.5 * BB) * (gam - 1.0) / pr;
+    E2 = pr * S / (gam - 1.0) + 0.5 * BB + kin;
+}
+
 }  // namespace w5

@@ -73,4 +73,6 @@ double hm_e2s(double rho, double m1, double m2, double m3, double b1, double b2,
 { return w5::e2s(rho, m1, m2, m3, b1, b2, b3, E, gam); }
 double hm_s2e(double rho, double m1, double m2, double m3, double b1, double b2, double b3, double S, double gam)
 { return w5::s2e(rho, m1, m2, m3, b1, b2, b3, S, gam); }
+void hm_e2s_s2e(double rho, double m1, double m2, double m3, double b1, double b2, double b3, double E, double gam, double *out)
+{ w5::e2s_s2e(rho, m1, m2, m3, b1, b2, b3, E, gam, out[0], out[1]); }
 }

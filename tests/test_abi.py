@@ -65,8 +65,8 @@ def test_no_cpu_fallback(built):
 def test_argument_validation(built):
     lib = L.load()
     h = C.c_void_p()
-    bad = L.Params(4, 4, 0.1, 0.1, 5 / 3, 0.8, 1e-6, 0, 0, 1)       # grid too small
-    assert lib.weno5_create(C.byref(bad), 0, 4, 0, C.byref(h)) == L.ERR_ARG
+    bad = L.Params(3, 3, 0.1, 0.1, 5 / 3, 0.8, 1e-6, 0, 0, 1)       # grid too small (the reference ships 16 x 4)
+    assert lib.weno5_create(C.byref(bad), 0, 3, 0, C.byref(h)) == L.ERR_ARG
     bad = L.Params(32, 32, 0.1, 0.1, 5 / 3, 0.8, 1e-6, 0, 7, 1)     # unknown BC
     assert lib.weno5_create(C.byref(bad), 0, 32, 0, C.byref(h)) == L.ERR_ARG
     bad = L.Params(32, 32, 0.1, 0.1, 5 / 3, 0.8, 1e-6, 0, 0, 1)     # slab outside the grid
