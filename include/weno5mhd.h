@@ -100,6 +100,18 @@ int weno5_divb(weno5_ctx *ctx, double *divb);
  * cf. the per-component max/mean print at Weno5_2D.jl:69-71); local to this rank */
 int weno5_totals(weno5_ctx *ctx, double sums[11]);
 
+/* ---- dual-energy mode (SURVEY "next" row f3).  The shipped reference computes both the E sweeps
+ * (weno5_flux_difference_E, Weno5_2D.jl:973) and the entropy-variable S sweeps (weno5_flux_difference_S, :361)
+ * every stage and then discards the S state, because ES_Switch (:1734-1768) has its criterion commented out
+ * (`dS = 1`, :1741).  With enable = 1 the step runs both branches and applies the criterion the reference
+ * wrote and disabled (:1740): cells whose entropy derived from the E state differs from the advected entropy by
+ * >= threshold (reference value 1e-5) take the E state, all others the S state, and the constrained-transport
+ * seed fluxes follow the selection (:1754-1758).  enable = 0 (the default) is the shipped behaviour.
+ * 2-D, undivided grids.  weno5_es_switch_count returns the number of interior cells that took the E state in
+ * the most recent stage. */
+int weno5_set_es_switch(weno5_ctx *ctx, int enable, double threshold);
+int weno5_es_switch_count(weno5_ctx *ctx, unsigned long long *cells);
+
 /* ---- one-shot, reference-shaped calls: host arrays in -> host arrays out */
 /* (q4,bxb4,byb4) = classical_RK4_step(q0,bxb0,byb0,dt)   Weno5_2D.jl:125-317 */
 int weno5_classical_rk4_step_2d(const weno5_params *params, const double *q0, const double *bxb0,

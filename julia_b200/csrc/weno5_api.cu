@@ -144,6 +144,14 @@ struct weno5_ctx {
     CUtensorMap tmap_x[4], tmap_y[4];        // boxes of 8, 6, 4, 2 planes
     bool have_tmap = false;
     size_t nplanes = 0;
+    // dual-energy mode (weno5_set_es_switch): both branches are swept and ES_Switch selects per cell
+    bool dual = false;
+    double es_threshold = 1e-5;
+    double *dual_pool = nullptr;
+    double *candE[8], *candS[8];     // candidate states: rho,Mx,My,Mz,Bz,E|S,Bx,By
+    double *accS[6];                 // RK accumulators of the S run (rho,Mx,My,Mz,Bz duplicate the E run's)
+    double *fsyS, *gsxS, *tbx, *tby, *flag;
+    unsigned long long switched = 0; // cells that took the E state in the last stage (diagnostic)
 };
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point: no link-time libcuda dependency
@@ -326,6 +334,7 @@ extern "C" int weno5_destroy(weno5_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    if (c->dual_pool) cudaFree(c->dual_pool);
     if (c->ev_main) cudaEventDestroy(c->ev_main);
     if (c->ev_comm) cudaEventDestroy(c->ev_comm);
     if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
@@ -690,8 +699,111 @@ static int enqueue_stage(weno5_ctx *c, int stage, State &cur, State &nxt)
     return 0;
 }
 
+// One RK stage with both branches live (Weno5_2D.jl:134-180): E sweeps -> E candidate, S sweeps -> S candidate,
+// constrained transport for each (their cell-centred B enters E2S / S2E), ES_Switch, selection of the CT seed
+// fluxes, constrained transport with the selected fluxes.  Single GPU, 2-D.
+static int enqueue_stage_dual(weno5_ctx *c, int stage, State &cur, State &nxt)
+{
+    static const double ck[4] = {0.5, 0.5, 1.0, 1.0 / 6.0};
+    const weno5_params &P = c->P;
+    const Geom &g = c->g;
+    const double *dtp = c->ctl;
+    static const int sixE[6] = {C_RHO, C_MX, C_MY, C_MZ, C_BZ, C_E};
+    static const int sixS[6] = {C_RHO, C_MX, C_MY, C_MZ, C_BZ, C_S};
+    auto plane_of = [&](const double *p) { return (int)((p - c->pool) / (ptrdiff_t)g.plane); };
+
+    for (int br = 0; br < 2; ++br) {
+        const int *six = br == 0 ? sixE : sixS;
+        FluxArgs a;
+        memset(&a, 0, sizeof(a));
+        for (int k = 0; k < 7; ++k) a.qc[k] = cur.q[k];
+        a.qc[7] = cur.q[br == 0 ? C_E : C_S];
+        for (int k = 0; k < 7; ++k) a.rhs[k] = c->rhs[k];
+        a.dtp = dtp;
+        a.c_dx = ck[stage - 1] / P.dx;
+        a.c_dy = ck[stage - 1] / P.dy;
+        a.stage = stage;
+        a.gam = P.gamma; a.eps = P.eps;
+        a.pitch = g.pitch;
+        a.branch = br;
+        const bool tma = br == 0 && c->have_tmap;
+        a.tmap_x = tma ? c->tmap_x : nullptr;
+        a.tmap_y = tma ? c->tmap_y : nullptr;
+        if (tma) {
+            for (int k = 0; k < 8; ++k) a.qc_plane[k] = plane_of(cur.q[k]);
+            for (int k = 0; k < 7; ++k) a.rhs_plane[k] = plane_of(c->rhs[k]);
+        }
+        a.N = g.NXI; a.NP = g.NYI; a.bs = br == 0 ? c->fsy : c->fsyS;
+        a.seg_len = c->segx_len; a.nseg = c->nsegx;
+        launch_flux_x(a, c->stream);
+        a.N = g.NYI; a.NP = g.NXI; a.bs = br == 0 ? c->gsx : c->gsxS;
+        a.seg_len = c->segy_len; a.nseg = c->nsegy;
+        for (int k = 0; k < 6; ++k) {
+            a.base[k] = c->Q0.q[six[k]];
+            a.acc[k] = br == 0 ? c->acc[k] : c->accS[k];
+            a.qn[k] = br == 0 ? c->candE[k] : c->candS[k];
+            if (tma) { a.base_plane[k] = plane_of(a.base[k]); a.acc_plane[k] = plane_of(a.acc[k]); }
+        }
+        launch_flux_y(a, c->stream);
+        c->launches += 2;
+    }
+
+    CtArgs t;
+    memset(&t, 0, sizeof(t));
+    t.bx0 = c->Q0.bx; t.by0 = c->Q0.by; t.bxc = cur.bx; t.byc = cur.by;
+    t.accbx = c->accbx; t.accby = c->accby;
+    t.dtp = dtp; t.c_dx = ck[stage - 1] / P.dx; t.c_dy = ck[stage - 1] / P.dy; t.stage = stage;
+    t.Nx = g.Nx; t.Ny = g.Ny; t.pitch = g.pitch;
+    t.oxlo = c->side[0] == SIDE_OUTFLOW; t.oxhi = c->side[1] == SIDE_OUTFLOW;
+    t.oylo = c->side[2] == SIDE_OUTFLOW; t.oyhi = c->side[3] == SIDE_OUTFLOW;
+    t.bx_i0 = t.oxlo ? 1 : 2; t.bx_i1 = t.oxhi ? g.Nx : g.Nx - 2;
+    t.bx_j0 = t.oylo ? 1 : 3; t.bx_j1 = t.oyhi ? g.Ny : g.Ny - 2;
+    t.by_i0 = t.oxlo ? 1 : 3; t.by_i1 = t.oxhi ? g.Nx : g.Nx - 2;
+    t.by_j0 = t.oylo ? 1 : 2; t.by_j1 = t.oyhi ? g.Ny : g.Ny - 2;
+    // candidate face fields only feed the candidates' cell-centred B (:150-153, :168-170)
+    t.no_acc = 1; t.bxn = c->tbx; t.byn = c->tby;
+    t.fsy = c->fsy; t.gsx = c->gsx;
+    launch_ct_faces(t, c->stream);
+    launch_ct_centers(c->tbx, c->tby, c->candE[6], c->candE[7], g, dtp, c->stream);
+    t.fsy = c->fsyS; t.gsx = c->gsxS;
+    launch_ct_faces(t, c->stream);
+    launch_ct_centers(c->tbx, c->tby, c->candS[6], c->candS[7], g, dtp, c->stream);
+
+    SwitchArgs w;
+    for (int k = 0; k < 8; ++k) { w.ce[k] = c->candE[k]; w.cs[k] = c->candS[k]; }
+    static const int sel[7] = {C_RHO, C_MX, C_MY, C_MZ, C_BZ, C_S, C_E};
+    for (int k = 0; k < 7; ++k) w.qn[k] = nxt.q[sel[k]];
+    w.flag = c->flag;
+    w.NXI = g.NXI; w.NYI = g.NYI; w.pitch = g.pitch; w.gam = P.gamma; w.threshold = c->es_threshold; w.dtp = dtp;
+    launch_es_switch(w, c->stream);
+    double *fl[1] = {c->flag};
+    launch_bc_fill(fl, 1, g, c->side, dtp, c->stream);
+    launch_flux_select(c->flag, c->fsy, c->gsx, c->fsyS, c->gsxS, g, dtp, c->stream);
+
+    // constrained transport with the selected seed fluxes (:175-180)
+    t.no_acc = 0; t.bxn = nxt.bx; t.byn = nxt.by;
+    launch_ct_faces(t, c->stream);
+    launch_ct_centers(nxt.bx, nxt.by, nxt.q[C_BX], nxt.q[C_BY], g, dtp, c->stream);
+    c->launches += 9;
+    if (stage == 4) {
+        launch_face_bc(nxt.bx, nxt.by, g, c->side, dtp, c->stream);
+        c->launches++;
+    }
+    launch_bc_fill(nxt.q, NCELL, g, c->side, dtp, c->stream);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
 static int enqueue_step(weno5_ctx *c)
 {
+    if (c->dual) {
+        if (int r = enqueue_stage_dual(c, 1, c->Q0, c->QA)) return r;
+        if (int r = enqueue_stage_dual(c, 2, c->QA, c->QB)) return r;
+        if (int r = enqueue_stage_dual(c, 3, c->QB, c->QA)) return r;
+        if (int r = enqueue_stage_dual(c, 4, c->QA, c->Q0)) return r;
+        return 0;
+    }
     if (int r = enqueue_stage(c, 1, c->Q0, c->QA)) return r;
     if (int r = enqueue_stage(c, 2, c->QA, c->QB)) return r;
     if (int r = enqueue_stage(c, 3, c->QB, c->QA)) return r;
@@ -741,6 +853,52 @@ extern "C" int weno5_advance(weno5_ctx *c, int nsteps, double tmax, double *t, i
     if (t) *t = c->h_ctl[1];
     if (nsteps_done) *nsteps_done = (int)c->h_ctl[5];
     if (c->h_ctl[6] != 0.0) return fail(WENO5_ERR_NUMERIC, "non-finite wave speed / time step at t=%g", c->h_ctl[1]);
+    return 0;
+}
+
+// ------------------------------------------------------------------ dual-energy mode
+extern "C" int weno5_set_es_switch(weno5_ctx *c, int enable, double threshold)
+{
+    if (!c) return fail(WENO5_ERR_ARG, "null argument");
+    if (!enable) { c->dual = false; return 0; }
+    if (c->g.is1d) return fail(WENO5_ERR_ARG, "the dual-energy switch is implemented for 2-D grids");
+    if (c->comm || c->ny_local != c->P.ny) return fail(WENO5_ERR_ARG, "the dual-energy switch runs on undivided grids (one GPU)");
+    if (!(threshold >= 0.0)) return fail(WENO5_ERR_ARG, "threshold must be >= 0 (the reference uses 1e-5)");
+    CU(cudaSetDevice(c->device));
+    const Geom &g = c->g;
+    if (!c->dual_pool) {
+        const size_t n = 8 + 8 + 6 + 5;
+        if (cudaMalloc(&c->dual_pool, n * g.plane * sizeof(double)) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(WENO5_ERR_CUDA, "cudaMalloc of %.2f GB for the dual-energy planes failed", n * g.plane * 8.0 / 1e9);
+        }
+        CU(cudaMemsetAsync(c->dual_pool, 0, n * g.plane * sizeof(double), c->stream));
+        double *cur = c->dual_pool;
+        for (int k = 0; k < 8; ++k) { c->candE[k] = cur; cur += g.plane; }
+        for (int k = 0; k < 8; ++k) { c->candS[k] = cur; cur += g.plane; }
+        for (int k = 0; k < 6; ++k) { c->accS[k] = cur; cur += g.plane; }
+        c->fsyS = cur; cur += g.plane;
+        c->gsxS = cur; cur += g.plane;
+        c->tbx = cur; cur += g.plane;
+        c->tby = cur; cur += g.plane;
+        c->flag = cur; cur += g.plane;
+    }
+    c->dual = true;
+    c->es_threshold = threshold;
+    return 0;
+}
+
+extern "C" int weno5_es_switch_count(weno5_ctx *c, unsigned long long *cells)
+{
+    if (!c || !cells) return fail(WENO5_ERR_ARG, "null argument");
+    if (!c->dual) return fail(WENO5_ERR_STATE, "the dual-energy switch is off");
+    CU(cudaSetDevice(c->device));
+    const double *pl[1] = {c->flag};
+    launch_totals(pl, 1, c->g, c->sums, c->stream);
+    c->launches++;
+    CU(cudaMemcpyAsync(c->h_ctl, c->sums, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *cells = (unsigned long long)(c->h_ctl[0] + 0.5);
     return 0;
 }
 

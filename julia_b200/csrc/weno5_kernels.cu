@@ -27,7 +27,7 @@ namespace w5 {
 // 64 faces, DIR 1 (y sweep) NT/YW face rows of YW columns -- lanes always run along x so that
 // global accesses are coalesced in both sweeps.  Cell data lives in a ring of RS = NS + 5 slots
 // along the sweep (the 5 trailing stencil cells of a chunk stay where they are for the next one).
-template <int DIR, int NT, int YW> struct Tile {
+template <int DIR, int NT, int YW, int NCQ = CQ_COUNT> struct Tile {
     static constexpr int NS = DIR == 0 ? 64 : NT / YW;     // faces along the sweep per chunk
     static constexpr int NPB = DIR == 0 ? NT / 64 : YW;    // lines across the sweep per CTA
     static constexpr int RS = (NS + 5 + 15) / 16 * 16;     // ring slots along the sweep (>= NS + 5; a multiple of
@@ -40,7 +40,7 @@ template <int DIR, int NT, int YW> struct Tile {
     // box is 2 cells wider and starts at c0 - (c0 & 1); threads read at offset +(c0 & 1).
     static constexpr int BOX_X = DIR == 0 ? NS + 2 : NPB, BOX_Y = DIR == 0 ? NPB : NS;
     static constexpr int FST = BOX_X * BOX_Y;              // staging stride per field (one multi-plane TMA box is contiguous)
-    static constexpr int OFFQ = (CQ_COUNT * CBS + 7 * FBS + 15) / 16 * 16;   // 128-byte aligned (TMA destination)
+    static constexpr int OFFQ = (NCQ * CBS + 7 * FBS + 15) / 16 * 16;        // 128-byte aligned (TMA destination)
     static constexpr int STQ = 8 * FST;                    // staged raw state of the next chunk
     static constexpr int STU = DIR == 0 ? 0 : 18 * FST;    // staged RK operands (rhs, base, acc)
     static constexpr int SMEM = (OFFQ + (STQ + 15) / 16 * 16 + STU) * (int)sizeof(double) + 16;
@@ -101,11 +101,21 @@ __device__ __forceinline__ size_t cell_index(const FluxArgs &a, int c, int line)
 }
 
 // cons->prim, eigenvalues, flux of one cell -> shared memory entry i.  q is in the sweep frame.
-template <int CBS>
+// BR 1 (entropy branch): q[7] = S; two more ring entries, P(S) and rho^(1-gam), feed the face average
+constexpr int CQ_P = CQ_COUNT, CQ_RG0 = CQ_COUNT + 1, CQ_COUNT_S = CQ_COUNT + 2;
+
+template <int CBS, int BR = 0>
 __device__ __forceinline__ void cell_store(const FluxArgs &a, double *cb, const double q[8], int i)
 {
     CellOut o;
-    cell_quantities(q, a.gam, o);
+    if constexpr (BR == 0) {
+        cell_quantities(q, a.gam, o);
+    } else {
+        CellOutS os;
+        cell_quantities_S(q, a.gam, o, os);
+        cb[CQ_P * CBS + i] = os.P;
+        cb[CQ_RG0 * CBS + i] = os.rg0;
+    }
 #pragma unroll
     for (int m = 0; m < 7; ++m) cb[(CQ_F0 + m) * CBS + i] = o.F[m];
     cb[(CQ_Q0 + 0) * CBS + i] = q[0];
@@ -164,15 +174,16 @@ __device__ __forceinline__ void tma_issue_operands(const FluxArgs &a, const Flux
     if (a.stage >= 3) tma_load_box(stu + 12 * T::FST, &tm->m6, bx, s0, a.acc_plane[0], bar);
 }
 
-template <int DIR, int NT, int YW, int MINB, bool TMA>
+template <int DIR, int NT, int YW, int MINB, bool TMA, int BR = 0>
 __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a, const __grid_constant__ FluxMaps tmap)
 {
-    using T = Tile<DIR, NT, YW>;
+    constexpr int NCQ = BR == 0 ? CQ_COUNT : CQ_COUNT_S;
+    using T = Tile<DIR, NT, YW, NCQ>;
     constexpr int NS = T::NS, NPB = T::NPB, RS = T::RS;
     constexpr int CBS = T::CBS, FBS = T::FBS;
     extern __shared__ __align__(128) double sm[];
     double *cb = sm;
-    double *fb = sm + CQ_COUNT * CBS;
+    double *fb = sm + NCQ * CBS;
     double *stq = sm + T::OFFQ;                  // [8][NT]   raw state of the next chunk
     double *stu = stq + (T::STQ + 15) / 16 * 16; // [18][NT]  rhs, base, acc of this chunk (y sweep)
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(stu + T::STU);   // [0] state, [1] operands
@@ -227,7 +238,7 @@ __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a, const 
         double q[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) q[k] = __ldg(a.qc[perm<DIR>(k)] + g);
-        cell_store<CBS>(a, cb, q, T::cbi(sl, pp));
+        cell_store<CBS, BR>(a, cb, q, T::cbi(sl, pp));
     }
 
     int r0 = 0;                                  // ring slot of cell s0 - 2
@@ -248,7 +259,7 @@ __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a, const 
             double q[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) q[k] = stq[perm<DIR>(k) * T::FST + si];     // staged in physical plane order
-            cell_store<CBS>(a, cb, q, T::cbi(sl[5], p));
+            cell_store<CBS, BR>(a, cb, q, T::cbi(sl[5], p));
         }
         __syncthreads();
 
@@ -286,11 +297,18 @@ __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a, const 
         if (f < fB) {
             const int iL = T::cbi(sl[2], p), iR = T::cbi(sl[3], p);
             FaceCoef fc;
-            face_coefficients(cb[CQ_Q0 * CBS + iL], cb[CQ_Q0 * CBS + iR], cb[CQ_V1 * CBS + iL], cb[CQ_V1 * CBS + iR],
-                              cb[CQ_V2 * CBS + iL], cb[CQ_V2 * CBS + iR], cb[CQ_V3 * CBS + iL], cb[CQ_V3 * CBS + iR],
-                              cb[CQ_B1 * CBS + iL], cb[CQ_B1 * CBS + iR], cb[(CQ_Q0 + 4) * CBS + iL],
-                              cb[(CQ_Q0 + 4) * CBS + iR], cb[(CQ_Q0 + 5) * CBS + iL], cb[(CQ_Q0 + 5) * CBS + iR],
-                              cb[(CQ_Q0 + 6) * CBS + iL], cb[(CQ_Q0 + 6) * CBS + iR], a.gam, fc);
+            if constexpr (BR == 0)
+                face_coefficients(cb[CQ_Q0 * CBS + iL], cb[CQ_Q0 * CBS + iR], cb[CQ_V1 * CBS + iL], cb[CQ_V1 * CBS + iR],
+                                  cb[CQ_V2 * CBS + iL], cb[CQ_V2 * CBS + iR], cb[CQ_V3 * CBS + iL], cb[CQ_V3 * CBS + iR],
+                                  cb[CQ_B1 * CBS + iL], cb[CQ_B1 * CBS + iR], cb[(CQ_Q0 + 4) * CBS + iL],
+                                  cb[(CQ_Q0 + 4) * CBS + iR], cb[(CQ_Q0 + 5) * CBS + iL], cb[(CQ_Q0 + 5) * CBS + iR],
+                                  cb[(CQ_Q0 + 6) * CBS + iL], cb[(CQ_Q0 + 6) * CBS + iR], a.gam, fc);
+            else
+                face_coefficients_S(cb[CQ_Q0 * CBS + iL], cb[CQ_Q0 * CBS + iR], cb[CQ_RG0 * CBS + iL], cb[CQ_RG0 * CBS + iR],
+                                    cb[CQ_V1 * CBS + iL], cb[CQ_V1 * CBS + iR], cb[CQ_V2 * CBS + iL], cb[CQ_V2 * CBS + iR],
+                                    cb[CQ_V3 * CBS + iL], cb[CQ_V3 * CBS + iR], cb[CQ_B1 * CBS + iL], cb[CQ_B1 * CBS + iR],
+                                    cb[(CQ_Q0 + 4) * CBS + iL], cb[(CQ_Q0 + 4) * CBS + iR], cb[(CQ_Q0 + 5) * CBS + iL],
+                                    cb[(CQ_Q0 + 5) * CBS + iR], cb[CQ_P * CBS + iL], cb[CQ_P * CBS + iR], a.gam, fc);
             double amax[7];
             face_amax(cb[CQ_V1 * CBS + iL], cb[CQ_LF * CBS + iL], cb[CQ_LA * CBS + iL], cb[CQ_LS * CBS + iL],
                       cb[CQ_V1 * CBS + iR], cb[CQ_LF * CBS + iR], cb[CQ_LA * CBS + iR], cb[CQ_LS * CBS + iR], amax);
@@ -303,11 +321,18 @@ __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a, const 
                 }
             };
             double fh[7], Fs[7];
-            BackCoef bc;
-            split_back(fc, bc);
             RegStash st;
-            face_flux(fc, amax, a.eps, load, st, Fs);
-            back_project(bc, Fs, fh);
+            if constexpr (BR == 0) {
+                BackCoef bc;
+                split_back(fc, bc);
+                face_flux(fc, amax, a.eps, load, st, Fs);
+                back_project(bc, Fs, fh);
+            } else {
+                BackCoefS bc;
+                split_back_S(fc, bc);
+                face_flux_br<1>(fc, amax, a.eps, load, st, Fs);
+                back_project_S(bc, Fs, fh);
+            }
             const int io = T::fbi(s + 1, p);
 #pragma unroll
             for (int m = 0; m < 7; ++m) fb[m * FBS + io] = fh[m];
@@ -389,20 +414,20 @@ static int flux_variant()
     return v;
 }
 
-template <int DIR, int NT, int YW, int MINB, bool TMA>
+template <int DIR, int NT, int YW, int MINB, bool TMA, int BR = 0>
 static void launch_flux_t(const FluxArgs &a, cudaStream_t s)
 {
-    using T = Tile<DIR, NT, YW>;
+    using T = Tile<DIR, NT, YW, BR == 0 ? CQ_COUNT : CQ_COUNT_S>;
     static_assert(T::SMEM * MINB <= 227 * 1024, "shared memory budget");
     static bool once = false;
     if (!once) {
-        cudaFuncSetAttribute(flux_kernel<DIR, NT, YW, MINB, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM);
+        cudaFuncSetAttribute(flux_kernel<DIR, NT, YW, MINB, TMA, BR>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM);
         once = true;
     }
     dim3 grid((a.NP + T::NPB - 1) / T::NPB, a.nseg, 1);
     static const FluxMaps dummy = {};
     const FluxMaps *tm = reinterpret_cast<const FluxMaps *>(DIR == 0 ? a.tmap_x : a.tmap_y);
-    flux_kernel<DIR, NT, YW, MINB, TMA><<<grid, NT, T::SMEM, s>>>(a, TMA && tm ? *tm : dummy);
+    flux_kernel<DIR, NT, YW, MINB, TMA, BR><<<grid, NT, T::SMEM, s>>>(a, TMA && tm ? *tm : dummy);
 }
 
 template <int DIR>
@@ -410,7 +435,10 @@ static void launch_flux(const FluxArgs &a, cudaStream_t s)
 {
     const bool tma_ok = a.tmap_x != nullptr && a.tmap_y != nullptr && !a.is1d;
     const int v = flux_variant();
-    if (tma_ok && v == 4) launch_flux_t<DIR, 128, 16, 2, true>(a, s);
+    // entropy branch (dual-energy mode): its state planes are not consecutive in the pool, so it takes the
+    // cp.async staging, which addresses every plane through its own pointer
+    if (a.branch == 1) launch_flux_t<DIR, 128, 16, 2, false, 1>(a, s);
+    else if (tma_ok && v == 4) launch_flux_t<DIR, 128, 16, 2, true>(a, s);
     else launch_flux_t<DIR, 128, 16, 2, false>(a, s);
 }
 
@@ -517,8 +545,8 @@ __global__ void ct_faces_kernel(const CtArgs a)
         double b;
         if (a.stage <= 3) {
             b = a.bx0[g];
-            if (a.stage == 2) a.accbx[g] = cur - b;
-            if (a.stage == 3) a.accbx[g] = fma(2.0, cur, a.accbx[g]);
+            if (a.stage == 2 && !a.no_acc) a.accbx[g] = cur - b;
+            if (a.stage == 3 && !a.no_acc) a.accbx[g] = fma(2.0, cur, a.accbx[g]);
         } else {
             b = (a.accbx[g] + cur) * (1.0 / 3.0);
         }
@@ -530,8 +558,8 @@ __global__ void ct_faces_kernel(const CtArgs a)
         double b;
         if (a.stage <= 3) {
             b = a.by0[g];
-            if (a.stage == 2) a.accby[g] = cur - b;
-            if (a.stage == 3) a.accby[g] = fma(2.0, cur, a.accby[g]);
+            if (a.stage == 2 && !a.no_acc) a.accby[g] = cur - b;
+            if (a.stage == 3 && !a.no_acc) a.accby[g] = fma(2.0, cur, a.accby[g]);
         } else {
             b = (a.accby[g] + cur) * (1.0 / 3.0);
         }
@@ -764,6 +792,60 @@ void launch_entropy(double *const q9[9], const Geom &g, double gam, int roundtri
     a.all_cells = all_cells; a.dtp = dtp;
     dim3 block(64, 4), grid((g.NXI + 63) / 64, g.NYI > 1 ? (g.NYI + 3) / 4 : 1);
     entropy_kernel<<<grid, block, 0, s>>>(a);
+}
+
+// ------------------------------------------------------------------ dual-energy switch
+// ES_Switch, Weno5_2D.jl:1734-1768, with the reference's commented-out criterion (:1740) live:
+// dS = |E2S(q_E) - S(q_S)|; cells with dS >= threshold take the E state (with S = E2S(q_E)), all others the
+// S state; q[:,:,9] = S2E(q) of the selected state with the B of its own candidate (:1765).
+__global__ void es_switch_kernel(const SwitchArgs a)
+{
+    if (a.dtp && *a.dtp == 0.0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x + G;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y + G;
+    if (i >= a.NXI - G || j >= a.NYI - G) return;
+    const size_t g = (size_t)i + (size_t)a.pitch * j;
+    double e[8], s[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { e[k] = a.ce[k][g]; s[k] = a.cs[k][g]; }
+    const double SE = e2s(e[0], e[1], e[2], e[3], e[6], e[7], e[4], e[5], a.gam);
+    const bool bad = fabs(SE - s[5]) >= a.threshold;
+    const double rho = bad ? e[0] : s[0], mx = bad ? e[1] : s[1], my = bad ? e[2] : s[2], mz = bad ? e[3] : s[3];
+    const double bz = bad ? e[4] : s[4], S = bad ? SE : s[5], bx = bad ? e[6] : s[6], by = bad ? e[7] : s[7];
+    a.qn[0][g] = rho; a.qn[1][g] = mx; a.qn[2][g] = my; a.qn[3][g] = mz; a.qn[4][g] = bz;
+    a.qn[5][g] = S;
+    a.qn[6][g] = s2e(rho, mx, my, mz, bx, by, bz, S, a.gam);
+    a.flag[g] = bad ? 1.0 : 0.0;
+}
+
+void launch_es_switch(const SwitchArgs &a, cudaStream_t s)
+{
+    dim3 block(64, 4), grid((a.NXI - 2 * G + 63) / 64, (a.NYI - 2 * G + 3) / 4);
+    es_switch_kernel<<<grid, block, 0, s>>>(a);
+}
+
+// fsy[i,j], fsy[i-1,j], gsx[i,j], gsx[i,j-1] of a switched cell (i,j) come from the E sweep (:1754-1758); the
+// reference's loop starts at 2, so the outermost public row/column never switches.
+__global__ void flux_select_kernel(const double *__restrict__ flag, const double *__restrict__ fsyE,
+                                   const double *__restrict__ gsxE, double *__restrict__ fsyS, double *__restrict__ gsxS,
+                                   int NXI, int NYI, int pitch, const double *dtp)
+{
+    if (dtp && *dtp == 0.0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= NXI - 1 || j >= NYI - 1) return;
+    const size_t g = (size_t)i + (size_t)pitch * j;
+    auto bad = [&](int ii, int jj) { return ii >= 2 && jj >= 2 && flag[(size_t)ii + (size_t)pitch * jj] != 0.0; };
+    const bool here = bad(i, j);
+    if (here || bad(i + 1, j)) fsyS[g] = fsyE[g];
+    if (here || bad(i, j + 1)) gsxS[g] = gsxE[g];
+}
+
+void launch_flux_select(const double *flag, const double *fsyE, const double *gsxE, double *fsyS, double *gsxS,
+                        const Geom &g, const double *dtp, cudaStream_t s)
+{
+    dim3 block(64, 4), grid((g.NXI + 63) / 64, (g.NYI + 3) / 4);
+    flux_select_kernel<<<grid, block, 0, s>>>(flag, fsyE, gsxE, fsyS, gsxS, g.NXI, g.NYI, g.pitch, dtp);
 }
 
 // ------------------------------------------------------------------ CFL reduction

@@ -43,6 +43,7 @@ struct FluxArgs {
     double gam, eps;
     int is1d;
     int row_mode;            // x sweep: 0 all rows, 1 interior rows only, 2 ghost rows only (halo-exchange overlap)
+    int branch;              // 0: E branch (qc[7] = E), 1: S branch (qc[7] = S; weno5_flux_difference_S, Weno5_2D.jl:361)
     // TMA staging: plane indices into the pool (z coordinate of the 3-D tensor maps) and the maps
     // themselves (host pointers; copied into the kernel's parameter space at launch)
     int qc_plane[8], rhs_plane[7], base_plane[6], acc_plane[6];
@@ -62,6 +63,18 @@ struct CtArgs {
     int oxlo, oxhi, oylo, oyhi;  // 1 where the side is a physical outflow boundary
     int bx_i0, bx_i1, bx_j0, bx_j1;   // write ranges (inclusive) of bxn
     int by_i0, by_i1, by_j0, by_j1;   // and of byn
+    int no_acc;                  // 1: do not touch accbx/accby (candidate CT passes of the dual-energy stage)
+};
+
+// dual-energy stage (Weno5_2D.jl:134-180 with a live ES_Switch, :1734-1768)
+struct SwitchArgs {
+    const double *ce[8];         // E candidate: rho,Mx,My,Mz,Bz,E,Bx,By
+    const double *cs[8];         // S candidate: rho,Mx,My,Mz,Bz,S,Bx,By
+    double *qn[7];               // selected state: rho,Mx,My,Mz,Bz,S,E
+    double *flag;                // 1.0 where the E state was taken
+    int NXI, NYI, pitch;
+    double gam, threshold;
+    const double *dtp;
 };
 
 void launch_flux_x(const FluxArgs &a, cudaStream_t s);
@@ -76,6 +89,10 @@ void launch_bc_fill(double *const planes[], int nplanes, const Geom &g, const in
                     const double *dtp, cudaStream_t s);
 void launch_halo_pack(double *const planes[], int n, const Geom &g, double *up, double *down, int has_up, int has_down,
                       int unpack, cudaStream_t s);
+void launch_es_switch(const SwitchArgs &a, cudaStream_t s);
+// fsy/gsx of the S sweep <- E sweep on the faces of switched cells and of their low-side neighbours (:1754-1758)
+void launch_flux_select(const double *flag, const double *fsyE, const double *gsxE, double *fsyS, double *gsxS,
+                        const Geom &g, const double *dtp, cudaStream_t s);
 void launch_ct_centers_entropy(const double *bxn, const double *byn, double *const q9[9], const Geom &g, double gam,
                                int roundtrip, const double *dtp, cudaStream_t s);
 void launch_entropy(double *const q9[9], const Geom &g, double gam, int roundtrip, int all_cells,

@@ -125,6 +125,40 @@ W5_HD void cell_quantities(const double q[8], double gam, CellOut &o)
     o.F[6] = (E + pt) * v1 - B1 * vB;
 }
 
+// Entropy-variable twin (Weno5_2D.jl:953-969 primitives, :927-950 fluxes): q = [rho,M1,M2,M3,B1,B2,B3,S].
+// P = S rho^(gam-1); the face needs P and rho^(1-gam) of both cells (:657-667), so both are returned.
+struct CellOutS { double P, rg0; };
+
+W5_HD void cell_quantities_S(const double q[8], double gam, CellOut &o, CellOutS &os)
+{
+    const double rho = q[0];
+    const double ri = fast_rcp(rho);
+    const double v1 = q[1] * ri, v2 = q[2] * ri, v3 = q[3] * ri;
+    const double B1 = q[4], B2 = q[5], B3 = q[6], S = q[7];
+    const double BB = B1 * B1 + B2 * B2 + B3 * B3;
+    const double rg1 = pow(rho, gam - 1.0);
+    const double P = S * rg1;
+    os.P = P;
+    os.rg0 = fast_rcp(rg1);                                        // rho^(1-gam)
+    const double cs2 = fmax(0.0, gam * fabs(P * ri));
+    const double bnx2 = fmax(0.0, B1 * B1 * ri);
+    const double bbn2 = BB * ri;
+    const double s = bbn2 + cs2;
+    const double root = fast_sqrt(fmax(0.0, s * s - 4.0 * bnx2 * cs2));
+    o.lf = fast_sqrt(fmax(0.0, 0.5 * (s + root)));
+    o.ls = fast_sqrt(fmax(0.0, 0.5 * (s - root)));
+    o.la = fast_sqrt(bnx2);
+    o.v1 = v1; o.v2 = v2; o.v3 = v3;
+    const double pt = P + 0.5 * BB;
+    o.F[0] = rho * v1;
+    o.F[1] = q[1] * v1 + pt - B1 * B1;
+    o.F[2] = q[2] * v1 - B1 * B2;
+    o.F[3] = q[3] * v1 - B1 * B3;
+    o.F[4] = B2 * v1 - B1 * v2;
+    o.F[5] = B3 * v1 - B1 * v3;
+    o.F[6] = S * v1;
+}
+
 // Face-averaged state and everything the structured projection needs.
 // Field order m: fast-, Alfven-, slow-, entropy, slow+, Alfven+, fast+.
 struct FaceCoef {
@@ -139,6 +173,8 @@ struct FaceCoef {
     double ke_n;                          // entropy row: w = ke_n n + x1
     // back-projection
     double af, as_, afcf, ascs, a_r, s_r, sgn, sig, hf, hs, axy;
+    // S branch only: n = gS x1 + kap x7, entropy row w = x1/gam - kap x7, 7th back-projected component
+    double gS, kap, ig, Sr, g0;
 };
 
 // Weno5_2D.jl:1273-1359 (face averages, wave speeds, degeneracy handling) and the
@@ -263,6 +299,131 @@ W5_HD void back_project(const BackCoef &c, const double Fs[7], double fh[7])
     fh[6] = fma(c.hf, Sf, fma(c.hs, Ss, fma(c.vx, Y, fma(c.sig, sX, fma(c.hv2, Fs[3], c.axy * Sa)))));
 }
 
+// ------------------------------------------------------------------ S branch (entropy variable)
+// compute_eigenvectors_S_vec, Weno5_2D.jl:640-924.  The rows of L have the same structure as in the E
+// branch with the inner product n replaced by n_S = gamS x1 + kappa x7, kappa = rho/(gam S) (after the
+// 0.5/cs2 scaling the factor cs2 of columns 1 and 7 cancels), identical antisymmetric parts and
+// Alfven rows, and the unscaled entropy row x1/gam - kappa x7 (:872).  R differs in its 7th row only.
+W5_HD void face_coefficients_S(double rhoL, double rhoR, double rg0L, double rg0R, double v1L, double v1R,
+                               double v2L, double v2R, double v3L, double v3R, double B1L, double B1R, double B2L,
+                               double B2R, double B3L, double B3R, double PL, double PR, double gam, FaceCoef &c)
+{
+    const double g0 = 1.0 - gam;
+    const double drho = fabs(rhoL - rhoR);
+    // :657-667: arithmetic mean for (nearly) equal densities, else the mean of rho^(1-gam)
+    double rho = 0.5 * (rhoL + rhoR);
+    if (drho > 1e-12) rho = pow(fabs(g0 * drho / (rg0R - rg0L)), 1.0 / gam);
+    const double vx = 0.5 * (v1L + v1R), vy = 0.5 * (v2L + v2R), vz = 0.5 * (v3L + v3R);
+    const double Bx = 0.5 * (B1L + B1R), By = 0.5 * (B2L + B2R), Bz = 0.5 * (B3L + B3R);
+    const double pg = 0.5 * (PL + PR);
+    const double rinv = fast_rsqrt(rho);
+    const double r = rho * rinv;
+    const double ri = rinv * rinv;
+    const double S = pg / pow(rho, gam - 1.0);
+    const double Bt2 = By * By + Bz * Bz;
+    const double B2 = Bx * Bx + Bt2;
+    const double bbn2 = B2 * ri;
+    const double cs2 = fmax(0.0, gam * fabs(pg * ri));
+    const double bnx2 = Bx * Bx * ri;
+    const double a = fast_sqrt(cs2);
+    const double s_ = bbn2 + cs2;
+    const double root = fast_sqrt(fmax(0.0, s_ * s_ - 4.0 * bnx2 * cs2));
+    const double cf = fast_sqrt(fmax(0.0, 0.5 * (s_ + root)));
+    const double cs = fast_sqrt(fmax(0.0, 0.5 * (s_ - root)));
+    const double sg = (Bx < 0.0) ? -1.0 : 1.0;
+    const bool tang = Bt2 > 1e-30;
+    const double ib = fast_rsqrt(tang ? Bt2 : 1.0);
+    const double bty = tang ? By * ib : 0.70710678118654752440;
+    const double btz = tang ? Bz * ib : 0.70710678118654752440;
+    const double dl2 = cf * cf - cs * cs;
+    const bool split = dl2 >= 1e-30;
+    const double id = fast_rcp(split ? dl2 : 1.0);
+    const double af = split ? fast_sqrt(fmax(0.0, cs2 - cs * cs) * id) : 1.0;
+    const double as_ = split ? fast_sqrt(fmax(0.0, cf * cf - cs2) * id) : 1.0;
+    const double sig = bty * vy + btz * vz;
+    const double ih = 0.5 * fast_rcp(cs2);
+    const double afcf = af * cf, ascs = as_ * cs;
+
+    c.hv2 = 0.0; c.vx = vx; c.vy = vy; c.vz = vz; c.By = By; c.Bz = Bz;
+    c.bty = bty; c.btz = btz;
+    c.kf_n = 0.5 * af;
+    c.kf_t = a * as_ * r * ih;
+    c.kf_1 = (afcf * vx - ascs * sig * sg) * ih;
+    c.kf_2 = -afcf * ih;
+    c.kf_u = ascs * sg * ih;
+    c.ks_n = 0.5 * as_;
+    c.ks_t = -a * af * r * ih;
+    c.ks_1 = (ascs * vx + afcf * sig * sg) * ih;
+    c.ks_2 = -ascs * ih;
+    c.ks_u = -afcf * sg * ih;
+    c.ka_1 = 0.5 * (btz * vy - bty * vz);
+    c.ka_3 = -0.5 * btz;
+    c.ka_4 = 0.5 * bty;
+    c.kb_5 = -0.5 * sg * r * btz;
+    c.kb_6 = 0.5 * sg * r * bty;
+    c.ke_n = 0.0;
+    c.af = af; c.as_ = as_; c.afcf = afcf; c.ascs = ascs;
+    c.a_r = a * rinv; c.s_r = sg * rinv; c.sgn = sg; c.sig = sig;
+    c.hf = 0.0; c.hs = 0.0; c.axy = 0.0;
+    c.gS = (gam - 1.0) / gam;
+    c.kap = rho / (gam * S);
+    c.ig = 1.0 / gam;
+    c.Sr = S * ri;
+    c.g0 = g0;
+}
+
+// characteristic projection, S branch: x = [rho,M1,M2,M3,B2,B3,S]-shaped quantity
+W5_HD void project_S(const FaceCoef &c, const double x[7], double w[7])
+{
+    const double n = fma(c.gS, x[0], c.kap * x[6]);
+    const double t = fma(c.bty, x[4], c.btz * x[5]);
+    const double u = fma(c.bty, x[2], c.btz * x[3]);
+    const double pf = fma(c.kf_n, n, c.kf_t * t);
+    const double mf = fma(c.kf_1, x[0], fma(c.kf_2, x[1], c.kf_u * u));
+    const double ps = fma(c.ks_n, n, c.ks_t * t);
+    const double ms = fma(c.ks_1, x[0], fma(c.ks_2, x[1], c.ks_u * u));
+    const double A = fma(c.ka_1, x[0], fma(c.ka_3, x[2], c.ka_4 * x[3]));
+    const double B = fma(c.kb_5, x[4], c.kb_6 * x[5]);
+    w[0] = pf + mf; w[6] = pf - mf;
+    w[2] = ps + ms; w[4] = ps - ms;
+    w[1] = A + B;   w[5] = A - B;
+    w[3] = fma(c.ig, x[0], -c.kap * x[6]);
+}
+
+// fhat = R_S . Fs (Weno5_2D.jl:1879-1888 with :812-866): rows 1-6 as in the E branch, row 7 = S/rho (...)
+struct BackCoefS {
+    double vx, vy, vz, bty, btz;
+    double af, as_, afcf, ascs, a_r, s_r, sgn, Sr, g0;
+};
+
+W5_HD void split_back_S(const FaceCoef &c, BackCoefS &b)
+{
+    b.vx = c.vx; b.vy = c.vy; b.vz = c.vz; b.bty = c.bty; b.btz = c.btz;
+    b.af = c.af; b.as_ = c.as_; b.afcf = c.afcf; b.ascs = c.ascs; b.a_r = c.a_r; b.s_r = c.s_r;
+    b.sgn = c.sgn; b.Sr = c.Sr; b.g0 = c.g0;
+}
+
+W5_HD void back_project_S(const BackCoefS &c, const double Fs[7], double fh[7])
+{
+    const double Sf = Fs[0] + Fs[6], Df = Fs[6] - Fs[0];
+    const double Ss = Fs[2] + Fs[4], Ds = Fs[4] - Fs[2];
+    const double Sa = Fs[1] + Fs[5], Da = Fs[5] - Fs[1];
+    const double X = fma(c.afcf, Ds, -c.ascs * Df);
+    const double Y = fma(c.afcf, Df, c.ascs * Ds);
+    const double fs = fma(c.af, Sf, c.as_ * Ss);
+    const double f1 = fs + Fs[3];
+    const double sX = c.sgn * X;
+    const double Z = c.a_r * fma(c.as_, Sf, -c.af * Ss);
+    const double sDa = c.s_r * Da;
+    fh[0] = f1;
+    fh[1] = fma(c.vx, f1, Y);
+    fh[2] = fma(c.vy, f1, fma(c.bty, sX, -c.btz * Sa));
+    fh[3] = fma(c.vz, f1, fma(c.btz, sX, c.bty * Sa));
+    fh[4] = fma(c.bty, Z, c.btz * sDa);
+    fh[5] = fma(c.btz, Z, -c.bty * sDa);
+    fh[6] = c.Sr * fma(c.g0, Fs[3], fs);
+}
+
 // One side of the Jiang & Wu correction (Weno5_2D.jl:1836-1853) for UNHALVED inputs
 // A = 2a, B = 2b, ...; returns 2 phi.
 //  * smoothness indicators as quadratic forms, scaled by 1/16:
@@ -307,23 +468,37 @@ struct RegStash {
 // differences are live, not the 84 stencil operands.  The minus-side differences Q and the
 // central term `first` are only needed after the streaming loop; they go through `stash`
 // (registers, or thread-private shared memory in the kernel) to keep register pressure down.
+template <int BR> W5_HD void project_br(const FaceCoef &c, const double x[7], double w[7])
+{
+    if (BR == 0) project(c, x, w); else project_S(c, x, w);
+}
+
+template <int BR, class Loader, class Stash>
+W5_HD void face_flux_br(const FaceCoef &c, const double amax[7], double eps, Loader load, Stash &stash, double Fs[7]);
+
 template <class Loader, class Stash>
 W5_HD void face_flux(const FaceCoef &c, const double amax[7], double eps, Loader load, Stash &stash, double Fs[7])
+{
+    face_flux_br<0>(c, amax, eps, load, stash, Fs);
+}
+
+template <int BR, class Loader, class Stash>
+W5_HD void face_flux_br(const FaceCoef &c, const double amax[7], double eps, Loader load, Stash &stash, double Fs[7])
 {
     double P[4][7];                // P[k-1] = dw_k + amax dv_k (k=1..4); stash.q[k-2] = dw_k - amax dv_k (k=2..5)
     double wp[7], vp[7];
     {
         double F[7], q[7];
         load(0, F, q);
-        project(c, F, wp);
-        project(c, q, vp);
+        project_br<BR>(c, F, wp);
+        project_br<BR>(c, q, vp);
     }
 #pragma unroll
     for (int k = 1; k < 6; ++k) {
         double F[7], q[7], w[7], v[7];
         load(k, F, q);
-        project(c, F, w);
-        project(c, q, v);
+        project_br<BR>(c, F, w);
+        project_br<BR>(c, q, v);
 #pragma unroll
         for (int m = 0; m < 7; ++m) {
             const double dw = w[m] - wp[m], dv = v[m] - vp[m];

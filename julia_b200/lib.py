@@ -51,6 +51,8 @@ SIGNATURES = {
     "weno5_advance": (C.c_int, [_vp, C.c_int, C.c_double, _dp, C.POINTER(C.c_int)]),
     "weno5_divb": (C.c_int, [_vp, _dp]),
     "weno5_totals": (C.c_int, [_vp, _dp]),
+    "weno5_set_es_switch": (C.c_int, [_vp, C.c_int, C.c_double]),
+    "weno5_es_switch_count": (C.c_int, [_vp, C.POINTER(C.c_ulonglong)]),
     "weno5_classical_rk4_step_2d": (C.c_int, [C.POINTER(Params), _dp, _dp, _dp, C.c_double, _dp, _dp, _dp]),
     "weno5_classical_rk4_step_1d": (C.c_int, [C.POINTER(Params), _dp, C.c_double, _dp]),
     "weno5_step_host": (C.c_int, [_vp, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp]),

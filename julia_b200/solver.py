@@ -129,6 +129,17 @@ class Solver:
                                          L.dptr(out[0]), L.dptr(out[1]), L.dptr(out[2])))
         return out
 
+    # -- dual-energy mode
+    def set_es_switch(self, enable=True, threshold=1e-5):
+        """Run both the E and the S sweeps every stage and let ES_Switch (Weno5_2D.jl:1734) choose per cell
+        with the criterion the reference wrote and disabled (:1740): |S(E) - S| >= threshold -> E state."""
+        L.check(self.lib.weno5_set_es_switch(self.h, 1 if enable else 0, float(threshold)))
+
+    def es_switch_count(self):
+        n = C.c_ulonglong()
+        L.check(self.lib.weno5_es_switch_count(self.h, C.byref(n)))
+        return int(n.value)
+
     # -- diagnostics
     def divb(self):
         d = np.zeros((self.Nx, self.Ny), order="F")

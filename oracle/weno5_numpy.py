@@ -214,6 +214,123 @@ def eigenvectors_E(uL, uR, EL, ER, gam, variant="2d"):
     return L, R
 
 
+# ----------------------------------------------------------------------------- S branch
+def primitives_S(q, gam):
+    """Weno5_2D.jl:953-969: q = [rho,Mx,My,Mz,Bx,By,Bz,S] -> u = [rho,vx,vy,vz,Bx,By,Bz,P(S)]."""
+    u = q.copy()
+    u[..., 1] = u[..., 1] / u[..., 0]
+    u[..., 2] = u[..., 2] / u[..., 0]
+    u[..., 3] = u[..., 3] / u[..., 0]
+    u[..., 7] = u[..., 7] * u[..., 0] ** (gam - 1.0)
+    return u
+
+
+def fluxes_S(q, u):
+    """Weno5_2D.jl:927-950: like compute_fluxes_E, the 7th flux is S*vx."""
+    F = np.zeros(u.shape[:-1] + (7,))
+    pt = u[..., 7] + 0.5 * (u[..., 4] * u[..., 4] + u[..., 5] * u[..., 5] + u[..., 6] * u[..., 6])
+    F[..., 0] = u[..., 0] * u[..., 1]
+    F[..., 1] = q[..., 1] * u[..., 1] + pt - u[..., 4] * u[..., 4]
+    F[..., 2] = q[..., 2] * u[..., 1] - u[..., 4] * u[..., 5]
+    F[..., 3] = q[..., 3] * u[..., 1] - u[..., 4] * u[..., 6]
+    F[..., 4] = u[..., 5] * u[..., 1] - u[..., 4] * u[..., 2]
+    F[..., 5] = u[..., 6] * u[..., 1] - u[..., 4] * u[..., 3]
+    F[..., 6] = q[..., 7] * u[..., 1]
+    return F
+
+
+def eigenvectors_S(uL, uR, gam):
+    """Weno5_2D.jl:640-924 (the ``_vec`` variant, the one called at :373): entropy-variable eigenvectors at
+    the face between two cells.  The face density is the mean of rho^(1-gam) (":657-667"), the pressure the
+    arithmetic mean of P(S).  Component order [rho,Mx,My,Mz,By,Bz,S]."""
+    g0, gS = 1.0 - gam, (gam - 1.0) / gam
+    drho = np.abs(uL[..., 0] - uR[..., 0])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rho_log = np.abs(g0 * drho / (uR[..., 0] ** g0 - uL[..., 0] ** g0)) ** (1.0 / gam)
+    rho = np.where(drho <= 1e-12, 0.5 * (uL[..., 0] + uR[..., 0]), rho_log)
+    vx = 0.5 * (uL[..., 1] + uR[..., 1])
+    vy = 0.5 * (uL[..., 2] + uR[..., 2])
+    vz = 0.5 * (uL[..., 3] + uR[..., 3])
+    Bx = 0.5 * (uL[..., 4] + uR[..., 4])
+    By = 0.5 * (uL[..., 5] + uR[..., 5])
+    Bz = 0.5 * (uL[..., 6] + uR[..., 6])
+    pg = 0.5 * (uL[..., 7] + uR[..., 7])
+    r = np.sqrt(rho)
+    S = pg / rho ** (gam - 1.0)
+    B2 = Bx * Bx + By * By + Bz * Bz
+    bbn2 = B2 / rho
+    cs2 = np.maximum(0.0, gam * np.abs(pg / rho))
+    bnx2 = Bx * Bx / rho
+    a = np.sqrt(cs2)
+    s_ = bbn2 + cs2
+    root = np.sqrt(np.maximum(0.0, s_ * s_ - 4.0 * bnx2 * cs2))
+    cf = np.sqrt(np.maximum(0.0, (bbn2 + cs2 + root) / 2.0))
+    ca = np.sqrt(np.maximum(0.0, bnx2))
+    cs = np.sqrt(np.maximum(0.0, (bbn2 + cs2 - root) / 2.0))
+    Bt2 = By * By + Bz * Bz
+    s = np.sign(Bx)
+    s = np.where(s == 0.0, 1.0, s)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        degenerate = Bt2 <= 1e-30
+        bty = np.where(degenerate, 1.0 / np.sqrt(2.0), By / np.sqrt(Bt2))
+        btz = np.where(degenerate, 1.0 / np.sqrt(2.0), Bz / np.sqrt(Bt2))
+        dl2 = cf * cf - cs * cs
+        ok = dl2 >= 1e-30
+        af = np.where(ok, np.sqrt(np.maximum(0.0, cs2 - cs * cs) / dl2), 1.0)
+        as_ = np.where(ok, np.sqrt(np.maximum(0.0, cf * cf - cs2) / dl2), 1.0)
+    sig = bty * vy + btz * vz
+    shp = rho.shape
+    L = np.zeros(shp + (7, 7))
+    R = np.zeros(shp + (7, 7))
+    zero, one = np.zeros(shp), np.ones(shp)
+    kap = rho / (gam * S)
+
+    def rowL(m, vals):
+        for c, v in enumerate(vals):
+            L[..., m, c] = v
+
+    def colR(m, vals):
+        for c, v in enumerate(vals):
+            R[..., c, m] = v
+
+    rowL(0, [af * (gS * cs2 + cf * vx) - as_ * cs * sig * s, -af * cf, as_ * cs * bty * s, as_ * cs * btz * s,
+             a * as_ * bty * r, a * as_ * btz * r, af * cs2 * kap])
+    rowL(1, [btz * vy - bty * vz, zero, -btz, bty, -btz * s * r, bty * s * r, zero])
+    rowL(2, [as_ * (gS * cs2 + cs * vx) + af * cf * sig * s, -as_ * cs, -af * cf * bty * s, -af * cf * btz * s,
+             -a * af * bty * r, -a * af * btz * r, as_ * cs2 * kap])
+    rowL(3, [one / gam, zero, zero, zero, zero, zero, -kap])
+    rowL(4, [as_ * (gS * cs2 - cs * vx) - af * cf * sig * s, as_ * cs, af * cf * bty * s, af * cf * btz * s,
+             -a * af * bty * r, -a * af * btz * r, as_ * cs2 * kap])
+    rowL(5, [btz * vy - bty * vz, zero, -btz, bty, btz * s * r, -bty * s * r, zero])
+    rowL(6, [af * (gS * cs2 - cf * vx) + as_ * cs * sig * s, af * cf, -as_ * cs * bty * s, -as_ * cs * btz * s,
+             a * as_ * bty * r, a * as_ * btz * r, af * cs2 * kap])
+    Sr = S / rho
+    colR(0, [af, af * (vx - cf), af * vy + as_ * cs * bty * s, af * vz + as_ * cs * btz * s,
+             a * as_ * bty / r, a * as_ * btz / r, af * Sr])
+    colR(1, [zero, zero, -btz, bty, -btz * s / r, bty * s / r, zero])
+    colR(2, [as_, as_ * (vx - cs), as_ * vy - af * cf * bty * s, as_ * vz - af * cf * btz * s,
+             -a * af * bty / r, -a * af * btz / r, as_ * Sr])
+    colR(3, [one, vx, vy, vz, zero, zero, g0 * Sr])
+    colR(4, [as_, as_ * (vx + cs), as_ * vy + af * cf * bty * s, as_ * vz + af * cf * btz * s,
+             -a * af * bty / r, -a * af * btz / r, as_ * Sr])
+    colR(5, [zero, zero, -btz, bty, btz * s / r, -bty * s / r, zero])
+    colR(6, [af, af * (vx + cf), af * vy - as_ * cs * bty * s, af * vz - as_ * cs * btz * s,
+             a * as_ * bty / r, a * as_ * btz / r, af * Sr])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        scale = [0.5 / cs2, 0.5 * one, 0.5 / cs2, one, 0.5 / cs2, 0.5 * one, 0.5 / cs2]    # row 4 unscaled, :872
+    for m in range(7):
+        L[..., m, :] *= scale[m][..., None]
+    sgnBt = np.sign(By)
+    sgnBt = np.where(By == 0.0, np.sign(Bz), sgnBt)
+    sgnBt = np.where(sgnBt == 0.0, 1.0, sgnBt)
+    slowflip = np.where(a >= ca, sgnBt, 1.0)
+    fastflip = np.where(a >= ca, 1.0, sgnBt)
+    for m, flip in ((2, slowflip), (4, slowflip), (0, fastflip), (6, fastflip)):
+        L[..., m, :] *= flip[..., None]
+        R[..., :, m] *= flip[..., None]
+    return L, R
+
+
 def _ext_index(idx, Nq, bc):
     """Continuation of a stencil index past the high end of the array (quirk Q3)."""
     n = Nq - 2 * NB
@@ -222,16 +339,20 @@ def _ext_index(idx, Nq, bc):
     return np.minimum(idx, Nq - 1)
 
 
-def weno5_face_flux(q, a, F, gam, eps, bc, variant="2d"):
+def weno5_face_flux(q, a, F, gam, eps, bc, variant="2d", branch="E"):
     """Numerical flux at faces fi = NB-1 .. Nq-NB (0-based; reference 1-based 3..Nq-2).
 
     Weno5_2D.jl:1795-1895 (1D twin Weno5_1D.jl:287-405).  q is (Nq, Nr, 8) and the sweep
     runs along axis 0.  Returns dF (Nq, Nr, 7), zero at faces that are not computed.
     """
     Nq = q.shape[0]
-    u = primitives_E(q, gam)
     faces = np.arange(NB - 1, Nq - NB + 1)
-    L, R = eigenvectors_E(u[faces], u[faces + 1], q[faces, ..., 7], q[faces + 1, ..., 7], gam, variant)
+    if branch == "E":
+        u = primitives_E(q, gam)
+        L, R = eigenvectors_E(u[faces], u[faces + 1], q[faces, ..., 7], q[faces + 1, ..., 7], gam, variant)
+    else:
+        u = primitives_S(q, gam)
+        L, R = eigenvectors_S(u[faces], u[faces + 1], gam)
     q7 = q[..., [0, 1, 2, 3, 5, 6, 7]]
     Fs = np.zeros(L.shape[:-2] + (7,))
     for m in range(7):
@@ -274,13 +395,22 @@ def weno5_face_flux(q, a, F, gam, eps, bc, variant="2d"):
     return dF, u
 
 
-def flux_difference_E(q, gam, eps, bc, variant="2d"):
+def flux_difference_S(q, gam, eps, bc):
+    """Weno5_2D.jl:361-401: the entropy-variable twin of flux_difference_E (q[...,7] = S)."""
+    return flux_difference_E(q, gam, eps, bc, branch="S")
+
+
+def flux_difference_E(q, gam, eps, bc, variant="2d", branch="E"):
     """Weno5_2D.jl:973-1018: one directional sweep along axis 0 of q (Nq, Nr, 8)."""
     Nq, Nr = q.shape[0], q.shape[1]
-    u = primitives_E(q, gam)
+    if branch == "E":
+        u = primitives_E(q, gam)
+        F = fluxes_E(q, u)
+    else:
+        u = primitives_S(q, gam)
+        F = fluxes_S(q, u)
     a = eigenvalues(u, gam)
-    F = fluxes_E(q, u)
-    dF, _ = weno5_face_flux(q, a, F, gam, eps, bc, variant)
+    dF, _ = weno5_face_flux(q, a, F, gam, eps, bc, variant, branch)
     dq = np.zeros((Nq, Nr, 8))
     bsy = np.zeros((Nq, Nr))
     bsz = np.zeros((Nq, Nr))
@@ -501,6 +631,87 @@ def classical_RK4_step_2d(q0, bxb0, byb0, dt, P):
     boundaries_flux(bx4, P)          # Weno5_2D.jl:313 boundaries!(q4, bxb4, byb4)
     boundaries_flux(by4, P)
     return q4, bx4, by4
+
+
+# ----------------------------------------------------------------------------- dual-energy step
+def ES_Switch(q_E, q_S, fsy_S, gsx_S, fsy_E, gsx_E, gam, threshold=1e-5):
+    """Weno5_2D.jl:1734-1768 with the reference's own (commented-out) criterion restored:
+    ``dS = abs.(q_SE[:,:,8] - q_S[:,:,8])`` instead of ``dS = 1``.  Cells (1-based i,j >= 2) whose entropy
+    derived from the E state differs from the advected entropy by >= threshold take the E state and pull the
+    E fluxes of their own and their low-side neighbour faces; all others keep the S state."""
+    Nx, Ny = q_E.shape[:2]
+    q_SE = q_E.copy()
+    q_SE[..., 7] = E2S(q_E, gam)
+    dS = np.abs(q_SE[..., 7] - q_S[..., 7])
+    bad = dS >= threshold
+    bad[0, :] = False
+    bad[:, 0] = False
+    q = np.zeros((Nx, Ny, 9))
+    q[..., 0:8] = np.where(bad[..., None], q_SE, q_S)
+    fE = bad.copy()
+    fE[:-1, :] |= bad[1:, :]                     # fsy[i-1,j] of a bad cell
+    gE = bad.copy()
+    gE[:, :-1] |= bad[:, 1:]                     # gsx[i,j-1] of a bad cell
+    fsy = np.where(fE, fsy_E, fsy_S)
+    gsx = np.where(gE, gsx_E, gsx_S)
+    q[..., 8] = S2E(q[..., 0:8], gam)
+    return q, fsy, gsx, bad
+
+
+def _stage_2d_dual(qk9, baseE, baseS, bbx, bby, c, dt, P, stage, threshold):
+    """One stage of Weno5_2D.jl:134-180 with both branches live."""
+    def ct(qn, fsy, gsx):
+        boundaries(qn, fsy, gsx, P)
+        Ox, Oxi, Oxj = corner_fluxes(fsy, gsx)
+        bxn = bbx - c * dt / P.dy * (Ox - Oxj)
+        byn = bby - c * dt / P.dx * (Oxi - Ox)
+        qn[..., 4:6] = face2center(bxn, byn)
+        boundaries(qn, fsy, gsx, P)
+        return bxn, byn
+
+    qE = np.ascontiguousarray(qk9[..., [0, 1, 2, 3, 4, 5, 6, 8]])
+    qS = np.ascontiguousarray(qk9[..., 0:8])
+    out = []
+    for branch, qb, base in (("E", qE, baseE), ("S", qS, baseS)):
+        dFx, fsy, _ = flux_difference_E(qb, P.gam, P.eps, P.bc_x, branch=branch)
+        dFy_rot, _, gsx_rot = flux_difference_E(rotate_fwd(qb), P.gam, P.eps, P.bc_y, branch=branch)
+        dFy = rotate_bwd(dFy_rot)
+        gsx = np.ascontiguousarray(gsx_rot.T)
+        y_first = branch == "E" and stage <= 2                         # :145,:190 vs :164,:210
+        if stage <= 3:
+            cc = c if stage <= 2 else 1.0
+            qn = (base - cc * dt / P.dy * dFy - cc * dt / P.dx * dFx) if y_first else \
+                 (base - cc * dt / P.dx * dFx - cc * dt / P.dy * dFy)
+        else:
+            qn = base + (-1 / 6 * dt / P.dx * dFx - 1 / 6 * dt / P.dy * dFy)
+        ct(qn, fsy, gsx)
+        out.append((qn, fsy, gsx))
+    (qnE, fsyE, gsxE), (qnS, fsyS, gsxS) = out
+    q9, fsy, gsx, bad = ES_Switch(qnE, qnS, fsyS, gsxS, fsyE, gsxE, P.gam, threshold)
+    q8 = np.ascontiguousarray(q9[..., 0:8])
+    bxn, byn = ct(q8, fsy, gsx)
+    q9[..., 0:8] = q8
+    # the reference leaves q[:,:,9] = S2E(q) from before the final face->centre update (:1765, :176-180)
+    boundaries_q(q9, P)
+    return q9, bxn, byn, bad
+
+
+def classical_RK4_step_2d_dual(q0, bxb0, byb0, dt, P, threshold=1e-5):
+    """Weno5_2D.jl:125-317 with a working ES_Switch (see ES_Switch above).  Returns (q4, bxb4, byb4, nbad) with nbad = interior cells that took the E state, per stage."""
+    idxE = [0, 1, 2, 3, 4, 5, 6, 8]
+    q0E = np.ascontiguousarray(q0[..., idxE])
+    q0S = np.ascontiguousarray(q0[..., 0:8])
+    q1, bx1, by1, b1 = _stage_2d_dual(q0, q0E, q0S, bxb0, byb0, 0.5, dt, P, 1, threshold)
+    q2, bx2, by2, b2 = _stage_2d_dual(q1, q0E, q0S, bxb0, byb0, 0.5, dt, P, 2, threshold)
+    q3, bx3, by3, b3 = _stage_2d_dual(q2, q0E, q0S, bxb0, byb0, 1.0, dt, P, 3, threshold)
+    baseE = 1 / 3 * (-q0E + q1[..., idxE] + 2 * q2[..., idxE] + q3[..., idxE])
+    baseS = 1 / 3 * (-q0S + q1[..., 0:8] + 2 * q2[..., 0:8] + q3[..., 0:8])
+    bbx = 1 / 3 * (-bxb0 + bx1 + 2 * bx2 + bx3)
+    bby = 1 / 3 * (-byb0 + by1 + 2 * by2 + by3)
+    q4, bx4, by4, b4 = _stage_2d_dual(q3, baseE, baseS, bbx, bby, 1.0 / 6.0, dt, P, 4, threshold)
+    boundaries_flux(bx4, P)
+    boundaries_flux(by4, P)
+    return q4, bx4, by4, [int(b[NB:-NB, NB:-NB].sum()) for b in (b1, b2, b3, b4)]     # interior cells switched to E
 
 
 def boundaries_1d(q, P):

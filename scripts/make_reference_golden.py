@@ -19,6 +19,10 @@ are called unmodified; what the harness does around them is stated per case:
   ref2d_periodic_ot  the RK4 step on a 16x16 Orszag-Tang state with `boundaries!` REPLACED by a periodic wrap
                      (the reference has outflow only; this pins the interior numerics the bench workload uses).
 
+  ref2d_dual_*       "next" row f3: the same RK4 step with the reference's own commented-out switching criterion
+                     restored (the only source edit, see DUAL_PATCH), so that the S branch is live: periodic blast
+                     wave 16x16 (2 steps) and the shock-cloud problem (1 step); `nbad` = cells switched to E per stage.
+
 `oob` in each file counts the @inbounds reads that left their column: "wrapped" ones read
 the neighbouring column like the Julia binary would, "outside" ones (past the allocation) read NaN here.
 """
@@ -39,15 +43,24 @@ OUT = os.path.join(ROOT, "tests", "golden")
 GEN = os.path.join(ROOT, "oracle", "_ref")
 
 
-def load(name):
+# The one source edit any case makes (case_dual only): the reference's own commented-out switching criterion
+# (Weno5_2D.jl:1740-1741) is restored, i.e. `#dS = abs.(...)` is uncommented and the override `dS = 1` dropped.
+DUAL_PATCH = (("#dS = abs.(q_SE[:,:,8] - q_S[:,:,8])", "dS = abs.(q_SE[:,:,8] - q_S[:,:,8])"), ("\ndS = 1\n", "\n"))
+
+
+def load(name, patch=(), tag=""):
     os.makedirs(GEN, exist_ok=True)
     with open(os.path.join(REF, name + ".jl")) as f:
-        py, failed = jl2py.translate(f.read())
+        src = f.read()
+    for old, new in patch:
+        assert src.count(old) == 1, old
+        src = src.replace(old, new)
+    py, failed = jl2py.translate(src)
     assert not failed, failed
-    path = os.path.join(GEN, name.lower() + "_ref.py")
+    path = os.path.join(GEN, name.lower() + tag + "_ref.py")
     with open(path, "w") as f:
         f.write(py)
-    spec = importlib.util.spec_from_file_location(name.lower() + "_ref", path)
+    spec = importlib.util.spec_from_file_location(name.lower() + tag + "_ref", path)
     m = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(m)
     return m
@@ -217,8 +230,62 @@ def case_periodic(m2):
     configure_2d(m2, 16, 4, 4, 1)
 
 
+def case_dual():
+    """f3: the RK4 step with the S branch live.  Blast wave 16x16 with periodic ghosts (uniform far field keeps
+    the S state, the blast front switches to E) and the reference's shock-cloud problem with its own boundaries!."""
+    m2 = load("Weno5_2D", DUAL_PATCH, "_dual")
+    nb = m2.NBnd
+    calls = []
+    orig_switch = m2.ES_Switch
+
+    def counting_switch(*a):
+        r = orig_switch(*a)
+        calls.append(len(r[3]))
+        return r
+
+    m2.ES_Switch = counting_switch
+    # periodic blast
+    reset_oob()
+    n = 16
+    configure_2d(m2, n, n, 1.0, 1.0)
+    g, q, bxb, byb = pr.blast(n)
+    q, bxb, byb = (np.asfortranarray(a) for a in (q, bxb, byb))
+
+    def wrap(a):
+        Nx, Ny = a.shape[0], a.shape[1]
+        a[0:nb] = a[Nx - 2 * nb:Nx - nb]
+        a[Nx - nb:Nx] = a[nb:2 * nb]
+        a[:, 0:nb] = a[:, Ny - 2 * nb:Ny - nb]
+        a[:, Ny - nb:Ny] = a[:, nb:2 * nb]
+
+    def periodic_boundaries(q_, fsy, gsx):
+        for a in (q_, fsy, gsx):
+            wrap(a)
+
+    saved = m2.boundaries_b
+    m2.boundaries_b = periodic_boundaries
+    try:
+        periodic_boundaries(q, bxb, byb)
+        out = dict(nx=n, ny=n, xsize=1.0, ysize=1.0, q0=q, bxb0=bxb, byb0=byb)
+        dts = []
+        for s in (1, 2):
+            dt, vxmax, vymax = m2.timestep(q)
+            q, bxb, byb = m2.classical_RK4_step(q, bxb, byb, dt)
+            dts.append(float(dt))
+            out[f"q{s}"], out[f"bxb{s}"], out[f"byb{s}"] = np.array(q), np.array(bxb), np.array(byb)
+    finally:
+        m2.boundaries_b = saved
+    save("ref2d_dual_blast", **out, dt=np.array(dts), nbad=np.array(calls), oob=oob())
+    # the reference's own problem
+    reset_oob()
+    del calls[:]
+    configure_2d(m2, 16, 4, 4, 1)
+    out = run_2d(m2, 1)
+    save("ref2d_dual_shockcloud", nx=16, ny=4, xsize=4.0, ysize=1.0, **out, nbad=np.array(calls), oob=oob())
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["functions", "1d", "shockcloud", "periodic"]
+    which = sys.argv[1:] or ["functions", "1d", "shockcloud", "periodic", "dual"]
     os.makedirs(OUT, exist_ok=True)
     t0 = time.time()
     if "1d" in which:
@@ -231,4 +298,6 @@ if __name__ == "__main__":
             case_shockcloud(m2)
         if "periodic" in which:
             case_periodic(m2)
+    if "dual" in which:
+        case_dual()
     print(f"done in {time.time() - t0:.0f} s")

@@ -34,6 +34,7 @@ def hostmath():
     lib = C.CDLL(so)
     dp = C.POINTER(C.c_double)
     lib.hm_sweep.argtypes = [C.c_int, C.c_int, dp, C.c_int, C.c_int, C.c_double, C.c_double, dp, dp]
+    lib.hm_sweep_S.argtypes = lib.hm_sweep.argtypes
     for f in (lib.hm_e2s, lib.hm_s2e):
         f.restype = C.c_double
         f.argtypes = [C.c_double] * 9

@@ -38,6 +38,29 @@ def test_structured_sweep_matches_oracle(hostmath, name, direction):
     assert np.abs(bs[sl] - bso[sl]).max() <= 1e-12 * max(1.0, np.abs(bso[sl]).max())
 
 
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("direction", [0, 1])
+def test_structured_sweep_S_branch_matches_oracle(hostmath, name, direction):
+    """The entropy-variable sweep against the numpy restatement of
+    weno5_flux_difference_S, which tests/test_reference_pin.py pins against the reference."""
+    from oracle import weno5_numpy as M
+    g, q, bx, by = CASES[name]()
+    qS = np.asfortranarray(q[..., 0:8])
+    dq = np.zeros_like(qS, order="F")
+    bs = np.zeros(qS.shape[:2], order="F")
+    bc = g.bc_y if direction else g.bc_x
+    hostmath.hm_sweep_S(g.Nx, g.Ny, dp(qS), direction, int(bc), g.gam, g.eps, dp(dq), dp(bs))
+    bcname = {0: "outflow", 1: "periodic"}[int(bc)]
+    if direction == 0:
+        dqo, bso, _ = M.flux_difference_S(np.ascontiguousarray(qS), g.gam, g.eps, bcname)
+    else:
+        dqr, _, gr = M.flux_difference_S(M.rotate_fwd(np.ascontiguousarray(qS)), g.gam, g.eps, bcname)
+        dqo, bso = M.rotate_bwd(dqr), gr.T
+    sl = (slice(2, g.Nx - 2), slice(2, g.Ny - 2))
+    assert np.abs(dq[sl] - dqo[sl]).max() <= 1e-12 * max(1.0, np.abs(dqo[sl]).max())
+    assert np.abs(bs[sl] - bso[sl]).max() <= 1e-12 * max(1.0, np.abs(bso[sl]).max())
+
+
 def test_degenerate_faces_are_ill_conditioned_but_bounded(hostmath):
     """Orszag-Tang has faces where By changes sign with Bz = 0: there alpha_s is the square
     root of a round-off residual (Weno5_2D.jl:1355-1356), so two correct implementations differ

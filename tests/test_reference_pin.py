@@ -246,6 +246,54 @@ def test_rk4_step_1d_bit_identical(name, ctor):
         assert ulps(q4[:, 7], qs[s + 1][:, 7]) <= 2
 
 
+# ------------------------------------------------------------------------------------------ S branch / dual energy (f3)
+def test_s_branch_functions_match_reference():
+    """compute_primitive_variables_S (:953), compute_fluxes_S (:927), compute_eigenvectors_S_vec (:640) and
+    weno5_flux_difference_S (:361), x and y: round-off (pow) level against the reference's outputs."""
+    d = golden("ref2d_functions")
+    g = grid_of(d, pr.OUTFLOW)
+    qS = np.ascontiguousarray(d["q"][..., 0:8])
+    Nx, Ny = qS.shape[:2]
+    u = M.primitives_S(qS, g.gam)
+    assert ulps(u, d["uS"]) <= 4
+    F = M.fluxes_S(qS, u)
+    assert np.abs(F - d["FS"]).max() <= 1e-15 * np.abs(d["FS"]).max()
+    L, R = M.eigenvectors_S(u[:-1, :-1], u[1:, :-1], g.gam)
+    assert np.abs(L - d["LS"][:-1, :-1]).max() <= 1e-14 * np.abs(d["LS"]).max()
+    assert np.abs(R - d["RS"][:-1, :-1]).max() <= 1e-14 * np.abs(d["RS"]).max()
+    LR = np.einsum("ijmc,ijck->ijmk", d["LS"][:-1, :-1], d["RS"][:-1, :-1])
+    assert np.abs(LR - np.eye(7)).max() < 1e-14                      # the reference's S eigenvectors are a valid pair
+    dq, fsy, _ = M.flux_difference_S(qS, g.gam, g.eps, "outflow")
+    assert np.abs(dq - d["dqx_S"])[:Nx - 3].max() <= 1e-14 * np.abs(d["dqx_S"]).max()
+    assert np.abs(fsy - d["fsy_S"])[:Nx - 3].max() <= 1e-14 * np.abs(d["fsy_S"]).max()
+    dqr, _, gr = M.flux_difference_S(M.rotate_fwd(qS), g.gam, g.eps, "outflow")
+    assert np.abs(M.rotate_bwd(dqr) - d["dqy_S"])[:, :Ny - 3].max() <= 1e-14 * np.abs(d["dqy_S"]).max()
+    assert np.abs(gr.T - d["gsx_S"])[:, :Ny - 3].max() <= 1e-14 * np.abs(d["gsx_S"]).max()
+
+
+def test_dual_energy_step_matches_reference():
+    """The RK4 step with the reference's own (commented-out, Weno5_2D.jl:1740) switching criterion restored:
+    blast wave 16x16 with periodic ghosts, two steps; 52..98 of the cells switch to the E state per stage."""
+    d = golden("ref2d_dual_blast")
+    g = grid_of(d, pr.PERIODIC)
+    P = mirror_params(g)
+    assert d["nbad"].min() > 20 and d["nbad"].max() < 150            # a genuine mixture of E and S cells (ghosts included)
+    q, bx, by = d["q0"], d["bxb0"], d["byb0"]
+    for s in range(1, len(d["dt"]) + 1):
+        q, bx, by, nbad = M.classical_RK4_step_2d_dual(q, bx, by, float(d["dt"][s - 1]), P)
+        err = group_err(q, d[f"q{s}"])
+        assert max(err.values()) <= 1e-13, err
+        assert np.abs(bx - d[f"bxb{s}"]).max() <= 1e-14 and np.abs(by - d[f"byb{s}"]).max() <= 1e-14
+
+
+def test_dual_energy_step_reference_problem():
+    d = golden("ref2d_dual_shockcloud")
+    g = grid_of(d, pr.OUTFLOW)
+    q, bx, by, nbad = M.classical_RK4_step_2d_dual(d["q0"], d["bxb0"], d["byb0"], float(d["dt"][0]), mirror_params(g))
+    err = group_err(q, d["q1"])
+    assert max(err.values()) <= 1e-9, err                            # Q3-limited, like the E-only step
+
+
 # ------------------------------------------------------------------------------------------ CUDA path
 gpu = pytest.mark.gpu
 
@@ -315,3 +363,61 @@ def test_gpu_rk4_step_1d_vs_reference(cuda, name, ctor, tol_linf, tol_l1):
             scale = np.abs(ref[:, idx]).max()
             assert np.abs(q4[3:-3][:, idx] - ref[3:-3][:, idx]).max() <= tol_linf * scale, (s, gname)
             assert rel_l1(q4[3:-3][:, idx], ref[3:-3][:, idx]) <= tol_l1, (s, gname)
+
+
+# ------------------------------------------------------------------------------------------ dual energy on the GPU
+@gpu
+def test_gpu_dual_energy_vs_reference(cuda):
+    d = golden("ref2d_dual_blast")
+    g = grid_of(d, pr.PERIODIC)
+    with cuda.Solver(g, es_roundtrip=True) as s:
+        s.set_es_switch(True, 1e-5)
+        s.upload(d["q0"], d["bxb0"], d["byb0"])
+        for k in range(1, len(d["dt"]) + 1):
+            s.rk4_step(float(d["dt"][k - 1]))
+            q, bx, by = s.download()
+            inner = (slice(3, -3), slice(3, -3))
+            err = group_err(q[inner], d[f"q{k}"][inner])
+            assert max(err.values()) <= 1e-10, (k, err)
+            assert np.abs(bx - d[f"bxb{k}"])[inner].max() <= 1e-11 and np.abs(by - d[f"byb{k}"])[inner].max() <= 1e-11
+        assert 20 < s.es_switch_count() < 150
+
+
+@gpu
+def test_gpu_dual_energy_vs_oracle_and_limits(cuda):
+    """48^2 blast, 3 steps against the numpy oracle; threshold 0 switches every cell to the E state, which is the
+    shipped E-only step; a huge threshold keeps the S state everywhere (entropy is advected, E derived)."""
+    g, q0, bx0, by0 = pr.blast(48)
+    P = mirror_params(g)
+    dt = O.timestep_2d(g, q0)[0]
+    qo, bxo, byo = q0, bx0, by0
+    for _ in range(3):
+        qo, bxo, byo, nbad = M.classical_RK4_step_2d_dual(qo, bxo, byo, dt, P)
+    inner = (slice(3, -3), slice(3, -3))
+    with cuda.Solver(g, es_roundtrip=True) as s:
+        s.set_es_switch(True, 1e-5)
+        s.upload(q0, bx0, by0)
+        for _ in range(3):
+            s.rk4_step(dt)
+        q, bx, by = s.download()
+        nsw = s.es_switch_count()
+        err = group_err(q[inner], qo[inner])
+        assert max(err.values()) <= 1e-9, err
+        assert 0 < nsw < g.nx * g.ny and abs(nsw - nbad[3]) <= 2       # cells switched in the last stage (2: borderline dS)
+        # threshold 0: every cell takes the E state -> the E-only step
+        s.set_es_switch(True, 0.0)
+        s.upload(q0, bx0, by0)
+        s.rk4_step(dt)
+        qa = s.download()[0]
+        assert s.es_switch_count() == g.nx * g.ny
+        s.set_es_switch(False)
+        s.upload(q0, bx0, by0)
+        s.rk4_step(dt)
+        qb = s.download()[0]
+        err = group_err(qa[inner], qb[inner])
+        assert max(err.values()) <= 1e-13, err
+        # huge threshold: S state everywhere
+        s.set_es_switch(True, 1e30)
+        s.upload(q0, bx0, by0)
+        s.rk4_step(dt)
+        assert s.es_switch_count() == 0
