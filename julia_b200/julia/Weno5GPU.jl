@@ -15,7 +15,7 @@
 # same entry points and is what the test-suite drives.
 module Weno5GPU
 
-export Weno5Params, Solver, upload!, download, boundaries!, timestep, classical_RK4_step,
+export Weno5Params, Solver, upload!, download, boundaries!, timestep, classical_RK4_step, set_es_switch!, es_switch_count,
        classical_RK4_step!, advance!, compute_divB, compute_global_vmax, interpolateB_center2face,
        state2conserved, WENO5_2D, WENO5_1D, Pipe, pipe_step!
 
@@ -112,6 +112,19 @@ compute_global_vmax(s::Solver) = (r = timestep(s); is1d(s) ? r[2] : (r[2], r[3])
 
 "classical_RK4_step on the resident state (Weno5_2D.jl:125 / Weno5_1D.jl:152)."
 classical_RK4_step!(s::Solver, dt::Real) = check(ccall((:weno5_rk4_step, libweno5), Cint, (Ptr{Cvoid}, Cdouble), s.h, dt))
+
+"""
+Dual-energy mode: run the E sweeps and the entropy-variable S sweeps (weno5_flux_difference_S, Weno5_2D.jl:361)
+every stage and let ES_Switch (:1734) choose per cell with the criterion the reference wrote and disabled
+(:1740): |S(E) - S| >= threshold takes the E state.  `enable = false` is the shipped behaviour.
+"""
+set_es_switch!(s::Solver, enable::Bool=true; threshold::Real=1e-5) =
+    check(ccall((:weno5_set_es_switch, libweno5), Cint, (Ptr{Cvoid}, Cint, Cdouble), s.h, enable ? 1 : 0, threshold))
+function es_switch_count(s::Solver)
+    n = Ref{Culonglong}(0)
+    check(ccall((:weno5_es_switch_count, libweno5), Cint, (Ptr{Cvoid}, Ref{Culonglong}), s.h, n))
+    return Int(n[])
+end
 
 "The driver loop of WENO5_2D()/WENO5_1D() kept on the device; returns (t, steps_done)."
 function advance!(s::Solver, nsteps::Integer; tmax::Real=0.0, t::Real=0.0)
