@@ -112,6 +112,15 @@ int weno5_totals(weno5_ctx *ctx, double sums[11]);
 int weno5_set_es_switch(weno5_ctx *ctx, int enable, double threshold);
 int weno5_es_switch_count(weno5_ctx *ctx, unsigned long long *cells);
 
+/* ---- snapshot hook (SURVEY "next" row f4).  Arr2Img(arr, cmap; range, log) of JColorMaps.jl:92-146, which the
+ * reference driver calls on q[:,:,k] and divB for its frames (Weno5_2D.jl:75-99), evaluated on the resident
+ * state up to the colour-table lookup: rimg (Ny x Nx Int16, column-major -- the reference transposes) receives
+ * the 1-based colour index of every pixel, so the caller's image is cmap[rimg].  component: 0..8 = the 9
+ * components of q in the reference's order, 9 = bxb, 10 = byb, 11 = compute_divB.  lo == hi == 0 selects the
+ * automatic range (finite pixels); log_scale = 1 is the reference's log = true.  range_used may be NULL. */
+int weno5_arr2img(weno5_ctx *ctx, int component, double lo, double hi, int log_scale, int ncolours, short *rimg,
+                  double range_used[2]);
+
 /* ---- one-shot, reference-shaped calls: host arrays in -> host arrays out */
 /* (q4,bxb4,byb4) = classical_RK4_step(q0,bxb0,byb0,dt)   Weno5_2D.jl:125-317 */
 int weno5_classical_rk4_step_2d(const weno5_params *params, const double *q0, const double *bxb0,

@@ -118,6 +118,7 @@ struct weno5_ctx {
     double *scratch;                 // one plane (divB)
     double *ctl = nullptr;           // device: dt, t, vxmax, vymax, tmax, steps, bad
     unsigned long long *vmax_bits = nullptr;
+    unsigned long long *vmax_bits_img = nullptr;   // 3 keys of the snapshot range reduction
     double *sums = nullptr;
     double *h_ctl = nullptr;         // pinned mirror
     int side[4];                     // SideBC of x-lo, x-hi, y-lo, y-hi for this slab
@@ -328,7 +329,8 @@ static int create_ctx(const weno5_params *P, int device, int ny_local, int j_off
 
     CU(cudaMalloc(&c->ctl, 8 * sizeof(double)));
     CU(cudaMemsetAsync(c->ctl, 0, 8 * sizeof(double), c->stream));
-    CU(cudaMalloc(&c->vmax_bits, 2 * sizeof(unsigned long long)));
+    CU(cudaMalloc(&c->vmax_bits, 8 * sizeof(unsigned long long)));
+    c->vmax_bits_img = c->vmax_bits + 4;
     CU(cudaMalloc(&c->sums, 16 * sizeof(double)));
     CU(cudaMallocHost(&c->h_ctl, 16 * sizeof(double)));
 
@@ -949,6 +951,41 @@ extern "C" int weno5_totals(weno5_ctx *c, double sums[11])
     CU(cudaMemcpyAsync(c->h_ctl, c->sums, 11 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     for (int k = 0; k < 11; ++k) sums[k] = (c->g.is1d && k >= 9) ? 0.0 : c->h_ctl[k];
+    return 0;
+}
+
+// ------------------------------------------------------------------ snapshot hook
+extern "C" int weno5_arr2img(weno5_ctx *c, int component, double lo, double hi, int log_scale, int ncolours, short *rimg,
+                             double range_used[2])
+{
+    if (!c || !rimg) return fail(WENO5_ERR_ARG, "null argument");
+    if (!c->uploaded) return fail(WENO5_ERR_STATE, "no state on the device yet");
+    if (ncolours < 2 || ncolours > 32767) return fail(WENO5_ERR_ARG, "ncolours must be in 2..32767 (Int16 indices)");
+    const Geom &g = c->g;
+    if (component < 0 || component > 11 || (g.is1d && component > 8)) return fail(WENO5_ERR_ARG, "unknown component %d", component);
+    CU(cudaSetDevice(c->device));
+    const double *field;
+    if (component <= 8) {
+        int k = component;                         // reference order: ..., 8th = S, 9th = E
+        if (component == 7) k = C_S;
+        if (component == 8) k = C_E;
+        field = c->Q0.q[k];
+    } else if (component == 9) field = c->Q0.bx;
+    else if (component == 10) field = c->Q0.by;
+    else {
+        launch_divb(c->Q0.bx, c->Q0.by, c->scratch, g, c->P.dx, c->P.dy, c->stream);
+        c->launches++;
+        field = c->scratch;
+    }
+    short *img = reinterpret_cast<short *>(c->rhs[1]);               // free between steps
+    launch_arr2img(field, g, lo, hi, log_scale ? 1 : 0, ncolours, c->vmax_bits_img, img, c->sums, c->stream);
+    c->launches += 2;
+    const size_t n = (size_t)g.Nx * g.Ny;
+    CU(cudaMemcpyAsync(rimg, img, n * sizeof(short), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_ctl, c->sums, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    if (range_used) { range_used[0] = c->h_ctl[0]; range_used[1] = c->h_ctl[1]; }
     return 0;
 }
 

@@ -1036,4 +1036,85 @@ void launch_totals(const double *const planes[], int nplanes, const Geom &g, dou
     totals_kernel<<<nplanes, 1024, 0, s>>>(a);
 }
 
+// ------------------------------------------------------------------ snapshot hook (Arr2Img, JColorMaps.jl:92-146)
+// Order-preserving map double -> unsigned 64-bit (all finite values and infinities), so that grid-wide
+// minima / maxima are integer atomics.
+__device__ __forceinline__ unsigned long long ord_key(double v)
+{
+    const long long b = __double_as_longlong(v);
+    return b >= 0 ? (unsigned long long)b ^ 0x8000000000000000ull : ~(unsigned long long)b;
+}
+__device__ __forceinline__ double ord_val(unsigned long long k)
+{
+    return __longlong_as_double((k & 0x8000000000000000ull) ? (long long)(k ^ 0x8000000000000000ull) : (long long)~k);
+}
+
+// keys[0] = min over v > 0, keys[1] = min over finite v, keys[2] = max over finite v (public Nx x Ny region)
+__global__ void img_range_kernel(const double *__restrict__ f, int Nx, int Ny, int pitch, int row0, unsigned long long *keys)
+{
+    unsigned long long kp = ~0ull, kmin = ~0ull, kmax = 0ull;
+    const int n = Nx * Ny;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const int i = e % Nx + 1, j = e / Nx + row0;
+        const double v = f[(size_t)i + (size_t)pitch * j];
+        const unsigned long long k = ord_key(v);
+        if (v > 0.0) kp = min(kp, k);
+        if (isfinite(v)) { kmin = min(kmin, k); kmax = max(kmax, k); }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        kp = min(kp, __shfl_xor_sync(0xffffffffu, kp, o));
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&keys[0], kp);
+        atomicMin(&keys[1], kmin);
+        atomicMax(&keys[2], kmax);
+    }
+}
+
+// colour index (1-based, Int16) of every pixel of the TRANSPOSED field: out[(j-1) + Ny (i-1)].
+// rng[0..1] receive the range that was used (before the log10).
+__global__ void img_index_kernel(const double *__restrict__ f, int Nx, int Ny, int pitch, int row0, double lo, double hi,
+                                 int log_scale, int ncolours, const unsigned long long *keys, short *out, double *rng)
+{
+    double minpos = 0.0;
+    if (log_scale) minpos = ord_val(keys[0]);
+    if (lo == 0.0 && hi == 0.0) {                                   // automatic range over the finite pixels
+        if (log_scale) {                                             // after non-positive pixels became minpos
+            const double mx = ord_val(keys[2]);
+            lo = minpos;
+            hi = mx > 0.0 ? mx : minpos;
+        } else {
+            lo = ord_val(keys[1]);
+            hi = ord_val(keys[2]);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { rng[0] = lo; rng[1] = hi; }
+    if (log_scale) { lo = log10(lo); hi = log10(hi); }
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= Nx * Ny) return;
+    const int i = e % Nx + 1, j = e / Nx + row0;
+    double v = f[(size_t)i + (size_t)pitch * j];
+    if (log_scale) {
+        if (v <= 0.0) v = minpos;
+        v = log10(v);
+    }
+    if (isnan(v)) v = lo;
+    double r = rint((v - lo) / (hi - lo) * (double)(ncolours - 1)) + 1.0;
+    r = fmin(fmax(r, 1.0), (double)ncolours);                       // also absorbs +-inf; NaN (0/0 range) -> 1
+    if (isnan(r)) r = 1.0;
+    out[(size_t)(j - row0) + (size_t)Ny * (i - 1)] = (short)r;
+}
+
+void launch_arr2img(const double *field, const Geom &g, double lo, double hi, int log_scale, int ncolours,
+                    unsigned long long *keys, short *out, double *rng, cudaStream_t s)
+{
+    const unsigned long long init[3] = {~0ull, ~0ull, 0ull};
+    cudaMemcpyAsync(keys, init, sizeof(init), cudaMemcpyHostToDevice, s);
+    const int n = g.Nx * g.Ny, row0 = g.is1d ? 0 : 1;
+    img_range_kernel<<<min((n + 255) / 256, 1184), 256, 0, s>>>(field, g.Nx, g.Ny, g.pitch, row0, keys);
+    img_index_kernel<<<(n + 255) / 256, 256, 0, s>>>(field, g.Nx, g.Ny, g.pitch, row0, lo, hi, log_scale, ncolours, keys, out, rng);
+}
+
 }  // namespace w5

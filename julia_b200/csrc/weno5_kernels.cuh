@@ -110,6 +110,9 @@ void launch_center2face(const double *Bx, const double *By, double *bxb, double 
 void launch_divb(const double *bxb, const double *byb, double *divb, const Geom &g, double dx, double dy,
                  cudaStream_t s);
 void launch_totals(const double *const planes[], int nplanes, const Geom &g, double *sums, cudaStream_t s);
+// Arr2Img (JColorMaps.jl:92-146) up to the colour-table lookup; keys: 3 x u64 scratch, rng: 2 doubles (range used)
+void launch_arr2img(const double *field, const Geom &g, double lo, double hi, int log_scale, int ncolours,
+                    unsigned long long *keys, short *out, double *rng, cudaStream_t s);
 int flux_chunk(int dir);          // faces per march step of the active launch variant
 int flux_lines_per_cta(int dir);  // lines across the sweep per CTA
 int flux_uses_tma();              // 1 if the active variant stages through TMA tensor maps

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libweno5mhd.so")
+# WENO5_LIB: development knob to time an experimental build of the same sources (never a different backend)
+LIB_PATH = os.environ.get("WENO5_LIB") or os.path.join(_HERE, "libweno5mhd.so")
 
 WENO5_OK, ERR_ARG, ERR_CUDA, ERR_NCCL, ERR_STATE, ERR_NUMERIC = 0, -1, -2, -3, -4, -5
 BC_OUTFLOW, BC_PERIODIC = 0, 1
@@ -53,6 +54,7 @@ SIGNATURES = {
     "weno5_totals": (C.c_int, [_vp, _dp]),
     "weno5_set_es_switch": (C.c_int, [_vp, C.c_int, C.c_double]),
     "weno5_es_switch_count": (C.c_int, [_vp, C.POINTER(C.c_ulonglong)]),
+    "weno5_arr2img": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_short), _dp]),
     "weno5_classical_rk4_step_2d": (C.c_int, [C.POINTER(Params), _dp, _dp, _dp, C.c_double, _dp, _dp, _dp]),
     "weno5_classical_rk4_step_1d": (C.c_int, [C.POINTER(Params), _dp, C.c_double, _dp]),
     "weno5_step_host": (C.c_int, [_vp, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp]),

@@ -140,6 +140,20 @@ class Solver:
         L.check(self.lib.weno5_es_switch_count(self.h, C.byref(n)))
         return int(n.value)
 
+    # -- snapshot hook
+    def arr2img(self, component, cmap=None, range=(0.0, 0.0), log=False, ncolours=None):
+        """``Arr2Img(q[:,:,component+1], cmap; range, log)`` (JColorMaps.jl:92) on the resident state: returns
+        ``cmap[rimg]`` (shape (Ny, Nx) + cmap.shape[1:]) -- or the 1-based Int16 colour indices if ``cmap`` is
+        None -- and the range used.  Components 9, 10, 11 are bxb, byb and compute_divB."""
+        n = int(ncolours if cmap is None else len(cmap))
+        rimg = np.zeros((self.Ny, self.Nx), dtype=np.int16, order="F")
+        rng = np.zeros(2)
+        L.check(self.lib.weno5_arr2img(self.h, int(component), float(range[0]), float(range[1]), 1 if log else 0, n,
+                                       rimg.ctypes.data_as(C.POINTER(C.c_short)), L.dptr(rng)))
+        if cmap is None:
+            return rimg, tuple(rng)
+        return np.asarray(cmap)[rimg.astype(np.int64) - 1], tuple(rng)
+
     # -- diagnostics
     def divb(self):
         d = np.zeros((self.Nx, self.Ny), order="F")

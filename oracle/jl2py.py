@@ -557,6 +557,10 @@ class Parser:
                 return f"jnot({self.gen(n[2])})"
             return f"({n[1]}{self.gen(n[2])})"
         if k == "cmp":
+            if len(n[2]) == 1 and n[2][0] in ("==", "!=", "===", "!=="):
+                # `a == b` on arrays is a single Bool in Julia (elementwise is `.==`)
+                f = "jeq" if n[2][0] in ("==", "===") else "jne"
+                return f"{f}({self.gen(n[1][0])}, {self.gen(n[1][1])})"
             parts = [self.gen(n[1][0])]
             for op, x in zip(n[2], n[1][1:]):
                 op = {"===": "==", "!==": "!="}.get(op, op).lstrip(".")
@@ -891,6 +895,13 @@ def split_top_level(toks):
         if toks[i].kind == "NL":
             i += 1
             continue
+        if toks[i].kind == "ID" and toks[i].val == "module":        # `module X` ... `end`: look inside
+            while toks[i].kind != "NL":
+                i += 1
+            continue
+        if toks[i].kind == "ID" and toks[i].val == "end":           # the module's closing `end`
+            i += 1
+            continue
         start = i
         depth = brack = 0
         while i < n and toks[i].kind != "EOF":
@@ -911,13 +922,15 @@ def split_top_level(toks):
     return items
 
 
-def translate(src, header="from oracle.jlrt import *\n"):
+def translate(src, header="from oracle.jlrt import *\n", only=None):
     """Translate Julia source text; returns (python_source, report) where report lists the top-level items
-    that could not be translated (line, first tokens, error)."""
+    that could not be translated (line, first tokens, error).  `only`: keep just the named functions."""
     out = [header]
     failed = []
     for item in split_top_level(tokenize(src)):
         line0 = item[0].line
+        if only is not None and not (item[0].val == "function" and len(item) > 1 and item[1].val in only):
+            continue
         try:
             last = item[-1].line
             ps = Parser(item + [Tok("NL", "\n", last, True), Tok("EOF", "", last, True)])

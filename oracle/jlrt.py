@@ -24,6 +24,8 @@ NAN = math.nan
 Float64 = float
 String = str
 Bool = bool
+Int16 = np.int16
+Int32 = np.int32
 
 
 class _Colon:
@@ -408,7 +410,21 @@ def ceil(x, *a):
 
 
 def jround(x, *a):
-    return np.round(x)
+    if isinstance(x, type) or x in (Int16, Int32):          # round(Int16, v): ties to even, then convert
+        v = np.rint(a[0])
+        return v.astype(x) if isinstance(v, np.ndarray) else int(v)
+    return np.rint(x)
+
+
+def jeq(a, b):
+    if isinstance(a, (np.ndarray, list, tuple)) or isinstance(b, (np.ndarray, list, tuple)):
+        a, b = np.asarray(a), np.asarray(b)
+        return a.shape == b.shape and bool(np.all(a == b))
+    return a == b
+
+
+def jne(a, b):
+    return not jeq(a, b)
 
 
 def jInt(x):

@@ -714,6 +714,27 @@ def classical_RK4_step_2d_dual(q0, bxb0, byb0, dt, P, threshold=1e-5):
     return q4, bx4, by4, [int(b[NB:-NB, NB:-NB].sum()) for b in (b1, b2, b3, b4)]     # interior cells switched to E
 
 
+# ----------------------------------------------------------------------------- snapshot hook
+def arr2img_index(arr, ncolours, range_=(0.0, 0.0), log=False):
+    """Arr2Img, JColorMaps.jl:92-146, up to the colour-table lookup: the 1-based colour index of every pixel
+    of the transposed field (Int16 in the reference).  `range_ == (0,0)` selects the automatic range over the
+    finite pixels; with `log`, non-positive pixels are first set to the smallest positive one.  NaN pixels
+    take the first colour.  (The reference's `sqrt` option cannot run: its keyword shadows Base.sqrt.)"""
+    img = np.array(arr, dtype=np.float64).T.copy()
+    if log:
+        img[img <= 0] = img[img > 0].min()
+    lo, hi = float(range_[0]), float(range_[1])
+    if lo == 0.0 and hi == 0.0:
+        good = img[np.isfinite(img)]
+        lo, hi = good.min(), good.max()
+    if log:
+        img = np.log10(img)
+        lo, hi = np.log10(lo), np.log10(hi)
+    img[np.isnan(img)] = lo
+    r = np.rint((img - lo) / (hi - lo) * (ncolours - 1)) + 1
+    return np.clip(r, 1, ncolours).astype(np.int16)
+
+
 def boundaries_1d(q, P):
     """Weno5_1D.jl:1076-1090."""
     _fill_axis(q, 0, P.bc_x)

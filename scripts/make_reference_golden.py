@@ -23,6 +23,9 @@ are called unmodified; what the harness does around them is stated per case:
                      restored (the only source edit, see DUAL_PATCH), so that the S branch is live: periodic blast
                      wave 16x16 (2 steps) and the shock-cloud problem (1 step); `nbad` = cells switched to E per stage.
 
+  ref_arr2img        "next" row f4: Arr2Img (JColorMaps.jl:92-146, the only function translated from that file) on
+                     fields of the shock-cloud result with an identity colour table.
+
 `oob` in each file counts the @inbounds reads that left their column: "wrapped" ones read
 the neighbouring column like the Julia binary would, "outside" ones (past the allocation) read NaN here.
 """
@@ -48,14 +51,14 @@ GEN = os.path.join(ROOT, "oracle", "_ref")
 DUAL_PATCH = (("#dS = abs.(q_SE[:,:,8] - q_S[:,:,8])", "dS = abs.(q_SE[:,:,8] - q_S[:,:,8])"), ("\ndS = 1\n", "\n"))
 
 
-def load(name, patch=(), tag=""):
+def load(name, patch=(), tag="", only=None):
     os.makedirs(GEN, exist_ok=True)
     with open(os.path.join(REF, name + ".jl")) as f:
         src = f.read()
     for old, new in patch:
         assert src.count(old) == 1, old
         src = src.replace(old, new)
-    py, failed = jl2py.translate(src)
+    py, failed = jl2py.translate(src, only=only)
     assert not failed, failed
     path = os.path.join(GEN, name.lower() + tag + "_ref.py")
     with open(path, "w") as f:
@@ -284,8 +287,33 @@ def case_dual():
     save("ref2d_dual_shockcloud", nx=16, ny=4, xsize=4.0, ysize=1.0, **out, nbad=np.array(calls), oob=oob())
 
 
+def case_arr2img():
+    """f4: the snapshot hook.  Arr2Img (JColorMaps.jl:92-146) on fields of the shock-cloud state after one step,
+    with an identity colour table of n entries (the returned "image" is then the colour index itself): fixed
+    range, automatic range, log scaling, a field with NaNs."""
+    mc = load("JColorMaps", only={"Arr2Img"})
+    d = np.load(os.path.join(OUT, "ref2d_shockcloud32.npz"))
+    out = {}
+    rho = np.asfortranarray(d["q1"][:, :, 0])
+    by = np.asfortranarray(d["q1"][:, :, 5])
+    hole = rho.copy(order="F")
+    hole[5, 5] = np.nan
+    hole[20, 7] = np.nan
+    cases = {"fixed": (rho, 256, dict(range_=jlrt.jvect([1.0, 3.0]))),
+             "auto": (by, 256, {}),
+             "log": (rho, 64, dict(log=True)),
+             "nan": (hole, 256, {}),
+             "logneg": (np.asfortranarray(d["q1"][:, :, 1]), 200, dict(log=True))}
+    for name, (arr, n, kw) in cases.items():
+        cmap = np.arange(1.0, n + 1.0)
+        out["in_" + name] = arr
+        out["out_" + name] = mc.Arr2Img(np.array(arr, order="F"), cmap, **kw)
+        out["n_" + name] = n
+    save("ref_arr2img", **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["functions", "1d", "shockcloud", "periodic", "dual"]
+    which = sys.argv[1:] or ["functions", "1d", "shockcloud", "periodic", "dual", "arr2img"]
     os.makedirs(OUT, exist_ok=True)
     t0 = time.time()
     if "1d" in which:
@@ -300,4 +328,6 @@ if __name__ == "__main__":
             case_periodic(m2)
     if "dual" in which:
         case_dual()
+    if "arr2img" in which:
+        case_arr2img()
     print(f"done in {time.time() - t0:.0f} s")

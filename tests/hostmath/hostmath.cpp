@@ -64,7 +64,9 @@ static int sweep_t(int Nx, int Ny, const double *q, int dir, int bc, double gam,
             };
             w5::RegStash stash;
             double Fs[7];
-            w5::face_flux_br<BR>(c, amax, eps, load, stash, Fs);
+            // the same forms the kernel instantiates: E branch difference-first, S branch plain
+            if (BR == 0) w5::face_flux(c, amax, eps, load, stash, Fs);
+            else w5::face_flux_br<BR>(c, amax, eps, load, stash, Fs);
             if (BR == 0) {
                 w5::BackCoef bc_;
                 w5::split_back(c, bc_);

@@ -265,9 +265,13 @@ def test_orszag_tang_full_size_invariants(n):
     assert np.isfinite(qs).all() and qs[..., 0].min() > 0
 
 
-def test_tma_and_ldgsts_staging_are_bit_identical(tmp_path):
+def test_tma_and_ldgsts_staging_agree_to_roundoff(tmp_path):
     """The flux kernels stage their tiles either with TMA tensor-map copies (default) or with
-    cp.async (WENO5_FLUX_VARIANT=2); the arithmetic is the same, so results must be bit-equal."""
+    cp.async (WENO5_FLUX_VARIANT=2).  The arithmetic is the same source, but the two are separate
+    template instantiations and ptxas contracts a few multiply-adds of the difference-first projection
+    differently (measured 2.7e-15 after 3 steps; the 12-projection form, -DW5_FACE_PLAIN, is bit-equal):
+    results agree to round-off.  Runs on one GPU vs slabs and the pipelined host step use ONE
+    instantiation and stay bit-identical (test_gpu_multi.py, test_pipelined_host_step_is_bit_identical)."""
     import os
     import subprocess
     import sys
@@ -286,7 +290,7 @@ def test_tma_and_ldgsts_staging_are_bit_identical(tmp_path):
         subprocess.check_call([sys.executable, "-c", code, out], env=env)
         res[variant] = np.load(out)
     for k in ("q", "bx", "by"):
-        assert np.array_equal(res["4"][k], res["2"][k]), k
+        assert np.abs(res["4"][k] - res["2"][k]).max() <= 1e-13 * np.abs(res["4"][k]).max(), k
     assert np.isfinite(res["4"]["q"]).all()
 
 

@@ -294,6 +294,19 @@ def test_dual_energy_step_reference_problem():
     assert max(err.values()) <= 1e-9, err                            # Q3-limited, like the E-only step
 
 
+# ------------------------------------------------------------------------------------------ snapshot hook (f4)
+ARR2IMG_CASES = {"fixed": dict(range_=(1.0, 3.0)), "auto": {}, "log": dict(log=True), "nan": {}, "logneg": dict(log=True)}
+
+
+@pytest.mark.parametrize("case", sorted(ARR2IMG_CASES))
+def test_arr2img_matches_reference(case):
+    """Arr2Img (JColorMaps.jl:92-146) run with an identity colour table: the oracle's colour indices are the
+    reference's, pixel for pixel."""
+    d = golden("ref_arr2img")
+    r = M.arr2img_index(d["in_" + case], int(d["n_" + case]), **ARR2IMG_CASES[case])
+    assert np.array_equal(r, d["out_" + case].astype(np.int16))
+
+
 # ------------------------------------------------------------------------------------------ CUDA path
 gpu = pytest.mark.gpu
 
@@ -421,3 +434,45 @@ def test_gpu_dual_energy_vs_oracle_and_limits(cuda):
         s.upload(q0, bx0, by0)
         s.rk4_step(dt)
         assert s.es_switch_count() == 0
+
+
+# ------------------------------------------------------------------------------------------ snapshot hook on the GPU
+@gpu
+@pytest.mark.parametrize("case,component", [("fixed", 0), ("auto", 5), ("log", 0), ("nan", 0), ("logneg", 1)])
+def test_gpu_arr2img_vs_reference(cuda, case, component):
+    """weno5_arr2img on the resident state against the reference's Arr2Img output (identity colour table)."""
+    d, s32 = golden("ref_arr2img"), golden("ref2d_shockcloud32")
+    g = grid_of(s32, pr.OUTFLOW)
+    q = np.array(s32["q1"], order="F")
+    q[:, :, component] = d["in_" + case]
+    kw = ARR2IMG_CASES[case]
+    with cuda.Solver(g) as s:
+        s.upload(q, s32["bxb1"], s32["byb1"])
+        rimg, rng = s.arr2img(component, None, range=kw.get("range_", (0.0, 0.0)), log=kw.get("log", False),
+                              ncolours=int(d["n_" + case]))
+        lut = np.arange(1.0, int(d["n_" + case]) + 1.0)
+        img, _ = s.arr2img(component, lut, range=kw.get("range_", (0.0, 0.0)), log=kw.get("log", False))
+    ref = d["out_" + case].astype(np.int16)
+    if kw.get("log"):
+        diff = np.abs(rimg.astype(int) - ref.astype(int))           # device log10 vs libm: a tie may round the other way
+        assert diff.max() <= 1 and (diff > 0).mean() <= 0.01
+    else:
+        assert np.array_equal(rimg, ref)
+    assert np.array_equal(img, lut[rimg.astype(int) - 1])
+    if "range_" in kw:
+        assert rng == kw["range_"]
+
+
+@gpu
+def test_gpu_arr2img_divb_and_faces(cuda):
+    g, q, bx, by = pr.orszag_tang(32)
+    with cuda.Solver(g) as s:
+        s.upload(q, bx, by)
+        s.advance(3)
+        qd, bxd, byd = s.download()
+        for comp, field in ((9, bxd), (10, byd), (8, qd[:, :, 8]), (7, qd[:, :, 7])):
+            rimg, rng = s.arr2img(comp, None, ncolours=256)
+            assert np.array_equal(rimg, M.arr2img_index(field, 256))
+            assert rng == (field.min(), field.max())
+        rimg, rng = s.arr2img(11, None, range=(-1e-11, 1e-11), ncolours=256)          # Weno5_2D.jl:98
+        assert np.array_equal(rimg, M.arr2img_index(s.divb(), 256, (-1e-11, 1e-11)))
