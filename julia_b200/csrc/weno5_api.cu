@@ -1144,8 +1144,11 @@ extern "C" int weno5_pipe_step(weno5_pipe *p, const double *q0, const double *bx
                 run = Ny - src;
             }
             if (run > g.NYI - ii) run = g.NYI - ii;
+            // S (q0[:,:,8]) is an output of the E-branch step, never an input (ES_Switch derives it from E,
+            // Weno5_2D.jl:1738): its plane is not sent over PCIe
             for (int f = 0; f < NCELL; ++f)
-                if (int r = copy_rows(c, c->Q0.q[f], q0 + host_comp(f) * hp, nullptr, Ny, src, ii, run)) return r;
+                if (f != C_S)
+                    if (int r = copy_rows(c, c->Q0.q[f], q0 + host_comp(f) * hp, nullptr, Ny, src, ii, run)) return r;
             if (int r = copy_rows(c, c->Q0.bx, bxb0, nullptr, Ny, src, ii, run)) return r;
             if (int r = copy_rows(c, c->Q0.by, byb0, nullptr, Ny, src, ii, run)) return r;
             ii += run;
