@@ -8,7 +8,7 @@ the numerics) into Python that runs on top of `oracle/jlrt.py`, a runtime that r
 semantics the files rely on (1-based column-major arrays, copying slices, linear indexing, `@inbounds`
 reads that run off the end of a column, `x^2 == x*x`, ...).  `scripts/make_reference_golden.py` uses
 it inside this container to run the UNMODIFIED reference functions and to write golden vectors under
-`tests/golden/ref_*.npz`; the translated source is written to `oracle/_ref/` (git-ignored) and is never
+`tests/golden/ref_*.npz`; the translated source is written to a scratch directory outside the repository and is never
 committed.  Nothing in the product path imports this file.
 
 Supported subset: function definitions (long and short form), for/while/if/elseif/else, return,

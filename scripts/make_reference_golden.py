@@ -2,7 +2,7 @@
 executed on oracle/jlrt.py) and writes its inputs/outputs as golden vectors tests/golden/ref_*.npz.
 
 Only runnable in the build container (needs /root/reference); the fixtures and this script are committed,
-the translated source goes to oracle/_ref/ (git-ignored) and is never committed.  The translated functions
+the translated source goes to a scratch directory outside the repository and is never committed.  The translated functions
 are called unmodified; what the harness does around them is stated per case:
 
   ref1d_rj95_2a      Weno5_1D: reference IC (N = 256+6), the driver's loop `vxmax = compute_global_vmax(q);
@@ -32,6 +32,7 @@ the neighbouring column like the Julia binary would, "outside" ones (past the al
 import importlib.util
 import os
 import sys
+import tempfile
 import time
 
 import numpy as np
@@ -43,7 +44,8 @@ from oracle import jl2py, jlrt  # noqa: E402
 
 REF = "/root/reference"
 OUT = os.path.join(ROOT, "tests", "golden")
-GEN = os.path.join(ROOT, "oracle", "_ref")
+# translated source never enters the repository tree: it lives in a scratch directory for the duration of the run
+GEN = os.path.join(tempfile.gettempdir(), "weno5_jl2py_ref")
 
 
 # The one source edit any case makes (case_dual only): the reference's own commented-out switching criterion
