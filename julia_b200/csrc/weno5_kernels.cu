@@ -536,11 +536,29 @@ __global__ void ct_faces_kernel(const CtArgs a)
     if (!wbx && !wby) return;
     const size_t g = (size_t)i + (size_t)a.pitch * j;
     const double cy = a.c_dy * dt, cx = a.c_dx * dt;
-    const double o = corner(i, j, a);
-    // Oxi/Oxj are only filled on 2..N-1 (Weno5_2D.jl:334-339)
-    const bool inner = !ct_outside(i, j, a);
+    // Away from outflow sides none of the boundary rules of ld_flux / ct_outside applies to the three corners
+    // of this face pair: plain loads (the kernel was instruction-bound on the clamping logic: 435 -> ~90
+    // instructions per thread; same arithmetic, bit-identical results)
+    const bool outflow = a.oxlo | a.oxhi | a.oylo | a.oyhi;
+    const bool lean = !outflow || (i >= 4 && i <= a.Nx - 3 && j >= 4 && j <= a.Ny - 3);
+    double o, oj_, oi_;
+    bool inner;
+    if (lean) {
+        const size_t p = (size_t)a.pitch;
+        const double g00 = a.gsx[g], f00 = a.fsy[g];
+        o = 0.5 * (g00 + a.gsx[g + 1] - f00 - a.fsy[g + p]);
+        oj_ = 0.5 * (a.gsx[g - p] + a.gsx[g - p + 1] - a.fsy[g - p] - f00);
+        oi_ = 0.5 * (a.gsx[g - 1] + g00 - a.fsy[g - 1] - a.fsy[g - 1 + p]);
+        inner = true;
+    } else {
+        o = corner(i, j, a);
+        // Oxi/Oxj are only filled on 2..N-1 (Weno5_2D.jl:334-339)
+        inner = !ct_outside(i, j, a);
+        oj_ = (inner && wbx) ? corner(i, j - 1, a) : 0.0;
+        oi_ = (inner && wby) ? corner(i - 1, j, a) : 0.0;
+    }
     if (wbx) {
-        const double oj = inner ? corner(i, j - 1, a) : 0.0;
+        const double oj = inner ? oj_ : 0.0;
         const double cur = a.bxc[g];
         double b;
         if (a.stage <= 3) {
@@ -553,7 +571,7 @@ __global__ void ct_faces_kernel(const CtArgs a)
         a.bxn[g] = b - cy * (o - oj);                       // Weno5_2D.jl:150
     }
     if (wby) {
-        const double oi = inner ? corner(i - 1, j, a) : 0.0;
+        const double oi = inner ? oi_ : 0.0;
         const double cur = a.byc[g];
         double b;
         if (a.stage <= 3) {
@@ -872,7 +890,7 @@ __global__ void vmax_kernel(const VmaxArgs a)
         const double By = (a.q[C_BY][g] + a.q[C_BY][g + 1]) / 2;
         const double Bz = (a.q[C_BZ][g] + a.q[C_BZ][g + 1]) / 2;
         const double S = (a.q[C_S][g] + a.q[C_S][g + 1]) / 2;
-        const double pres = S * pow(rho, a.gam - 1.0);
+        const double pres = S * pow_gm1(rho, a.gam);
         const double cs2 = a.gam * fabs(pres * ri);
         const double B2 = Bx * Bx + By * By + Bz * Bz;
         const double bbn2 = B2 * ri, bnx2 = Bx * Bx * ri, bny2 = By * By * ri;

@@ -94,6 +94,21 @@ W5_HD double fast_sqrt(double x)
 #endif
 }
 
+// rho^(gam-1), the one transcendental of the path (E2S/S2E, Weno5_2D.jl:1770-1793; compute_global_vmax, :1962;
+// compute_primitive_variables_S, :964).  For the reference's gam = 5/3 the exponent is 2/3 to within one ulp
+// (5.0/3.0 - 1.0 = 2/3 + 1.1e-16), so the device takes cbrt(rho)^2: within 3 ulp of pow and about a third of its
+// instructions -- the kernels that call it were instruction-bound on pow.  Any other gam goes through pow.
+W5_HD double pow_gm1(double rho, double gam)
+{
+#if defined(__CUDA_ARCH__)
+    if (gam == 5.0 / 3.0) {
+        const double c = cbrt(rho);
+        return c * c;
+    }
+#endif
+    return pow(rho, gam - 1.0);
+}
+
 // cons -> prim, cell-centre wave speeds and flux in the sweep frame
 // (Weno5_2D.jl:1573-1606, :1608-1667, :1533-1555).  q = [rho,M1,M2,M3,B1,B2,B3,E].
 W5_HD void cell_quantities(const double q[8], double gam, CellOut &o)
@@ -136,7 +151,7 @@ W5_HD void cell_quantities_S(const double q[8], double gam, CellOut &o, CellOutS
     const double v1 = q[1] * ri, v2 = q[2] * ri, v3 = q[3] * ri;
     const double B1 = q[4], B2 = q[5], B3 = q[6], S = q[7];
     const double BB = B1 * B1 + B2 * B2 + B3 * B3;
-    const double rg1 = pow(rho, gam - 1.0);
+    const double rg1 = pow_gm1(rho, gam);
     const double P = S * rg1;
     os.P = P;
     os.rg0 = fast_rcp(rg1);                                        // rho^(1-gam)
@@ -249,15 +264,7 @@ W5_HD void face_coefficients(double rhoL, double rhoR, double v1L, double v1R, d
 // characteristic projection of one 7-vector x = [rho,M1,M2,M3,B2,B3,E]-shaped quantity
 W5_HD void project(const FaceCoef &c, const double x[7], double w[7])
 {
-#ifdef W5_TREE_N
-    // experiment: three short chains instead of one 6-deep chain (+2 operations)
-    const double n1 = fma(c.vy, x[2], c.vx * x[1]);
-    const double n2 = fma(c.By, x[4], c.vz * x[3]);
-    const double n3 = fma(c.Bz, x[5], fma(-c.hv2, x[0], -x[6]));
-    const double n = (n1 + n2) + n3;
-#else
     const double n = fma(c.vx, x[1], fma(c.vy, x[2], fma(c.vz, x[3], fma(c.By, x[4], fma(c.Bz, x[5], fma(-c.hv2, x[0], -x[6]))))));
-#endif
     const double t = fma(c.bty, x[4], c.btz * x[5]);
     const double u = fma(c.bty, x[2], c.btz * x[3]);
     const double pf = fma(c.kf_n, n, c.kf_t * t);
@@ -327,7 +334,7 @@ W5_HD void face_coefficients_S(double rhoL, double rhoR, double rg0L, double rg0
     const double rinv = fast_rsqrt(rho);
     const double r = rho * rinv;
     const double ri = rinv * rinv;
-    const double S = pg / pow(rho, gam - 1.0);
+    const double S = pg / pow_gm1(rho, gam);
     const double Bt2 = By * By + Bz * Bz;
     const double B2 = Bx * Bx + Bt2;
     const double bbn2 = B2 * ri;
@@ -599,14 +606,14 @@ W5_HD double e2s(double rho, double m1, double m2, double m3, double b1, double 
 {
     const double mom2 = m1 * m1 + m2 * m2 + m3 * m3;
     const double BB = b1 * b1 + b2 * b2 + b3 * b3;
-    return (E - 0.5 * mom2 / rho - 0.5 * BB) * (gam - 1.0) / pow(rho, gam - 1.0);
+    return (E - 0.5 * mom2 / rho - 0.5 * BB) * (gam - 1.0) / pow_gm1(rho, gam);
 }
 
 W5_HD double s2e(double rho, double m1, double m2, double m3, double b1, double b2, double b3, double S, double gam)
 {
     const double mom2 = m1 * m1 + m2 * m2 + m3 * m3;
     const double BB = b1 * b1 + b2 * b2 + b3 * b3;
-    return pow(rho, gam - 1.0) * S / (gam - 1.0) + 0.5 * BB + 0.5 * mom2 / rho;
+    return pow_gm1(rho, gam) * S / (gam - 1.0) + 0.5 * BB + 0.5 * mom2 / rho;
 }
 
 // E2S followed by S2E on the same cell (the residue of ES_Switch, Weno5_2D.jl:1738 and :1765): the two
@@ -617,7 +624,7 @@ W5_HD void e2s_s2e(double rho, double m1, double m2, double m3, double b1, doubl
 {
     const double mom2 = m1 * m1 + m2 * m2 + m3 * m3;
     const double BB = b1 * b1 + b2 * b2 + b3 * b3;
-    const double pr = pow(rho, gam - 1.0);
+    const double pr = pow_gm1(rho, gam);
     const double kin = 0.5 * mom2 / rho;
     S = (E - kin - 0.5 * BB) * (gam - 1.0) / pr;
     E2 = pr * S / (gam - 1.0) + 0.5 * BB + kin;
