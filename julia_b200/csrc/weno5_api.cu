@@ -209,14 +209,6 @@ static void choose_segments(int nfaces, int NS, int strips, int &seg_len, int &n
     if (per > chunks) per = chunks;
     seg_len = per * NS;
     nseg = (nfaces + seg_len - 1) / seg_len;
-    // development knob: force the number of segments per line (scripts/wave_sweep.sh)
-    static const int force = getenv("WENO5_NSEG") ? atoi(getenv("WENO5_NSEG")) : 0;
-    static const int force_dir = getenv("WENO5_NSEG_STRIPS") ? atoi(getenv("WENO5_NSEG_STRIPS")) : 0;
-    if (force > 0 && (force_dir == 0 || force_dir == strips)) {
-        per = (chunks + force - 1) / force;
-        seg_len = per * NS;
-        nseg = (nfaces + seg_len - 1) / seg_len;
-    }
 }
 
 extern "C" const char *weno5_last_error(void) { return g_err; }
