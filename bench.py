@@ -126,8 +126,19 @@ def cpu_baseline(budget_s=15.0):
     n = int(max(256, min(2048, (rate * budget_s / 2) ** 0.5 // 64 * 64)))
     steps = int(max(2, min(12, round(budget_s * rate / (n * n)))))
     rate, secs = oracle_rate(n, steps)
-    return {"value": rate, "unit": "cell-updates/s", "cores": O.num_threads(True), "kind": "port",
-            "sample": f"orszag_tang {n}x{n}, {steps} RK4 steps incl. timestep, C oracle -O3 OpenMP, {secs:.1f} s"}
+    out = {"value": rate, "unit": "cell-updates/s", "cores": O.num_threads(True), "kind": "port",
+           "host_cpus": os.cpu_count(),
+           "sample": f"orszag_tang {n}x{n}, {steps} RK4 steps incl. timestep, C oracle -O3 OpenMP, {secs:.1f} s"}
+    # the same port on ONE host thread (the reference itself is single-threaded)
+    try:
+        gomp = C.CDLL("libgomp.so.1")
+        gomp.omp_set_num_threads(1)
+        r1, s1 = oracle_rate(512, 1)
+        gomp.omp_set_num_threads(int(out["cores"]))
+        out["single_thread"] = {"value": r1, "unit": "cell-updates/s", "sample": f"orszag_tang 512x512, 1 RK4 step, {s1:.1f} s"}
+    except OSError:
+        pass
+    return out
 
 
 def run_reference(args):

@@ -15,7 +15,7 @@
 # same entry points and is what the test-suite drives.
 module Weno5GPU
 
-export Weno5Params, Solver, upload!, download, boundaries!, timestep, classical_RK4_step, set_es_switch!, es_switch_count,
+export Weno5Params, Solver, upload!, download, boundaries!, timestep, classical_RK4_step, set_es_switch!, es_switch_count, arr2img,
        classical_RK4_step!, advance!, compute_divB, compute_global_vmax, interpolateB_center2face,
        state2conserved, WENO5_2D, WENO5_1D, Pipe, pipe_step!
 
@@ -124,6 +124,20 @@ function es_switch_count(s::Solver)
     n = Ref{Culonglong}(0)
     check(ccall((:weno5_es_switch_count, libweno5), Cint, (Ptr{Cvoid}, Ref{Culonglong}), s.h, n))
     return Int(n[])
+end
+
+"""
+Arr2Img(q[:,:,component+1], cmap; range, log) (JColorMaps.jl:92) evaluated on the resident state: the colour
+indices come from the GPU, the lookup `cmap[rimg]` happens here.  component 0..8 = q's components in the
+reference's order, 9 = bxb, 10 = byb, 11 = compute_divB.  Returns (img, (lo, hi)).
+"""
+function arr2img(s::Solver, component::Integer, cmap::AbstractVector; range=(0.0, 0.0), log::Bool=false)
+    nx, ny = dims(s)
+    rimg = Array{Int16}(undef, ny, nx)
+    rng = zeros(2)
+    check(ccall((:weno5_arr2img, libweno5), Cint, (Ptr{Cvoid}, Cint, Cdouble, Cdouble, Cint, Cint, Ptr{Int16}, Ptr{Float64}),
+                s.h, component, range[1], range[2], log ? 1 : 0, length(cmap), rimg, rng))
+    return cmap[rimg], (rng[1], rng[2])
 end
 
 "The driver loop of WENO5_2D()/WENO5_1D() kept on the device; returns (t, steps_done)."
