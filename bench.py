@@ -142,8 +142,9 @@ def cpu_baseline(budget_s=15.0):
 
 
 def run_reference(args):
-    """The reference's own CPU implementation cannot run (Julia 0.6 source, no julia binary): this
-    arm times the oracle port of it on all host cores, on a bounded sample of the workload."""
+    """The reference's own CPU implementation cannot run natively (Julia 0.6 source, no julia binary): this
+    arm times the oracle port of it (bit-identical numerics, tests/test_reference_pin.py) on all host cores, on a
+    bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -170,8 +171,10 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "reference Julia solver is not runnable here (Julia 0.6 syntax, no julia); this is the C oracle "
-                "port of its E-branch numerics, OpenMP over lines, all host threads",
+        "note": "no julia binary exists here (Julia 0.6 source); the reference only runs through the mechanical "
+                "translation used for the golden vectors (scripts/make_reference_golden.py, ~1e4x slower than native "
+                "Julia, not a meaningful timing).  Timed instead: the C port of its E-branch numerics, which "
+                "tests/test_reference_pin.py shows to be bit-identical to it, OpenMP over lines, all host threads",
     }
     print(json.dumps(line), flush=True)
 
