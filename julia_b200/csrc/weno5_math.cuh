@@ -554,9 +554,9 @@ W5_HD void face_flux_diff(const FaceCoef &c, const double amax[7], double eps, L
 {
     double P[4][7];
     double Fa[7], qa[7], comb[7];
+    const double epsq = 0.25 * eps;
     load(0, Fa, qa);
-#pragma unroll
-    for (int k = 1; k < 6; ++k) {
+    auto kstep = [&](const int k) {
         double Fb[7], qb[7], dF[7], dq[7], dw[7], dv[7];
         load(k, Fb, qb);
 #pragma unroll
@@ -577,15 +577,18 @@ W5_HD void face_flux_diff(const FaceCoef &c, const double amax[7], double eps, L
             if (k <= 4) P[k - 1][m] = fma(amax[m], dv[m], dw[m]);
             if (k >= 2) stash.put_q(k - 2, m, fma(-amax[m], dv[m], dw[m]));
         }
-    }
+    };
+    kstep(1); kstep(2); kstep(3); kstep(4);
+    kstep(5);
+    double second2[7];
+#pragma unroll
+    for (int m = 0; m < 7; ++m) second2[m] = weno_phi2(P[0][m], P[1][m], P[2][m], P[3][m], epsq);
     double first[7];
     project_br<BR>(c, comb, first);
-    const double epsq = 0.25 * eps;
 #pragma unroll
     for (int m = 0; m < 7; ++m) {
-        const double second2 = weno_phi2(P[0][m], P[1][m], P[2][m], P[3][m], epsq);
         const double third2 = weno_phi2(stash.get_q(3, m), stash.get_q(2, m), stash.get_q(1, m), stash.get_q(0, m), epsq);
-        Fs[m] = fma(first[m], 1.0 / 12.0, 0.5 * (third2 - second2));
+        Fs[m] = fma(first[m], 1.0 / 12.0, 0.5 * (third2 - second2[m]));
     }
 }
 
