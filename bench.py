@@ -291,7 +291,7 @@ def run_gpu(args):
 
     nx, nyl = args.nx, args.ny
     gglob = pr.Grid(nx=nx, ny=nyl * world, xsize=1.0, ysize=float(world) * nyl / nx, bc_x=pr.PERIODIC, bc_y=pr.PERIODIC)
-    gs, q, bx, by = pr.orszag_tang(nx, ny=nyl, ysize=float(nyl) / nx, y0=float(rank) * nyl / nx)
+    gs, q, bx, by = getattr(pr, args.problem)(nx, ny=nyl, ysize=float(nyl) / nx, y0=float(rank) * nyl / nx)
     s = Solver(gglob, device=local, ny_local=nyl, j_offset=rank * nyl, es_roundtrip=bool(args.es_roundtrip))
     if world > 1:
         uid = pt.broadcast_unique_id(Solver.comm_unique_id, rank, dist)
@@ -358,8 +358,8 @@ def run_gpu(args):
             "metric": "cell_updates_per_sec", "value": value, "unit": "cell-updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(world) if (nx, nyl) == (NX_PER_GPU, NY_PER_GPU) else
-            {"workload": f"orszag_tang {nx}x{nyl} per GPU (non-default size)", "nx": nx, "ny_global": nyl * world},
+            "config": workload_config(world) if (nx, nyl, args.problem) == (NX_PER_GPU, NY_PER_GPU, "orszag_tang") else
+            {"workload": f"{args.problem} {nx}x{nyl} per GPU (non-default workload)", "nx": nx, "ny_global": nyl * world},
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": int(launches),
@@ -393,6 +393,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nx", type=int, default=NX_PER_GPU)
     ap.add_argument("--ny", type=int, default=NY_PER_GPU, help="rows per GPU")
+    ap.add_argument("--problem", default="orszag_tang", choices=["orszag_tang", "blast"],
+                    help="synthetic workload (BASELINE configs 3/4: orszag_tang, config 5: blast)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--es-roundtrip", type=int, default=1, help="1: E <- S2E(E2S(E)) after every stage (2-D reference form)")

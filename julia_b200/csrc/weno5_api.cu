@@ -376,6 +376,7 @@ extern "C" int weno5_comm_init(weno5_ctx *c, int rank, int nranks, const unsigne
     if (!c || !id) return fail(WENO5_ERR_ARG, "null argument");
     if (c->g.is1d) return fail(WENO5_ERR_ARG, "1-D grids cannot be decomposed");
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail(WENO5_ERR_ARG, "bad rank %d of %d", rank, nranks);
+    if (c->dual) return fail(WENO5_ERR_ARG, "the dual-energy switch runs on undivided grids (one GPU)");
     if (int r = nccl_load()) return r;
     CU(cudaSetDevice(c->device));
     ncclUniqueId u;
