@@ -397,6 +397,23 @@ def test_gpu_dual_energy_vs_reference(cuda):
 
 
 @gpu
+def test_gpu_dual_energy_reference_problem(cuda):
+    """The reference's own shock-cloud problem (16 x 4, outflow boundaries!) with the switching criterion restored:
+    one step against the reference's output; Q3-limited like the E-only step."""
+    d = golden("ref2d_dual_shockcloud")
+    g = grid_of(d, pr.OUTFLOW)
+    with cuda.Solver(g, es_roundtrip=True) as s:
+        s.set_es_switch(True, 1e-5)
+        s.upload(d["q0"], d["bxb0"], d["byb0"])
+        s.rk4_step(float(d["dt"][0]))
+        q, bx, by = s.download()
+        nsw = s.es_switch_count()
+    err = group_err(q[3:-3, 3:-3], d["q1"][3:-3, 3:-3])
+    assert max(err.values()) <= 1e-8, err
+    assert 0 < nsw <= g.nx * g.ny
+
+
+@gpu
 def test_gpu_dual_energy_vs_oracle_and_limits(cuda):
     """48^2 blast, 3 steps against the numpy oracle; threshold 0 switches every cell to the E state, which is the
     shipped E-only step; a huge threshold keeps the S state everywhere (entropy is advected, E derived)."""
