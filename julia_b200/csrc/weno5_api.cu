@@ -615,7 +615,7 @@ static int enqueue_stage(weno5_ctx *c, int stage, State &cur, State &nxt)
     a.c_dx = ck[stage - 1] / P.dx;
     a.c_dy = g.is1d ? 0.0 : ck[stage - 1] / P.dy;
     a.stage = stage;
-    a.gam = P.gamma; a.eps = P.eps;
+    a.gam = P.gamma; a.eps = P.eps; a.g2 = (P.gamma - 2.0) / (P.gamma - 1.0);
     a.is1d = g.is1d;
     a.pitch = g.pitch;
     a.tmap_x = c->have_tmap ? c->tmap_x : nullptr;
@@ -738,7 +738,7 @@ static int enqueue_stage_dual(weno5_ctx *c, int stage, State &cur, State &nxt)
         a.c_dx = ck[stage - 1] / P.dx;
         a.c_dy = ck[stage - 1] / P.dy;
         a.stage = stage;
-        a.gam = P.gamma; a.eps = P.eps;
+        a.gam = P.gamma; a.eps = P.eps; a.g2 = (P.gamma - 2.0) / (P.gamma - 1.0);
         a.pitch = g.pitch;
         a.branch = br;
         const bool tma = br == 0 && c->have_tmap;

@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a, const 
                                   cb[CQ_V2 * CBS + iL], cb[CQ_V2 * CBS + iR], cb[CQ_V3 * CBS + iL], cb[CQ_V3 * CBS + iR],
                                   cb[CQ_B1 * CBS + iL], cb[CQ_B1 * CBS + iR], cb[(CQ_Q0 + 4) * CBS + iL],
                                   cb[(CQ_Q0 + 4) * CBS + iR], cb[(CQ_Q0 + 5) * CBS + iL], cb[(CQ_Q0 + 5) * CBS + iR],
-                                  cb[(CQ_Q0 + 6) * CBS + iL], cb[(CQ_Q0 + 6) * CBS + iR], a.gam, fc);
+                                  cb[(CQ_Q0 + 6) * CBS + iL], cb[(CQ_Q0 + 6) * CBS + iR], a.gam, a.g2, fc);
             else
                 face_coefficients_S(cb[CQ_Q0 * CBS + iL], cb[CQ_Q0 * CBS + iR], cb[CQ_RG0 * CBS + iL], cb[CQ_RG0 * CBS + iR],
                                     cb[CQ_V1 * CBS + iL], cb[CQ_V1 * CBS + iR], cb[CQ_V2 * CBS + iL], cb[CQ_V2 * CBS + iR],

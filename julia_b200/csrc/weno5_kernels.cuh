@@ -41,6 +41,7 @@ struct FluxArgs {
     int N, NP, pitch;        // cells along the sweep, lines across it
     int seg_len, nseg;       // faces per segment, segments per line
     double gam, eps;
+    double g2;               // (gam-2)/(gam-1), a constant of the run (face_coefficients)
     int is1d;
     int row_mode;            // x sweep: 0 all rows, 1 interior rows only, 2 ghost rows only (halo-exchange overlap)
     int branch;              // 0: E branch (qc[7] = E), 1: S branch (qc[7] = S; weno5_flux_difference_S, Weno5_2D.jl:361)

@@ -196,11 +196,13 @@ struct FaceCoef {
 // coefficient groups of L (:1368-1426, scaling :1490-1502) and R (:1428-1486).
 // The sgnBt flip (:1506-1528) multiplies row m of L and column m of R by the same +-1 and
 // WENO is odd in its inputs, so it cancels exactly and is not applied.
+// g2 = (gam-2)/(gam-1) is passed in: it is a constant of the run, and computed here it costs an IEEE division
+// (with its slow-path call) once per march step in the kernel's loop.
 W5_HD void face_coefficients(double rhoL, double rhoR, double v1L, double v1R, double v2L, double v2R,
                              double v3L, double v3R, double B1L, double B1R, double B2L, double B2R,
-                             double B3L, double B3R, double EL, double ER, double gam, FaceCoef &c)
+                             double B3L, double B3R, double EL, double ER, double gam, double g2, FaceCoef &c)
 {
-    const double g0 = 1.0 - gam, g2 = (gam - 2.0) / (gam - 1.0);
+    const double g0 = 1.0 - gam;
     const double rho = 0.5 * (rhoL + rhoR);
     const double vx = 0.5 * (v1L + v1R), vy = 0.5 * (v2L + v2R), vz = 0.5 * (v3L + v3R);
     const double Bx = 0.5 * (B1L + B1R), By = 0.5 * (B2L + B2R), Bz = 0.5 * (B3L + B3R);

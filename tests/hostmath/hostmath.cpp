@@ -47,7 +47,7 @@ static int sweep_t(int Nx, int Ny, const double *q, int dir, int bc, double gam,
             if (BR == 0)
                 w5::face_coefficients(L[w5::CQ_Q0], R[w5::CQ_Q0], L[w5::CQ_V1], R[w5::CQ_V1], L[w5::CQ_V2], R[w5::CQ_V2],
                                       L[w5::CQ_V3], R[w5::CQ_V3], L[w5::CQ_B1], R[w5::CQ_B1], L[w5::CQ_Q0 + 4], R[w5::CQ_Q0 + 4],
-                                      L[w5::CQ_Q0 + 5], R[w5::CQ_Q0 + 5], L[w5::CQ_Q0 + 6], R[w5::CQ_Q0 + 6], gam, c);
+                                      L[w5::CQ_Q0 + 5], R[w5::CQ_Q0 + 5], L[w5::CQ_Q0 + 6], R[w5::CQ_Q0 + 6], gam, (gam - 2.0) / (gam - 1.0), c);
             else
                 w5::face_coefficients_S(L[w5::CQ_Q0], R[w5::CQ_Q0], L[CQ_RG0], R[CQ_RG0], L[w5::CQ_V1], R[w5::CQ_V1],
                                         L[w5::CQ_V2], R[w5::CQ_V2], L[w5::CQ_V3], R[w5::CQ_V3], L[w5::CQ_B1], R[w5::CQ_B1],
