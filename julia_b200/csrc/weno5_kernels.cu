@@ -899,7 +899,7 @@ __global__ void vmax_kernel(const VmaxArgs a)
         const double rooty = fast_sqrt(fmax(0.0, sm * sm - 4 * bny2 * cs2));
         vxm = fabs(vx) + fast_sqrt(0.5 * (sm + rootx));
         vym = fabs(vy) + fast_sqrt(0.5 * (sm + rooty));
-        if (sm != sm) { vxm = sm; vym = sm; }          // fast_sqrt maps NaN to 0: keep the NaN visible
+        if (sm != sm) { vxm = sm; vym = sm; }          // keep a NaN visible whatever the clamps above did
     }
     unsigned long long bx_ = (unsigned long long)__double_as_longlong(vxm);
     unsigned long long by_ = (unsigned long long)__double_as_longlong(vym);

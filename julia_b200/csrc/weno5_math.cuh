@@ -75,7 +75,7 @@ W5_HD double fast_rsqrt(double x)
 #endif
 }
 
-// sqrt(x) for x >= 0 (0 and denormals give 0), branch-free: one Newton step on the rsqrt seed
+// sqrt(x) for x >= 0 (0 gives 0), branch-free: one Newton step on the rsqrt seed
 // (1.3e-12) and one correction step s + (x - s^2) y/2 on the product, which squares that error.
 W5_HD double fast_sqrt(double x)
 {
@@ -85,10 +85,12 @@ W5_HD double fast_sqrt(double x)
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(xs));
     const double e = fma(-(0.5 * xs * y), y, 0.5);
     y = fma(y, e, y);
-    double s = xs * y;
-    const double d = fma(-s, s, xs);
+    // the product takes x itself, not the clamped value: x = 0 gives 0 * y = 0 without a final select (and a NaN
+    // stays a NaN); for x >= 1e-300 nothing changes
+    double s = x * y;
+    const double d = fma(-s, s, x);
     s = fma(d, 0.5 * y, s);
-    return x > 1e-300 ? s : 0.0;
+    return s;
 #else
     return sqrt(x);
 #endif
