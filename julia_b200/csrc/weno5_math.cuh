@@ -57,6 +57,19 @@ W5_HD double fast_rcp(double x)
 #endif
 }
 
+// max(0, x) on the integer pipe (sign bit -> all-zero mask): the FP64 form costs a DSETP on the FP64 pipe, which is
+// the binding resource of the flux kernel, plus two selects.  NaN stays NaN (Julia's max propagates it too), -0 -> +0.
+W5_HD double relu64(double x)
+{
+#if defined(__CUDA_ARCH__)
+    const int hi = __double2hiint(x), lo = __double2loint(x);
+    const int m = ~(hi >> 31);
+    return __hiloint2double(hi & m, lo & m);
+#else
+    return x > 0.0 ? x : (x != x ? x : 0.0);
+#endif
+}
+
 // 1/sqrt(x) for normal x > 0, branch-free: hardware seed + two Newton steps (e -> 1.5 e^2;
 // measured 2.7e-16).
 W5_HD double fast_rsqrt(double x)
@@ -80,7 +93,7 @@ W5_HD double fast_rsqrt(double x)
 W5_HD double fast_sqrt(double x)
 {
 #if defined(__CUDA_ARCH__)
-    const double xs = fmax(x, 1e-300);
+    const double xs = x + 1e-300;                 // = x for every normal x of interest, keeps rsqrt(0) finite
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(xs));
     const double e = fma(-(0.5 * xs * y), y, 0.5);
@@ -122,13 +135,13 @@ W5_HD void cell_quantities(const double q[8], double gam, CellOut &o)
     const double vv = v1 * v1 + v2 * v2 + v3 * v3;
     const double BB = B1 * B1 + B2 * B2 + B3 * B3;
     const double P = (gam - 1.0) * (E - 0.5 * (rho * vv + BB));
-    const double cs2 = fmax(0.0, gam * fabs(P * ri));
-    const double bnx2 = fmax(0.0, B1 * B1 * ri);
+    const double cs2 = gam * fabs(P * ri);                       // max(0, .) of Weno5_2D.jl:1619 is a no-op on |.|
+    const double bnx2 = relu64(B1 * B1 * ri);
     const double bbn2 = BB * ri;
     const double s = bbn2 + cs2;
-    const double root = fast_sqrt(fmax(0.0, s * s - 4.0 * bnx2 * cs2));
-    o.lf = fast_sqrt(fmax(0.0, 0.5 * (s + root)));
-    o.ls = fast_sqrt(fmax(0.0, 0.5 * (s - root)));
+    const double root = fast_sqrt(relu64(s * s - 4.0 * bnx2 * cs2));
+    o.lf = fast_sqrt(0.5 * (s + root));                          // s, root >= 0
+    o.ls = fast_sqrt(relu64(0.5 * (s - root)));
     o.la = fast_sqrt(bnx2);
     o.v1 = v1; o.v2 = v2; o.v3 = v3;
     const double pt = P + 0.5 * BB;
@@ -157,13 +170,13 @@ W5_HD void cell_quantities_S(const double q[8], double gam, CellOut &o, CellOutS
     const double P = S * rg1;
     os.P = P;
     os.rg0 = fast_rcp(rg1);                                        // rho^(1-gam)
-    const double cs2 = fmax(0.0, gam * fabs(P * ri));
-    const double bnx2 = fmax(0.0, B1 * B1 * ri);
+    const double cs2 = gam * fabs(P * ri);                       // max(0, .) of Weno5_2D.jl:1619 is a no-op on |.|
+    const double bnx2 = relu64(B1 * B1 * ri);
     const double bbn2 = BB * ri;
     const double s = bbn2 + cs2;
-    const double root = fast_sqrt(fmax(0.0, s * s - 4.0 * bnx2 * cs2));
-    o.lf = fast_sqrt(fmax(0.0, 0.5 * (s + root)));
-    o.ls = fast_sqrt(fmax(0.0, 0.5 * (s - root)));
+    const double root = fast_sqrt(relu64(s * s - 4.0 * bnx2 * cs2));
+    o.lf = fast_sqrt(0.5 * (s + root));                          // s, root >= 0
+    o.ls = fast_sqrt(relu64(0.5 * (s - root)));
     o.la = fast_sqrt(bnx2);
     o.v1 = v1; o.v2 = v2; o.v3 = v3;
     const double pt = P + 0.5 * BB;
@@ -217,13 +230,13 @@ W5_HD void face_coefficients(double rhoL, double rhoR, double v1L, double v1R, d
     const double v2 = vx * vx + vy * vy + vz * vz;
     const double pg = (gam - 1.0) * (E - 0.5 * (rho * v2 + B2));
     const double bbn2 = B2 * ri;
-    const double cs2 = fmax(0.0, gam * fabs(pg * ri));
+    const double cs2 = gam * fabs(pg * ri);                      // max(0, .) of Weno5_2D.jl:1310 is a no-op on |.|
     const double bnx2 = Bx * Bx * ri;
     const double a = fast_sqrt(cs2);
     const double s_ = bbn2 + cs2;
-    const double root = fast_sqrt(fmax(0.0, s_ * s_ - 4.0 * bnx2 * cs2));
-    const double cf = fast_sqrt(fmax(0.0, 0.5 * (s_ + root)));
-    const double cs = fast_sqrt(fmax(0.0, 0.5 * (s_ - root)));
+    const double root = fast_sqrt(relu64(s_ * s_ - 4.0 * bnx2 * cs2));
+    const double cf = fast_sqrt(0.5 * (s_ + root));                // s_, root >= 0
+    const double cs = fast_sqrt(relu64(0.5 * (s_ - root)));
     const double sg = (Bx < 0.0) ? -1.0 : 1.0;                    // sign(Bx), 0 -> 1
     // degenerate cases are resolved with selects, not branches (Weno5_2D.jl:1337-1359)
     const bool tang = Bt2 > 1e-30;
@@ -233,8 +246,8 @@ W5_HD void face_coefficients(double rhoL, double rhoR, double v1L, double v1R, d
     const double dl2 = cf * cf - cs * cs;
     const bool split = dl2 >= 1e-30;
     const double id = fast_rcp(split ? dl2 : 1.0);
-    const double af = split ? fast_sqrt(fmax(0.0, cs2 - cs * cs) * id) : 1.0;
-    const double as_ = split ? fast_sqrt(fmax(0.0, cf * cf - cs2) * id) : 1.0;
+    const double af = split ? fast_sqrt(relu64(cs2 - cs * cs) * id) : 1.0;
+    const double as_ = split ? fast_sqrt(relu64(cf * cf - cs2) * id) : 1.0;
     const double sig = bty * vy + btz * vz;
     const double ih = 0.5 * fast_rcp(cs2);                         // 1/(2 a^2)
     const double afcf = af * cf, ascs = as_ * cs;
@@ -342,13 +355,13 @@ W5_HD void face_coefficients_S(double rhoL, double rhoR, double rg0L, double rg0
     const double Bt2 = By * By + Bz * Bz;
     const double B2 = Bx * Bx + Bt2;
     const double bbn2 = B2 * ri;
-    const double cs2 = fmax(0.0, gam * fabs(pg * ri));
+    const double cs2 = gam * fabs(pg * ri);                      // max(0, .) of Weno5_2D.jl:1310 is a no-op on |.|
     const double bnx2 = Bx * Bx * ri;
     const double a = fast_sqrt(cs2);
     const double s_ = bbn2 + cs2;
-    const double root = fast_sqrt(fmax(0.0, s_ * s_ - 4.0 * bnx2 * cs2));
-    const double cf = fast_sqrt(fmax(0.0, 0.5 * (s_ + root)));
-    const double cs = fast_sqrt(fmax(0.0, 0.5 * (s_ - root)));
+    const double root = fast_sqrt(relu64(s_ * s_ - 4.0 * bnx2 * cs2));
+    const double cf = fast_sqrt(0.5 * (s_ + root));                // s_, root >= 0
+    const double cs = fast_sqrt(relu64(0.5 * (s_ - root)));
     const double sg = (Bx < 0.0) ? -1.0 : 1.0;
     const bool tang = Bt2 > 1e-30;
     const double ib = fast_rsqrt(tang ? Bt2 : 1.0);
@@ -357,8 +370,8 @@ W5_HD void face_coefficients_S(double rhoL, double rhoR, double rg0L, double rg0
     const double dl2 = cf * cf - cs * cs;
     const bool split = dl2 >= 1e-30;
     const double id = fast_rcp(split ? dl2 : 1.0);
-    const double af = split ? fast_sqrt(fmax(0.0, cs2 - cs * cs) * id) : 1.0;
-    const double as_ = split ? fast_sqrt(fmax(0.0, cf * cf - cs2) * id) : 1.0;
+    const double af = split ? fast_sqrt(relu64(cs2 - cs * cs) * id) : 1.0;
+    const double as_ = split ? fast_sqrt(relu64(cf * cf - cs2) * id) : 1.0;
     const double sig = bty * vy + btz * vz;
     const double ih = 0.5 * fast_rcp(cs2);
     const double afcf = af * cf, ascs = as_ * cs;
