@@ -609,16 +609,28 @@ W5_HD void face_flux_diff(const FaceCoef &c, const double amax[7], double eps, L
     }
 }
 
+// max(|a|, |b|): non-negative doubles order like their bit patterns, so the maximum is an integer compare off the
+// FP64 pipe (a NaN has the largest pattern and survives, like Julia's max)
+W5_HD double absmax(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+    const long long x = __double_as_longlong(fabs(a)), y = __double_as_longlong(fabs(b));
+    return __longlong_as_double(x > y ? x : y);
+#else
+    return fmax(fabs(a), fabs(b));
+#endif
+}
+
 W5_HD void face_amax(double v1L, double lfL, double laL, double lsL,
                      double v1R, double lfR, double laR, double lsR, double amax[7])
 {
-    amax[0] = fmax(fabs(v1L - lfL), fabs(v1R - lfR));
-    amax[1] = fmax(fabs(v1L - laL), fabs(v1R - laR));
-    amax[2] = fmax(fabs(v1L - lsL), fabs(v1R - lsR));
-    amax[3] = fmax(fabs(v1L), fabs(v1R));
-    amax[4] = fmax(fabs(v1L + lsL), fabs(v1R + lsR));
-    amax[5] = fmax(fabs(v1L + laL), fabs(v1R + laR));
-    amax[6] = fmax(fabs(v1L + lfL), fabs(v1R + lfR));
+    amax[0] = absmax(v1L - lfL, v1R - lfR);
+    amax[1] = absmax(v1L - laL, v1R - laR);
+    amax[2] = absmax(v1L - lsL, v1R - lsR);
+    amax[3] = absmax(v1L, v1R);
+    amax[4] = absmax(v1L + lsL, v1R + lsR);
+    amax[5] = absmax(v1L + laL, v1R + laR);
+    amax[6] = absmax(v1L + lfL, v1R + lfR);
 }
 
 // Weno5_2D.jl:1770-1793
