@@ -457,31 +457,30 @@ W5_HD void back_project_S(const BackCoefS &c, const double Fs[7], double fh[7])
 }
 
 // One side of the Jiang & Wu correction (Weno5_2D.jl:1836-1853) for UNHALVED inputs
-// A = 2a, B = 2b, ...; returns 2 phi.
+// A = 2a, B = 2b, ...; returns 6 phi (the factor is undone where the two sides are combined).
 //  * smoothness indicators as quadratic forms, scaled by 1/16:
 //      IS0 = 13(a-b)^2 + 3(a-3b)^2 = 16 a^2 - 44 ab + 40 b^2   ->  A(A - 2.75 B) + 2.5 B^2
 //      IS1 = 13(b-c)^2 + 3(b+c)^2  = 16 b^2 - 20 bc + 16 c^2   ->  B(B - 1.25 C) + C^2
 //      IS2 = 13(c-d)^2 + 3(3c-d)^2 = 40 c^2 - 44 cd + 16 d^2   ->  D(D - 2.75 C) + 2.5 C^2
-//    (10 operations instead of 18).  With unhalved inputs these are IS_k/4, so eps is passed as
+//    (10 operations instead of 18; with eps folded in, 11 for the three eps + IS_k instead of 13).  With unhalved inputs these are IS_k/4, so eps is passed as
 //    eps/4 and the weight ratios are unchanged.
 //  * omega0 = al0/(al0+al1+al2), al = (1,6,3)/d_k, d_k = (eps+IS_k)^2, written over the common
 //    denominator so that a single reciprocal replaces five divisions.
 // Algebraically identical to the reference; differs in round-off only.
-W5_HD double weno_phi2(double A, double B, double C, double D, double epsq)
+W5_HD double weno_phi6(double A, double B, double C, double D, double epsq)
 {
     const double BB = B * B, CC = C * C;
-    const double IS0 = fma(A, fma(-2.75, B, A), 2.5 * BB);
-    const double IS1 = fma(B, fma(-1.25, C, B), CC);
-    const double IS2 = fma(D, fma(-2.75, C, D), 2.5 * CC);
-    double d0 = epsq + IS0, d1 = epsq + IS1, d2 = epsq + IS2;
+    // eps + IS_k with eps folded into the constant term of each quadratic form (one operation less per indicator)
+    double d0 = fma(A, fma(-2.75, B, A), fma(2.5, BB, epsq));
+    double d1 = fma(B, fma(-1.25, C, B), CC + epsq);
+    double d2 = fma(D, fma(-2.75, C, D), fma(2.5, CC, epsq));
     d0 *= d0; d1 *= d1; d2 *= d2;
     const double p12 = d1 * d2, p02 = d0 * d2, p01 = d0 * d1;
     const double inv = fast_rcp(fma(6.0, p02, fma(3.0, p01, p12)));
-    const double om0_3 = p12 * inv * (1.0 / 3.0);                   // omega0 / 3
-    const double om2_6 = fma(p01 * inv, 0.5, -1.0 / 12.0);          // (omega2 - 1/2) / 6
     const double D1 = fma(-2.0, B, A) + C;
     const double D2 = fma(-2.0, C, B) + D;
-    return fma(om0_3, D1, om2_6 * D2);
+    // 6 phi = omega0 D1 + (omega2 - 1/2) D2 / 2 with omega0 = p12 inv, omega2 = 3 p01 inv, over the common reciprocal
+    return fma(fma(1.5, p01 * D2, p12 * D1), inv, -0.25 * D2);
 }
 
 // No-op stash: everything stays in registers (host tests, and the reference point for the
@@ -555,9 +554,9 @@ W5_HD void face_flux_br(const FaceCoef &c, const double amax[7], double eps, Loa
     const double epsq = 0.25 * eps;
 #pragma unroll
     for (int m = 0; m < 7; ++m) {
-        const double second2 = weno_phi2(P[0][m], P[1][m], P[2][m], P[3][m], epsq);
-        const double third2 = weno_phi2(stash.get_q(3, m), stash.get_q(2, m), stash.get_q(1, m), stash.get_q(0, m), epsq);
-        Fs[m] = fma(stash.get_first(m), 1.0 / 12.0, 0.5 * (third2 - second2));
+        const double second6 = weno_phi6(P[0][m], P[1][m], P[2][m], P[3][m], epsq);
+        const double third6 = weno_phi6(stash.get_q(3, m), stash.get_q(2, m), stash.get_q(1, m), stash.get_q(0, m), epsq);
+        Fs[m] = fma(stash.get_first(m), 1.0 / 12.0, (1.0 / 6.0) * (third6 - second6));
     }
 }
 
@@ -597,15 +596,15 @@ W5_HD void face_flux_diff(const FaceCoef &c, const double amax[7], double eps, L
     };
     kstep(1); kstep(2); kstep(3); kstep(4);
     kstep(5);
-    double second2[7];
+    double second6[7];
 #pragma unroll
-    for (int m = 0; m < 7; ++m) second2[m] = weno_phi2(P[0][m], P[1][m], P[2][m], P[3][m], epsq);
+    for (int m = 0; m < 7; ++m) second6[m] = weno_phi6(P[0][m], P[1][m], P[2][m], P[3][m], epsq);
     double first[7];
     project_br<BR>(c, comb, first);
 #pragma unroll
     for (int m = 0; m < 7; ++m) {
-        const double third2 = weno_phi2(stash.get_q(3, m), stash.get_q(2, m), stash.get_q(1, m), stash.get_q(0, m), epsq);
-        Fs[m] = fma(first[m], 1.0 / 12.0, 0.5 * (third2 - second2[m]));
+        const double third6 = weno_phi6(stash.get_q(3, m), stash.get_q(2, m), stash.get_q(1, m), stash.get_q(0, m), epsq);
+        Fs[m] = fma(first[m], 1.0 / 12.0, (1.0 / 6.0) * (third6 - second6[m]));
     }
 }
 
