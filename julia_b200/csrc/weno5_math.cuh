@@ -254,28 +254,31 @@ W5_HD void face_coefficients(double rhoL, double rhoR, double v1L, double v1R, d
 
     c.hv2 = 0.5 * v2; c.vx = vx; c.vy = vy; c.vz = vz; c.By = By; c.Bz = Bz;
     c.bty = bty; c.btz = btz;
-    c.kf_n = g0 * af * ih;
-    c.kf_t = a * as_ * r * ih;
-    c.kf_1 = (afcf * vx - ascs * sig * sg) * ih;
-    c.kf_2 = -afcf * ih;
-    c.kf_u = ascs * sg * ih;
-    c.ks_n = g0 * as_ * ih;
-    c.ks_t = -a * af * r * ih;
-    c.ks_1 = (ascs * vx + afcf * sig * sg) * ih;
-    c.ks_2 = -ascs * ih;
-    c.ks_u = -afcf * sg * ih;
-    c.ka_1 = 0.5 * (btz * vy - bty * vz);
+    // shared factors first: 28 multiplications for the 16 coefficients instead of 41
+    const double Fh = afcf * ih, Sh = ascs * ih;                   // af cf / 2a^2, as cs / 2a^2
+    const double sgsig = sg * sig, g0ih = g0 * ih, arh = a * r * ih, hsr = 0.5 * sg * r;
+    c.kf_n = g0ih * af;
+    c.kf_t = arh * as_;
+    c.kf_1 = fma(Fh, vx, -Sh * sgsig);
+    c.kf_2 = -Fh;
+    c.kf_u = Sh * sg;
+    c.ks_n = g0ih * as_;
+    c.ks_t = -arh * af;
+    c.ks_1 = fma(Sh, vx, Fh * sgsig);
+    c.ks_2 = -Sh;
+    c.ks_u = -Fh * sg;
+    c.axy = bty * vz - btz * vy;
+    c.ka_1 = -0.5 * c.axy;
     c.ka_3 = -0.5 * btz;
     c.ka_4 = 0.5 * bty;
-    c.kb_5 = -0.5 * sg * r * btz;
-    c.kb_6 = 0.5 * sg * r * bty;
-    c.ke_n = -2.0 * g0 * ih;
+    c.kb_5 = -hsr * btz;
+    c.kb_6 = hsr * bty;
+    c.ke_n = -2.0 * g0ih;
     c.af = af; c.as_ = as_; c.afcf = afcf; c.ascs = ascs;
     c.a_r = a * rinv; c.s_r = sg * rinv; c.sgn = sg; c.sig = sig;
     const double h = 0.5 * v2 - g2 * cs2;
     c.hf = af * (cf * cf + h);
     c.hs = as_ * (cs * cs + h);
-    c.axy = bty * vz - btz * vy;
 }
 
 // characteristic projection of one 7-vector x = [rho,M1,M2,M3,B2,B3,E]-shaped quantity
