@@ -45,6 +45,8 @@ def lib(fast=False):
         L.orc_sweep_2d.argtypes = [pp, dp, C.c_int, dp, dp]
         L.orc_rk4_step_1d.argtypes = [pp, dp, C.c_double, dp]
         L.orc_advance_2d.argtypes = [pp, dp, dp, dp, C.c_int, dp]
+        L.orc_sweep_2d_S.argtypes = [pp, dp, C.c_int, dp, dp]
+        L.orc_rk4_step_2d_dual.argtypes = [pp, dp, dp, dp, C.c_double, C.c_double, dp, dp, dp, C.POINTER(C.c_long)]
         L.orc_num_threads.restype = C.c_int
         _libs[key] = L
     return _libs[key]
@@ -124,6 +126,28 @@ def sweep_2d(g, q8, direction):
     P = params(g)
     lib().orc_sweep_2d(C.byref(P), _p(q8), int(direction), _p(dq), _p(bs))
     return dq, bs
+
+
+def sweep_2d_S(g, q8, direction):
+    """weno5_flux_difference_S (Weno5_2D.jl:361): q8 = (Nx,Ny,8) [rho,M,B,S] -> dq, fsy (dir 0) / gsx (dir 1)."""
+    q8 = _f(q8)
+    dq = np.zeros_like(q8, order="F")
+    bs = np.zeros(q8.shape[:2], order="F")
+    P = params(g)
+    lib().orc_sweep_2d_S(C.byref(P), _p(q8), int(direction), _p(dq), _p(bs))
+    return dq, bs
+
+
+def rk4_step_2d_dual(g, q, bxb, byb, dt, threshold=1e-5, fast=False):
+    """classical_RK4_step with both branches and the live ES_Switch.  Returns (q4, bxb4, byb4, nbad)."""
+    q, bxb, byb = _f(q), _f(bxb), _f(byb)
+    q4, bx4, by4 = np.zeros_like(q, order="F"), np.zeros_like(bxb, order="F"), np.zeros_like(byb, order="F")
+    nbad = (C.c_long * 4)()
+    P = params(g)
+    rc = lib(fast).orc_rk4_step_2d_dual(C.byref(P), _p(q), _p(bxb), _p(byb), float(dt), float(threshold),
+                                        _p(q4), _p(bx4), _p(by4), nbad)
+    assert rc == 0
+    return q4, bx4, by4, [int(x) for x in nbad]
 
 
 def rk4_step_1d(g, q, dt):

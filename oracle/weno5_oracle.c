@@ -1,8 +1,8 @@
 /*
  * TEST INFRASTRUCTURE ONLY -- CPU oracle for the WENO5 MHD hot path.
  *
- * A plain-C restatement of the E-branch algorithm of jdonnert/julia's Weno5_2D.jl /
- * Weno5_1D.jl (reference file:line cited at every function).  It is the checker for the
+ * A plain-C restatement of the algorithm of jdonnert/julia's Weno5_2D.jl /
+ * Weno5_1D.jl (E branch = the shipped behaviour; S branch and live ES_Switch = orc_rk4_step_2d_dual) (reference file:line cited at every function).  It is the checker for the
  * CUDA path (tests/, __graft_entry__.smoke()) and the timed CPU baseline of bench.py;
  * nothing in the product (julia_b200/, libweno5mhd.so) may call, link or load it.
  *
@@ -226,6 +226,121 @@ static void face_eigenvectors(const double uL[8], const double uR[8], double EL,
     }
 }
 
+/* ------------------------------------------------------------------ S branch
+ * The entropy-variable twins that the shipped classical_RK4_step evaluates and discards (ES_Switch has its
+ * criterion commented out); live in orc_rk4_step_2d_dual. */
+
+/* Weno5_2D.jl:953-969  q8 = [rho,M1,M2,M3,B1,B2,B3,S] -> u = [rho,v1,v2,v3,B1,B2,B3,P(S)] */
+static void cell_primitives_S(const double q[8], double gam, double u[8])
+{
+    u[0] = q[0];
+    u[1] = q[1] / q[0];
+    u[2] = q[2] / q[0];
+    u[3] = q[3] / q[0];
+    u[4] = q[4];
+    u[5] = q[5];
+    u[6] = q[6];
+    u[7] = q[7] * pow(q[0], gam - 1.0);
+}
+
+/* Weno5_2D.jl:927-950 */
+static void cell_fluxes_S(const double q[8], const double u[8], double F[7])
+{
+    double pt = u[7] + 0.5 * (u[4] * u[4] + u[5] * u[5] + u[6] * u[6]);
+    F[0] = u[0] * u[1];
+    F[1] = q[1] * u[1] + pt - u[4] * u[4];
+    F[2] = q[2] * u[1] - u[4] * u[5];
+    F[3] = q[3] * u[1] - u[4] * u[6];
+    F[4] = u[5] * u[1] - u[4] * u[2];
+    F[5] = u[6] * u[1] - u[4] * u[3];
+    F[6] = q[7] * u[1];
+}
+
+/* compute_eigenvectors_S_vec, Weno5_2D.jl:640-924.  L[m][c], R[c][m]; components [rho,M1,M2,M3,B2,B3,S]. */
+static void face_eigenvectors_S(const double uL[8], const double uR[8], double gam, double L[7][7], double R[7][7])
+{
+    const double g0 = 1.0 - gam, gS = (gam - 1.0) / gam;
+    double drho = fabs(uL[0] - uR[0]);
+    double rho = 0.5 * (uL[0] + uR[0]);
+    if (!(drho <= 1e-12)) rho = pow(fabs(g0 * drho / (pow(uR[0], g0) - pow(uL[0], g0))), 1.0 / gam);   /* :657-667 */
+    double r = sqrt(rho);
+    double vx = 0.5 * (uL[1] + uR[1]), vy = 0.5 * (uL[2] + uR[2]), vz = 0.5 * (uL[3] + uR[3]);
+    double Bx = 0.5 * (uL[4] + uR[4]), By = 0.5 * (uL[5] + uR[5]), Bz = 0.5 * (uL[6] + uR[6]);
+    double pg = 0.5 * (uL[7] + uR[7]);
+    double S = pg / pow(rho, gam - 1.0);
+    double B2 = Bx * Bx + By * By + Bz * Bz;
+    double bbn2 = B2 / rho;
+    double cs2 = fmax(0.0, gam * fabs(pg / rho));
+    double bnx2 = Bx * Bx / rho;
+    double a = sqrt(cs2);
+    double s_ = bbn2 + cs2;
+    double root = sqrt(fmax(0.0, s_ * s_ - 4.0 * bnx2 * cs2));
+    double cf = sqrt(fmax(0.0, (bbn2 + cs2 + root) / 2.0));
+    double ca = sqrt(fmax(0.0, bnx2));
+    double cs = sqrt(fmax(0.0, (bbn2 + cs2 - root) / 2.0));
+    double Bt2 = By * By + Bz * Bz;
+    double s = sgn(Bx);
+    if (s == 0.0) s = 1.0;
+    double bty = 1.0 / sqrt(2.0), btz = 1.0 / sqrt(2.0);
+    if (!(Bt2 <= 1e-30)) { bty = By / sqrt(Bt2); btz = Bz / sqrt(Bt2); }
+    double dl2 = cf * cf - cs * cs;
+    double af = 1.0, as = 1.0;
+    if (dl2 >= 1e-30) {
+        af = sqrt(fmax(0.0, cs2 - cs * cs) / dl2);
+        as = sqrt(fmax(0.0, cf * cf - cs2) / dl2);
+    }
+    double sig = bty * vy + btz * vz;
+    double kap = rho / (gam * S), Sr = S / rho;
+
+    L[0][0] = af * (gS * cs2 + cf * vx) - as * cs * sig * s; L[0][1] = -af * cf;
+    L[0][2] = as * cs * bty * s; L[0][3] = as * cs * btz * s;
+    L[0][4] = a * as * bty * r; L[0][5] = a * as * btz * r; L[0][6] = af * cs2 * kap;
+    L[1][0] = btz * vy - bty * vz; L[1][1] = 0.0; L[1][2] = -btz; L[1][3] = bty;
+    L[1][4] = -btz * s * r; L[1][5] = bty * s * r; L[1][6] = 0.0;
+    L[2][0] = as * (gS * cs2 + cs * vx) + af * cf * sig * s; L[2][1] = -as * cs;
+    L[2][2] = -af * cf * bty * s; L[2][3] = -af * cf * btz * s;
+    L[2][4] = -a * af * bty * r; L[2][5] = -a * af * btz * r; L[2][6] = as * cs2 * kap;
+    L[3][0] = 1.0 / gam; L[3][1] = 0.0; L[3][2] = 0.0; L[3][3] = 0.0; L[3][4] = 0.0; L[3][5] = 0.0; L[3][6] = -kap;
+    L[4][0] = as * (gS * cs2 - cs * vx) - af * cf * sig * s; L[4][1] = as * cs;
+    L[4][2] = af * cf * bty * s; L[4][3] = af * cf * btz * s;
+    L[4][4] = -a * af * bty * r; L[4][5] = -a * af * btz * r; L[4][6] = as * cs2 * kap;
+    L[5][0] = btz * vy - bty * vz; L[5][1] = 0.0; L[5][2] = -btz; L[5][3] = bty;
+    L[5][4] = btz * s * r; L[5][5] = -bty * s * r; L[5][6] = 0.0;
+    L[6][0] = af * (gS * cs2 - cf * vx) + as * cs * sig * s; L[6][1] = af * cf;
+    L[6][2] = -as * cs * bty * s; L[6][3] = -as * cs * btz * s;
+    L[6][4] = a * as * bty * r; L[6][5] = a * as * btz * r; L[6][6] = af * cs2 * kap;
+
+    R[0][0] = af; R[1][0] = af * (vx - cf);
+    R[2][0] = af * vy + as * cs * bty * s; R[3][0] = af * vz + as * cs * btz * s;
+    R[4][0] = a * as * bty / r; R[5][0] = a * as * btz / r; R[6][0] = af * Sr;
+    R[0][1] = 0.0; R[1][1] = 0.0; R[2][1] = -btz; R[3][1] = bty;
+    R[4][1] = -btz * s / r; R[5][1] = bty * s / r; R[6][1] = 0.0;
+    R[0][2] = as; R[1][2] = as * (vx - cs);
+    R[2][2] = as * vy - af * cf * bty * s; R[3][2] = as * vz - af * cf * btz * s;
+    R[4][2] = -a * af * bty / r; R[5][2] = -a * af * btz / r; R[6][2] = as * Sr;
+    R[0][3] = 1.0; R[1][3] = vx; R[2][3] = vy; R[3][3] = vz; R[4][3] = 0.0; R[5][3] = 0.0; R[6][3] = g0 * Sr;
+    R[0][4] = as; R[1][4] = as * (vx + cs);
+    R[2][4] = as * vy + af * cf * bty * s; R[3][4] = as * vz + af * cf * btz * s;
+    R[4][4] = -a * af * bty / r; R[5][4] = -a * af * btz / r; R[6][4] = as * Sr;
+    R[0][5] = 0.0; R[1][5] = 0.0; R[2][5] = -btz; R[3][5] = bty;
+    R[4][5] = btz * s / r; R[5][5] = -bty * s / r; R[6][5] = 0.0;
+    R[0][6] = af; R[1][6] = af * (vx + cf);
+    R[2][6] = af * vy - as * cs * bty * s; R[3][6] = af * vz - as * cs * btz * s;
+    R[4][6] = a * as * bty / r; R[5][6] = a * as * btz / r; R[6][6] = af * Sr;
+
+    const double sc[7] = {0.5 / cs2, 0.5, 0.5 / cs2, 1.0, 0.5 / cs2, 0.5, 0.5 / cs2};   /* row 4 unscaled, :872 */
+    for (int m = 0; m < 7; ++m)
+        for (int c = 0; c < 7; ++c) L[m][c] *= sc[m];
+    double sgnBt = sgn(By);
+    if (By == 0.0) sgnBt = sgn(Bz);
+    if (sgnBt == 0.0) sgnBt = 1.0;
+    int m1 = (a >= ca) ? 2 : 0, m2 = (a >= ca) ? 4 : 6;
+    for (int c = 0; c < 7; ++c) {
+        L[m1][c] *= sgnBt; L[m2][c] *= sgnBt;
+        R[c][m1] *= sgnBt; R[c][m2] *= sgnBt;
+    }
+}
+
 /* one side of the Jiang & Wu WENO correction, Weno5_2D.jl:1841-1853 */
 static double weno_phi(double a, double b, double c, double d, double eps)
 {
@@ -284,7 +399,7 @@ static void face_flux(const double *const Fk[6], const double *const qk[6],
  * The stencil cell f+3 = n of the last face continues the boundary condition (Q3).
  * work: 4 arrays of n*8 doubles.
  */
-static void sweep_line(int n, const double (*line)[8], double gam, double eps, int bc, int variant,
+static void sweep_line(int n, const double (*line)[8], double gam, double eps, int bc, int variant, int branch,
                        double (*fhat)[7], double *bs2, double *bs3, double *work)
 {
     double (*u)[8] = (double (*)[8])work;
@@ -292,16 +407,17 @@ static void sweep_line(int n, const double (*line)[8], double gam, double eps, i
     double (*F)[8] = (double (*)[8])(work + 16 * (size_t)n);
     double (*q7)[8] = (double (*)[8])(work + 24 * (size_t)n);
     for (int i = 0; i < n; ++i) {
-        cell_primitives(line[i], gam, u[i]);
+        if (branch == 0) { cell_primitives(line[i], gam, u[i]); cell_fluxes(line[i], u[i], F[i]); }
+        else { cell_primitives_S(line[i], gam, u[i]); cell_fluxes_S(line[i], u[i], F[i]); }
         cell_eigenvalues(u[i], gam, a[i]);
-        cell_fluxes(line[i], u[i], F[i]);
         q7[i][0] = line[i][0]; q7[i][1] = line[i][1]; q7[i][2] = line[i][2]; q7[i][3] = line[i][3];
         q7[i][4] = line[i][5]; q7[i][5] = line[i][6]; q7[i][6] = line[i][7];
     }
     const int ni = n - 2 * NB;
     for (int f = NB - 1; f <= n - NB; ++f) {
         double L[7][7], R[7][7];
-        face_eigenvectors(u[f], u[f + 1], line[f][7], line[f + 1][7], gam, variant, L, R);
+        if (branch == 0) face_eigenvectors(u[f], u[f + 1], line[f][7], line[f + 1][7], gam, variant, L, R);
+        else face_eigenvectors_S(u[f], u[f + 1], gam, L, R);
         const double *Fk[6], *qk[6];
         for (int k = 0; k < 6; ++k) {
             int c = f - 2 + k;
@@ -393,7 +509,7 @@ static double s2e(double rho, double mx, double my, double mz, double bx, double
 /* ------------------------------------------------------------------ directional sweeps on the grid
  * q: 8 planes [rho,Mx,My,Mz,Bx,By,Bz,E]; dq: 8 planes (zeroed here); bs: one plane. */
 
-static void sweep_x(const orc_params *P, const double *q, double *dq, double *fsy)
+static void sweep_x_br(const orc_params *P, const double *q, int branch, double *dq, double *fsy)
 {
     const int Nx = P->nx + 2 * NB, Ny = (P->ny > 1) ? P->ny + 2 * NB : 1;
     const size_t pl = (size_t)Nx * Ny;
@@ -411,7 +527,7 @@ static void sweep_x(const orc_params *P, const double *q, double *dq, double *fs
             for (int i = 0; i < Nx; ++i)
                 for (int c = 0; c < 8; ++c) line[i][c] = q[c * pl + IDX(i, j)];
             memset(fh, 0, sizeof(double[7]) * Nx);
-            sweep_line(Nx, line, P->gam, P->eps, P->bc_x, P->variant, fh, b2, b3, work);
+            sweep_line(Nx, line, P->gam, P->eps, P->bc_x, P->variant, branch, fh, b2, b3, work);
             static const int out[7] = {0, 1, 2, 3, 5, 6, 7};
             for (int i = NB - 1; i <= Nx - NB; ++i) {
                 for (int c = 0; c < 7; ++c) dq[out[c] * pl + IDX(i, j)] = fh[i][c] - fh[i - 1][c];
@@ -424,7 +540,7 @@ static void sweep_x(const orc_params *P, const double *q, double *dq, double *fs
 
 /* y sweep without a transposed copy: the line runs along j and the vector components are
  * permuted (x,y,z) -> (y,z,x) as rotate_state does (Weno5_2D.jl:1897-1927). */
-static void sweep_y(const orc_params *P, const double *q, double *dq, double *gsx)
+static void sweep_y_br(const orc_params *P, const double *q, int branch, double *dq, double *gsx)
 {
     const int Nx = P->nx + 2 * NB, Ny = P->ny + 2 * NB;
     const size_t pl = (size_t)Nx * Ny;
@@ -444,7 +560,7 @@ static void sweep_y(const orc_params *P, const double *q, double *dq, double *gs
             for (int j = 0; j < Ny; ++j)
                 for (int c = 0; c < 8; ++c) line[j][c] = q[in[c] * pl + IDX(i, j)];
             memset(fh, 0, sizeof(double[7]) * Ny);
-            sweep_line(Ny, line, P->gam, P->eps, P->bc_y, P->variant, fh, b2, b3, work);
+            sweep_line(Ny, line, P->gam, P->eps, P->bc_y, P->variant, branch, fh, b2, b3, work);
             for (int j = NB - 1; j <= Ny - NB; ++j) {
                 for (int c = 0; c < 7; ++c) dq[out[c] * pl + IDX(i, j)] = fh[j][c] - fh[j - 1][c];
                 gsx[IDX(i, j)] = b3[j];
@@ -453,6 +569,9 @@ static void sweep_y(const orc_params *P, const double *q, double *dq, double *gs
         free(line); free(fh); free(b2); free(b3); free(work);
     }
 }
+
+static void sweep_x(const orc_params *P, const double *q, double *dq, double *fsy) { sweep_x_br(P, q, 0, dq, fsy); }
+static void sweep_y(const orc_params *P, const double *q, double *dq, double *gsx) { sweep_y_br(P, q, 0, dq, gsx); }
 
 /* Weno5_2D.jl:319-342 + the face-B update lines (:150-151 etc.) + :344-356 */
 static void ct_update(const orc_params *P, const double *fsy, const double *gsx,
@@ -572,6 +691,136 @@ int orc_rk4_step_2d(const orc_params *P, const double *q0, const double *bxb0, c
     free(W.dFx); free(W.dFy); free(W.fsy); free(W.gsx); free(W.Ox); free(W.qE);
     free(q0E); free(base); free(q1); free(q2); free(q3); free(bbx); free(bby);
     for (int k = 1; k < 4; ++k) { free(bx[k]); free(by[k]); }
+    return 0;
+}
+
+/* ------------------------------------------------------------------ dual-energy step
+ * classical_RK4_step with both branches live and ES_Switch (Weno5_2D.jl:1734-1768) using the criterion the
+ * reference wrote and commented out (:1740): dS = |E2S(q_E) - S(q_S)| >= threshold -> the E state, and the CT seed
+ * fluxes of that cell and of its low-side neighbour faces from the E sweep (:1754-1758); else the S state. */
+typedef struct { double *dFx, *dFy, *fsy[2], *gsx[2], *Ox, *cand[2], *bxt, *byt; unsigned char *bad; } dual_work;
+
+static void stage_2d_dual(const orc_params *P, const double *qk, const double *baseE, const double *baseS,
+                          const double *bbx, const double *bby, double c, double dt, int stage, double threshold,
+                          double *out, double *bxn, double *byn, long *nbad, dual_work *W)
+{
+    const int Nx = P->nx + 2 * NB, Ny = P->ny + 2 * NB;
+    const size_t pl = (size_t)Nx * Ny;
+    const double hx = dt / P->dx, hy = dt / P->dy;
+    for (int br = 0; br < 2; ++br) {
+        double *qb = W->cand[br];
+        memcpy(qb, qk, 7 * pl * sizeof(double));
+        memcpy(qb + 7 * pl, qk + (br == 0 ? 8 : 7) * pl, pl * sizeof(double));
+        sweep_x_br(P, qb, br, W->dFx, W->fsy[br]);
+        sweep_y_br(P, qb, br, W->dFy, W->gsx[br]);
+        const double *base = br == 0 ? baseE : baseS;
+        for (int cmp = 0; cmp < 8; ++cmp) {
+            const double *b = base + cmp * pl, *fx = W->dFx + cmp * pl, *fy = W->dFy + cmp * pl;
+            double *o = qb + cmp * pl;
+#pragma omp parallel for schedule(static)
+            for (size_t k = 0; k < pl; ++k) {
+                /* term order of the reference: E stages 1,2 take y first (:145,:190), everything else x first */
+                if (stage <= 2 && br == 0) o[k] = b[k] - 1.0 / 2 * dt / P->dy * fy[k] - 1.0 / 2 * dt / P->dx * fx[k];
+                else if (stage <= 2)       o[k] = b[k] - 1.0 / 2 * dt / P->dx * fx[k] - 1.0 / 2 * dt / P->dy * fy[k];
+                else if (stage == 3)       o[k] = b[k] - hx * fx[k] - hy * fy[k];
+                else                       o[k] = b[k] + (-1.0 / 6 * dt / P->dx * fx[k] - 1.0 / 6 * dt / P->dy * fy[k]);
+            }
+        }
+        boundaries_q(qb, 8, Nx, Ny, P);
+        boundaries_flux(W->fsy[br], Nx, Ny, P);
+        boundaries_flux(W->gsx[br], Nx, Ny, P);
+        ct_update(P, W->fsy[br], W->gsx[br], bbx, bby, c, dt, W->bxt, W->byt, qb + 4 * pl, qb + 5 * pl, W->Ox);
+        boundaries_q(qb, 8, Nx, Ny, P);
+    }
+    const double *qE = W->cand[0], *qS = W->cand[1];
+    long count = 0;
+#pragma omp parallel for schedule(static) reduction(+ : count)
+    for (int j = 0; j < Ny; ++j)
+        for (int i = 0; i < Nx; ++i) {
+            const size_t k = IDX(i, j);
+            const double SE = e2s(qE[k], qE[pl + k], qE[2 * pl + k], qE[3 * pl + k], qE[4 * pl + k], qE[5 * pl + k],
+                                  qE[6 * pl + k], qE[7 * pl + k], P->gam);
+            const int b = i >= 1 && j >= 1 && fabs(SE - qS[7 * pl + k]) >= threshold;      /* the loop starts at 2 */
+            W->bad[k] = (unsigned char)b;
+            const double *src = b ? qE : qS;
+            for (int cmp = 0; cmp < 7; ++cmp) out[cmp * pl + k] = src[cmp * pl + k];
+            out[7 * pl + k] = b ? SE : qS[7 * pl + k];
+            out[8 * pl + k] = s2e(out[k], out[pl + k], out[2 * pl + k], out[3 * pl + k], out[4 * pl + k],
+                                  out[5 * pl + k], out[6 * pl + k], out[7 * pl + k], P->gam);       /* :1765 */
+            if (b && i >= NB && i < Nx - NB && j >= NB && j < Ny - NB) ++count;
+        }
+    *nbad = count;
+    double *fsy = W->fsy[1], *gsx = W->gsx[1];
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < Ny; ++j)
+        for (int i = 0; i < Nx; ++i) {
+            const size_t k = IDX(i, j);
+            const int here = W->bad[k];
+            if (here || (i + 1 < Nx && W->bad[IDX(i + 1, j)])) fsy[k] = W->fsy[0][k];
+            if (here || (j + 1 < Ny && W->bad[IDX(i, j + 1)])) gsx[k] = W->gsx[0][k];
+        }
+    boundaries_q(out, 9, Nx, Ny, P);
+    boundaries_flux(fsy, Nx, Ny, P);
+    boundaries_flux(gsx, Nx, Ny, P);
+    ct_update(P, fsy, gsx, bbx, bby, c, dt, bxn, byn, out + 4 * pl, out + 5 * pl, W->Ox);
+    boundaries_q(out, 9, Nx, Ny, P);
+}
+
+/* classical_RK4_step with the live switch; nbad[4] = interior cells that took the E state, per stage */
+int orc_rk4_step_2d_dual(const orc_params *P, const double *q0, const double *bxb0, const double *byb0, double dt,
+                         double threshold, double *q4, double *bxb4, double *byb4, long nbad[4])
+{
+    const int Nx = P->nx + 2 * NB, Ny = P->ny + 2 * NB;
+    const size_t pl = (size_t)Nx * Ny;
+    dual_work W;
+    W.dFx = malloc(8 * pl * sizeof(double)); W.dFy = malloc(8 * pl * sizeof(double));
+    for (int b = 0; b < 2; ++b) {
+        W.fsy[b] = malloc(pl * sizeof(double)); W.gsx[b] = malloc(pl * sizeof(double));
+        W.cand[b] = malloc(8 * pl * sizeof(double));
+    }
+    W.Ox = malloc(pl * sizeof(double)); W.bxt = malloc(pl * sizeof(double)); W.byt = malloc(pl * sizeof(double));
+    W.bad = malloc(pl);
+    double *q0E = malloc(8 * pl * sizeof(double)), *q0S = malloc(8 * pl * sizeof(double));
+    double *baseE = malloc(8 * pl * sizeof(double)), *baseS = malloc(8 * pl * sizeof(double));
+    double *q[4];
+    double *bx[4], *by[4];
+    for (int k = 1; k < 4; ++k) {
+        q[k] = malloc(9 * pl * sizeof(double)); bx[k] = malloc(pl * sizeof(double)); by[k] = malloc(pl * sizeof(double));
+    }
+    double *bbx = malloc(pl * sizeof(double)), *bby = malloc(pl * sizeof(double));
+    memcpy(q0E, q0, 7 * pl * sizeof(double));
+    memcpy(q0E + 7 * pl, q0 + 8 * pl, pl * sizeof(double));
+    memcpy(q0S, q0, 8 * pl * sizeof(double));
+
+    stage_2d_dual(P, q0, q0E, q0S, bxb0, byb0, 0.5, dt, 1, threshold, q[1], bx[1], by[1], &nbad[0], &W);
+    stage_2d_dual(P, q[1], q0E, q0S, bxb0, byb0, 0.5, dt, 2, threshold, q[2], bx[2], by[2], &nbad[1], &W);
+    stage_2d_dual(P, q[2], q0E, q0S, bxb0, byb0, 1.0, dt, 3, threshold, q[3], bx[3], by[3], &nbad[2], &W);
+    for (int c = 0; c < 8; ++c) {
+        const int srcE = (c == 7) ? 8 : c;
+        for (size_t k = 0; k < pl; ++k) {
+            baseE[c * pl + k] = 1.0 / 3 * (-q0E[c * pl + k] + q[1][srcE * pl + k] + 2 * q[2][srcE * pl + k] + q[3][srcE * pl + k]);
+            baseS[c * pl + k] = 1.0 / 3 * (-q0S[c * pl + k] + q[1][c * pl + k] + 2 * q[2][c * pl + k] + q[3][c * pl + k]);
+        }
+    }
+    for (size_t k = 0; k < pl; ++k) {
+        bbx[k] = 1.0 / 3 * (-bxb0[k] + bx[1][k] + 2 * bx[2][k] + bx[3][k]);
+        bby[k] = 1.0 / 3 * (-byb0[k] + by[1][k] + 2 * by[2][k] + by[3][k]);
+    }
+    stage_2d_dual(P, q[3], baseE, baseS, bbx, bby, 1.0 / 6, dt, 4, threshold, q4, bxb4, byb4, &nbad[3], &W);
+    boundaries_flux(bxb4, Nx, Ny, P);
+    boundaries_flux(byb4, Nx, Ny, P);
+
+    free(W.dFx); free(W.dFy); free(W.Ox); free(W.bxt); free(W.byt); free(W.bad);
+    for (int b = 0; b < 2; ++b) { free(W.fsy[b]); free(W.gsx[b]); free(W.cand[b]); }
+    free(q0E); free(q0S); free(baseE); free(baseS); free(bbx); free(bby);
+    for (int k = 1; k < 4; ++k) { free(q[k]); free(bx[k]); free(by[k]); }
+    return 0;
+}
+
+/* weno5_flux_difference_S (Weno5_2D.jl:361), one direction: q8 = [rho,Mx,My,Mz,Bx,By,Bz,S] */
+int orc_sweep_2d_S(const orc_params *P, const double *q8, int dir, double *dq, double *bs)
+{
+    if (dir == 0) sweep_x_br(P, q8, 1, dq, bs); else sweep_y_br(P, q8, 1, dq, bs);
     return 0;
 }
 

@@ -269,6 +269,13 @@ def test_s_branch_functions_match_reference():
     dqr, _, gr = M.flux_difference_S(M.rotate_fwd(qS), g.gam, g.eps, "outflow")
     assert np.abs(M.rotate_bwd(dqr) - d["dqy_S"])[:, :Ny - 3].max() <= 1e-14 * np.abs(d["dqy_S"]).max()
     assert np.abs(gr.T - d["gsx_S"])[:, :Ny - 3].max() <= 1e-14 * np.abs(d["gsx_S"]).max()
+    # the C oracle's entropy-variable sweeps
+    dqc, fc = O.sweep_2d_S(g, qS, 0)
+    assert np.abs(dqc - d["dqx_S"])[:Nx - 3].max() <= 1e-14 * np.abs(d["dqx_S"]).max()
+    assert np.abs(fc - d["fsy_S"])[:Nx - 3].max() <= 1e-14 * np.abs(d["fsy_S"]).max()
+    dqc, gc = O.sweep_2d_S(g, qS, 1)
+    assert np.abs(dqc - d["dqy_S"])[:, :Ny - 3].max() <= 1e-14 * np.abs(d["dqy_S"]).max()
+    assert np.abs(gc - d["gsx_S"])[:, :Ny - 3].max() <= 1e-14 * np.abs(d["gsx_S"]).max()
 
 
 def test_dual_energy_step_matches_reference():
@@ -278,12 +285,15 @@ def test_dual_energy_step_matches_reference():
     g = grid_of(d, pr.PERIODIC)
     P = mirror_params(g)
     assert d["nbad"].min() > 20 and d["nbad"].max() < 150            # a genuine mixture of E and S cells (ghosts included)
-    q, bx, by = d["q0"], d["bxb0"], d["byb0"]
-    for s in range(1, len(d["dt"]) + 1):
-        q, bx, by, nbad = M.classical_RK4_step_2d_dual(q, bx, by, float(d["dt"][s - 1]), P)
-        err = group_err(q, d[f"q{s}"])
-        assert max(err.values()) <= 1e-13, err
-        assert np.abs(bx - d[f"bxb{s}"]).max() <= 1e-14 and np.abs(by - d[f"byb{s}"]).max() <= 1e-14
+    for step in (lambda q, bx, by, dt: M.classical_RK4_step_2d_dual(q, bx, by, dt, P),
+                 lambda q, bx, by, dt: O.rk4_step_2d_dual(g, q, bx, by, dt)):
+        q, bx, by = d["q0"], d["bxb0"], d["byb0"]
+        for s in range(1, len(d["dt"]) + 1):
+            q, bx, by, nbad = step(q, bx, by, float(d["dt"][s - 1]))
+            err = group_err(q, d[f"q{s}"])
+            assert max(err.values()) <= 1e-13, err
+            assert np.abs(bx - d[f"bxb{s}"]).max() <= 1e-14 and np.abs(by - d[f"byb{s}"]).max() <= 1e-14
+            assert 20 < min(nbad) and max(nbad) < 150
 
 
 def test_dual_energy_step_reference_problem():
@@ -292,6 +302,8 @@ def test_dual_energy_step_reference_problem():
     q, bx, by, nbad = M.classical_RK4_step_2d_dual(d["q0"], d["bxb0"], d["byb0"], float(d["dt"][0]), mirror_params(g))
     err = group_err(q, d["q1"])
     assert max(err.values()) <= 1e-9, err                            # Q3-limited, like the E-only step
+    qc, bxc, byc, nbc = O.rk4_step_2d_dual(g, d["q0"], d["bxb0"], d["byb0"], float(d["dt"][0]))
+    assert max(group_err(qc, q).values()) <= 1e-13 and nbc == nbad    # the two restatements agree with each other
 
 
 # ------------------------------------------------------------------------------------------ snapshot hook (f4)
