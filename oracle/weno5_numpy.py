@@ -2,8 +2,9 @@
 TEST INFRASTRUCTURE ONLY -- numpy restatement of the reference WENO5 MHD numerics.
 
 This file is one of two independent CPU restatements (the other is the C oracle in
-``oracle/weno5_oracle.c``) of the E-branch algorithm of jdonnert/julia's
-``Weno5_2D.jl`` / ``Weno5_1D.jl``.  It is array-at-a-time like the reference
+``oracle/weno5_oracle.c``) of the algorithm of jdonnert/julia's
+``Weno5_2D.jl`` / ``Weno5_1D.jl`` (the shipped E-branch step, the entropy-variable S sweeps, the dual-energy
+step with a live ES_Switch, and Arr2Img of JColorMaps.jl).  It is array-at-a-time like the reference
 (whole-grid temporaries, transposed copy for the y sweep) and is only ever imported
 by ``tests/`` -- never by the product path.
 
