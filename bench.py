@@ -186,7 +186,7 @@ def workload_config(ngpu):
             "l2": "no flush needed: ~6.5 GB of resident planes per GPU >> 126 MB L2",
             "es_roundtrip": 1,
             "note": "E <- S2E(E2S(E)) after every stage, exactly as the 2-D reference's ES_Switch does "
-                    "(Weno5_2D.jl:1738,1765); --es-roundtrip 0 selects the 1-D reference's form (keeps E, ~3% faster)"}
+                    "(Weno5_2D.jl:1738,1765); --es-roundtrip 0 selects the 1-D reference's form (keeps E, ~3.5% faster)"}
 
 
 # ----------------------------------------------------------------------------- GPU arm
