@@ -88,22 +88,21 @@ W5_HD double fast_rsqrt(double x)
 #endif
 }
 
-// sqrt(x) for x >= 0 (0 gives 0), branch-free: one Newton step on the rsqrt seed
-// (1.3e-12) and one correction step s + (x - s^2) y/2 on the product, which squares that error.
+// sqrt(x) for x >= 0 (0 gives 0), branch-free, from the rsqrt seed.
 W5_HD double fast_sqrt(double x)
 {
 #if defined(__CUDA_ARCH__)
     const double xs = x + 1e-300;                 // = x for every normal x of interest, keeps rsqrt(0) finite
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(xs));
-    const double e = fma(-(0.5 * xs * y), y, 0.5);
-    y = fma(y, e, y);
-    // the product takes x itself, not the clamped value: x = 0 gives 0 * y = 0 without a final select (and a NaN
-    // stays a NaN); for x >= 1e-300 nothing changes
-    double s = x * y;
-    const double d = fma(-s, s, x);
-    s = fma(d, 0.5 * y, s);
-    return s;
+    // coupled iteration on s ~ sqrt(x) and h ~ 1/(2 sqrt(x)) (one step from the seed: 1.5 e^2 ~ 1e-12) and one
+    // correction s + (x - s^2) h, which squares that: five dependent operations after the seed.  The products take x
+    // itself, not the guarded value: x = 0 gives 0 without a final select (and a NaN stays a NaN).
+    const double s0 = x * y, h0 = 0.5 * y;
+    const double r = fma(-s0, h0, 0.5);
+    const double s1 = fma(s0, r, s0), h1 = fma(h0, r, h0);
+    const double d = fma(-s1, s1, x);
+    return fma(d, h1, s1);
 #else
     return sqrt(x);
 #endif
