@@ -18,7 +18,7 @@
 #include <cstdlib>
 
 #ifndef W5_DEFAULT_VARIANT
-#define W5_DEFAULT_VARIANT 4
+#define W5_DEFAULT_VARIANT 5
 #endif
 
 namespace w5 {
@@ -394,24 +394,263 @@ __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a, const 
     }
 }
 
-// Launch variants (CTA size x resident CTAs per SM; always 8 warps of ~252 registers per SM);
-// chosen once per process by WENO5_FLUX_VARIANT (development knob; the default is the fastest
-// measured on B200).  Smaller CTAs decouple the barriers of the march steps.
-//   2: cp.async (LDGSTS) staging        4: TMA tensor-map staging (default)
-// Both: 128 threads x 2 CTAs per SM, x tile 2 rows x 64 faces, y tile 8 face rows x 16 columns.
-// (256x1, 64x4, 4x32-tile and 128/168-register variants were measured and dropped)
-struct Variant { int nt, yw; };
-static const Variant kVariants[5] = {{128, 16}, {128, 16}, {128, 16}, {128, 16}, {128, 16}};
+// ------------------------------------------------------------------ warp-specialised flux kernel
+// Same arithmetic as flux_kernel, different division of labour.  In flux_kernel every warp walks through
+// cell phase -> barrier -> face phase -> barrier -> update phase; with two 252-register warps per SM
+// sub-partition the FP64 pipe idles whenever one of them is in the (latency-bound, FP64-poor) cell or update
+// phase: measured 72-74 % pipe utilisation although the face phase alone sustains 93 %.  Here a CTA has two
+// warpgroups with the register file split by `setmaxnreg`:
+//   warps 0-3  FACE warps (FREG registers): nothing but the face phase, back to back;
+//   warps 4-7  HELPER warps (HREG registers): TMA issue, cell phase of the NEXT chunk, flux difference /
+//              RK update of the PREVIOUS chunk, i.e. everything that is not dense FP64.
+// Each sub-partition holds one face and one helper warp of each of the two resident CTAs, so the FP64 pipe
+// always has two face warps to draw from and the helpers fill in.  Hand-over through four mbarriers
+// (helper_done / face_done, two each so that a parity can never be lapped); the face warps never meet a
+// CTA-wide barrier and may drift against each other by a march step.
+// Ring of 2 NS + 5 cell slots (cells of chunk n+1 are written while chunk n is read), double-buffered face
+// fluxes.  2-D, E branch, TMA staging (the 1-D, S-branch and no-tensor-map paths keep flux_kernel).
+template <int DIR> struct WsTile {
+    static constexpr int NT = 128, YW = 16;               // threads per role; columns of the y tile
+    static constexpr int NS = DIR == 0 ? 64 : NT / YW;
+    static constexpr int NPB = DIR == 0 ? NT / 64 : YW;
+    static constexpr int RS = DIR == 0 ? (2 * NS + 5 + 15) / 16 * 16 : 2 * NS + 5;
+    static constexpr int CBS = RS * NPB;
+    static constexpr int FBS = (NS + 1) * NPB;
+    static constexpr int BOX_X = DIR == 0 ? NS + 2 : NPB, BOX_Y = DIR == 0 ? NPB : NS;
+    static constexpr int FST = BOX_X * BOX_Y;
+    static constexpr int OFF_FB = CQ_COUNT * CBS;                              // [2][7][FBS]
+    static constexpr int OFF_STQ = (OFF_FB + 14 * FBS + 15) / 16 * 16;         // [8][FST]   (TMA destination)
+    static constexpr int OFF_STU = OFF_STQ + (8 * FST + 15) / 16 * 16;         // [18][FST]  (y sweep)
+    static constexpr int OFF_BAR = OFF_STU + (DIR == 0 ? 0 : 18 * FST);
+    static constexpr int SMEM = (OFF_BAR + 8) * (int)sizeof(double) + 16;
+    __device__ static __forceinline__ int sti(int s, int p, int e) { return DIR == 0 ? p * BOX_X + s + e : s * NPB + p; }
+    __device__ static __forceinline__ int cbi(int slot, int p) { return DIR == 0 ? p * RS + slot : slot * NPB + p; }
+    __device__ static __forceinline__ int fbi(int slot, int p) { return DIR == 0 ? p * (NS + 1) + slot : slot * NPB + p; }
+};
 
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void helper_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int DIR, int FREG, int HREG>
+__global__ void __launch_bounds__(256, 2) flux_ws_kernel(const FluxArgs a, const __grid_constant__ FluxMaps tmap)
+{
+    using T = WsTile<DIR>;
+    constexpr int NT = T::NT, NS = T::NS, NPB = T::NPB, RS = T::RS, CBS = T::CBS, FBS = T::FBS;
+    extern __shared__ __align__(128) double sm[];
+    double *cb = sm;
+    double *fb = sm + T::OFF_FB;
+    double *stq = sm + T::OFF_STQ;
+    double *stu = sm + T::OFF_STU;
+    // [0] state TMA, [1] operand TMA, [2],[3] helper_done, [4],[5] face_done (index = march step & 1)
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(sm + T::OFF_BAR);
+
+    const double dt = *a.dtp;
+    if (dt == 0.0) return;                       // advance() past tmax: leave the state untouched
+
+    const bool helper = threadIdx.x >= NT;
+    const int t = threadIdx.x & (NT - 1);
+    const int s = DIR == 0 ? (t % NS) : (t / NPB);
+    const int p = DIR == 0 ? (t / NS) : (t % NPB);
+    const int line = blockIdx.x * NPB + p;
+    const int seg = blockIdx.y;
+    const int fA = 2 + seg * a.seg_len;
+    const int fB = min(fA + a.seg_len, a.N - 3);
+    const int fStart = seg == 0 ? fA : fA - 1;
+    const int nsteps = (fB - fStart + NS - 1) / NS;
+
+    const bool line_ok = line >= G && line < a.NP - G;
+    bool row_sel = true;
+    if (DIR == 0 && a.row_mode != 0) {
+        const int l0 = blockIdx.x * NPB, l1 = min(l0 + NPB, a.NP) - 1;
+        const bool any_interior = l1 >= G && l0 < a.NP - G;
+        const bool any_ghost = l0 < G || l1 >= a.NP - G;
+        if (a.row_mode == 1 ? !any_interior : !any_ghost) return;
+        row_sel = (line >= G && line < a.NP - G) == (a.row_mode == 1);
+    }
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+        mbar_init(&bars[2], NT); mbar_init(&bars[3], NT); mbar_init(&bars[4], NT); mbar_init(&bars[5], NT);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (!helper) {
+        // ============================================================ FACE warps
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(FREG));
+        int r0 = 0;                              // ring slot of cell s0 - 2
+        for (int n = 0; n < nsteps; ++n) {
+            const int s0 = fStart + n * NS;
+            const int b = n & 1;
+            mbar_wait(&bars[2 + b], (unsigned)(n >> 1) & 1u);          // cells of this chunk ready, fb[b] free
+            int sl[6];
+            {
+                int r = r0 + s;
+                if (r >= RS) r -= RS;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) { sl[k] = r; r = (r + 1 == RS) ? 0 : r + 1; }
+            }
+            const int f = s0 + s;
+            if (f < fB) {
+                const int iL = T::cbi(sl[2], p), iR = T::cbi(sl[3], p);
+                FaceCoef fc;
+                face_coefficients(cb[CQ_Q0 * CBS + iL], cb[CQ_Q0 * CBS + iR], cb[CQ_V1 * CBS + iL], cb[CQ_V1 * CBS + iR],
+                                  cb[CQ_V2 * CBS + iL], cb[CQ_V2 * CBS + iR], cb[CQ_V3 * CBS + iL], cb[CQ_V3 * CBS + iR],
+                                  cb[CQ_B1 * CBS + iL], cb[CQ_B1 * CBS + iR], cb[(CQ_Q0 + 4) * CBS + iL],
+                                  cb[(CQ_Q0 + 4) * CBS + iR], cb[(CQ_Q0 + 5) * CBS + iL], cb[(CQ_Q0 + 5) * CBS + iR],
+                                  cb[(CQ_Q0 + 6) * CBS + iL], cb[(CQ_Q0 + 6) * CBS + iR], a.gam, a.g2, fc);
+                double amax[7];
+                face_amax(cb[CQ_V1 * CBS + iL], cb[CQ_LF * CBS + iL], cb[CQ_LA * CBS + iL], cb[CQ_LS * CBS + iL],
+                          cb[CQ_V1 * CBS + iR], cb[CQ_LF * CBS + iR], cb[CQ_LA * CBS + iR], cb[CQ_LS * CBS + iR], amax);
+                auto load = [&](int k, double F[7], double x[7]) {
+                    const int ii = T::cbi(sl[k], p);
+#pragma unroll
+                    for (int m = 0; m < 7; ++m) {
+                        F[m] = cb[(CQ_F0 + m) * CBS + ii];
+                        x[m] = cb[(CQ_Q0 + m) * CBS + ii];
+                    }
+                };
+                double fh[7], Fs[7];
+                RegStash st;
+                BackCoef bc;
+                split_back(fc, bc);
+                face_flux(fc, amax, a.eps, load, st, Fs);
+                back_project(bc, Fs, fh);
+                const int io = b * 7 * FBS + T::fbi(s + 1, p);
+#pragma unroll
+                for (int m = 0; m < 7; ++m) fb[m * FBS + io] = fh[m];
+                // CT seed flux, Weno5_2D.jl:1005-1008
+                if (line < a.NP && row_sel && (seg == 0 || f >= fA)) {
+                    constexpr int TV = DIR == 0 ? CQ_V2 : CQ_V3;
+                    const double bv = cb[CQ_B1 * CBS + iL] * cb[TV * CBS + iL] + cb[CQ_B1 * CBS + iR] * cb[TV * CBS + iR];
+                    const size_t g = DIR == 0 ? (size_t)f + (size_t)a.pitch * line : (size_t)line + (size_t)a.pitch * f;
+                    a.bs[g] = fma(0.5, bv, fh[DIR == 0 ? 4 : 5]);
+                }
+            }
+            mbar_arrive(&bars[4 + b]);
+            r0 += NS;
+            if (r0 >= RS) r0 -= RS;
+        }
+    } else {
+        // ============================================================ HELPER warps
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(HREG));
+        unsigned phq = 0, phu = 0;
+        if (t == 0) {
+            tma_issue_state<DIR, NT, T::YW>(a, &tmap, stq, &bars[0], fStart + 3);
+            if constexpr (DIR == 1) tma_issue_operands<NT, T::YW>(a, &tmap, stu, &bars[1], fStart);
+        }
+        // the 5 leading stencil cells of the segment, straight from global memory -> ring slots 0..4
+        for (int e = t; e < 5 * NPB; e += NT) {
+            const int sl = DIR == 0 ? e % 5 : e / NPB;
+            const int pp = DIR == 0 ? e / 5 : e % NPB;
+            const size_t g = cell_index<DIR>(a, fStart - 2 + sl, blockIdx.x * NPB + pp);
+            double q[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) q[k] = __ldg(a.qc[perm<DIR>(k)] + g);
+            cell_store<CBS, 0>(a, cb, q, T::cbi(sl, pp));
+        }
+        // iteration n: flux difference / RK update of chunk n-1, cells of chunk n+1
+        int rc = 5;                              // ring slot of the first new cell of chunk n+1
+        int ru = 2;                              // ring slot of the first centre cell of chunk n-1 (used from n = 1)
+        for (int n = -1; n <= nsteps; ++n) {
+            if (n >= 1) {
+                const int m1 = n - 1, bu = m1 & 1;
+                mbar_wait(&bars[4 + bu], (unsigned)(m1 >> 1) & 1u);    // faces of chunk n-1 are in fb[bu]
+                if constexpr (DIR == 1) { mbar_wait(&bars[1], phu); phu ^= 1u; }
+                const int s0 = fStart + m1 * NS;
+                const int c = s0 + s;
+                const bool upd_ok = (c > fStart) && (c < fB) && (c >= G) && (c < a.N - G) && line_ok && row_sel;
+                const double *fbu = fb + bu * 7 * FBS;
+                if (upd_ok) {
+                    const int i0 = T::fbi(s, p), i1 = T::fbi(s + 1, p);
+                    const size_t g = DIR == 0 ? (size_t)c + (size_t)a.pitch * line : (size_t)line + (size_t)a.pitch * c;
+                    if constexpr (DIR == 0) {
+                        constexpr int fi[6] = {0, 1, 2, 3, 5, 6};      // rho,Mx,My,Mz,Bz,E in fhat
+#pragma unroll
+                        for (int m = 0; m < 6; ++m) a.rhs[m][g] = fbu[fi[m] * FBS + i1] - fbu[fi[m] * FBS + i0];
+                    } else {
+                        constexpr int fi[6] = {0, 3, 1, 2, 4, 6};      // rotated frame -> physical rho,Mx,My,Mz,Bz,E
+                        int rr = ru + s;
+                        if (rr >= RS) rr -= RS;
+                        const int ic = T::cbi(rr, p);
+                        const double cx = a.c_dx * dt, cy = a.c_dy * dt;
+#pragma unroll
+                        for (int m = 0; m < 6; ++m) {
+                            const double dfy = fbu[fi[m] * FBS + i1] - fbu[fi[m] * FBS + i0];
+                            const double qcen = cb[(CQ_Q0 + fi[m]) * CBS + ic];
+                            const double rxm = stu[m * T::FST + t];
+                            double bb = a.stage <= 3 ? stu[(6 + m) * T::FST + t] : 0.0;
+                            const double acm = a.stage >= 3 ? stu[(12 + m) * T::FST + t] : 0.0;
+                            if (a.stage == 2) a.acc[m][g] = qcen - bb;                      // -q0 + q1
+                            if (a.stage == 3) a.acc[m][g] = fma(2.0, qcen, acm);            // + 2 q2
+                            if (a.stage == 4) bb = (acm + qcen) * (1.0 / 3.0);              // Weno5_2D.jl:279
+                            a.qn[m][g] = fma(-cx, rxm, fma(-cy, dfy, bb));
+                        }
+                    }
+                }
+                // the last face of chunk n-1 is the left face of chunk n's first cell
+                if (n < nsteps)
+                    for (int e = t; e < 7 * NPB; e += NT) {
+                        const int m = e / NPB, pp = e % NPB;
+                        fb[(bu ^ 1) * 7 * FBS + m * FBS + T::fbi(0, pp)] = fbu[m * FBS + T::fbi(NS, pp)];
+                    }
+                ru += NS;
+                if (ru >= RS) ru -= RS;
+            }
+            helper_sync();                       // every helper is done with stu and with the ring cells of chunk n-1
+            if constexpr (DIR == 1) {
+                if (t == 0 && n >= 1 && n < nsteps) tma_issue_operands<NT, T::YW>(a, &tmap, stu, &bars[1], fStart + n * NS);
+            }
+            if (n + 1 < nsteps) {
+                mbar_wait(&bars[0], phq); phq ^= 1u;
+                const int c0 = fStart + (n + 1) * NS + 3;               // first new cell of chunk n+1
+                const int si = T::sti(s, p, c0 & 1);
+                double q[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) q[k] = stq[perm<DIR>(k) * T::FST + si];
+                int rr = rc + s;
+                if (rr >= RS) rr -= RS;
+                cell_store<CBS, 0>(a, cb, q, T::cbi(rr, p));
+                rc += NS;
+                if (rc >= RS) rc -= RS;
+                helper_sync();                   // stq consumed
+                if (t == 0 && n + 2 < nsteps) tma_issue_state<DIR, NT, T::YW>(a, &tmap, stq, &bars[0], c0 + NS);
+            }
+            if (n + 1 < nsteps) mbar_arrive(&bars[2 + ((n + 1) & 1)]);
+        }
+    }
+}
+
+// Launch variants, chosen once per process by WENO5_FLUX_VARIANT (development knob; the default is the
+// fastest measured on B200):
+//   2: flux_kernel, cp.async (LDGSTS) staging     4: flux_kernel, TMA tensor-map staging
+//   5: flux_ws_kernel, warp-specialised, TMA staging (default)
+// All: x tile 2 rows x 64 faces, y tile 8 face rows x 16 columns per march step, 2 CTAs per SM.
+// 1-D grids, the entropy branch and contexts without tensor maps always take flux_kernel with cp.async.
 static int flux_variant()
 {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("WENO5_FLUX_VARIANT");
         v = e ? atoi(e) : W5_DEFAULT_VARIANT;
-        if (v < 0 || v > 4) v = W5_DEFAULT_VARIANT;
+        if (v != 2 && v != 4 && v != 5) v = W5_DEFAULT_VARIANT;
     }
     return v;
+}
+
+// Function attributes belong to the device's context: set the dynamic shared-memory limit once per device
+// (a `static bool` would leave every device but the first at the 48 KB default).
+template <auto kernel> static void ensure_smem(int bytes)      // one flag word per kernel instantiation
+{
+    static unsigned long long done = 0;          // bit d: attribute set on device d (devices >= 64: set every time)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && (__atomic_load_n(&done, __ATOMIC_ACQUIRE) >> dev & 1ull)) return;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (dev < 64) __atomic_fetch_or(&done, 1ull << dev, __ATOMIC_RELEASE);
 }
 
 template <int DIR, int NT, int YW, int MINB, bool TMA, int BR = 0>
@@ -419,15 +658,32 @@ static void launch_flux_t(const FluxArgs &a, cudaStream_t s)
 {
     using T = Tile<DIR, NT, YW, BR == 0 ? CQ_COUNT : CQ_COUNT_S>;
     static_assert(T::SMEM * MINB <= 227 * 1024, "shared memory budget");
-    static bool once = false;
-    if (!once) {
-        cudaFuncSetAttribute(flux_kernel<DIR, NT, YW, MINB, TMA, BR>, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM);
-        once = true;
-    }
+    ensure_smem<flux_kernel<DIR, NT, YW, MINB, TMA, BR>>(T::SMEM);
     dim3 grid((a.NP + T::NPB - 1) / T::NPB, a.nseg, 1);
     static const FluxMaps dummy = {};
     const FluxMaps *tm = reinterpret_cast<const FluxMaps *>(DIR == 0 ? a.tmap_x : a.tmap_y);
     flux_kernel<DIR, NT, YW, MINB, TMA, BR><<<grid, NT, T::SMEM, s>>>(a, TMA && tm ? *tm : dummy);
+}
+
+// register split of the two warpgroups (face + helper <= 256 = 2 x the 128 of __launch_bounds__(256, 2));
+// WENO5_WS_SPLIT selects among the compiled splits (development knob)
+template <int DIR, int FREG, int HREG> static void launch_flux_ws_t(const FluxArgs &a, cudaStream_t s)
+{
+    using T = WsTile<DIR>;
+    static_assert((T::SMEM + 1024) * 2 <= 227 * 1024, "shared memory budget (2 CTAs per SM)");
+    static_assert(FREG + HREG <= 256 && FREG % 8 == 0 && HREG % 8 == 0 && HREG >= 24, "register split of the two warpgroups");
+    ensure_smem<flux_ws_kernel<DIR, FREG, HREG>>(T::SMEM);
+    dim3 grid((a.NP + T::NPB - 1) / T::NPB, a.nseg, 1);
+    const FluxMaps *tm = reinterpret_cast<const FluxMaps *>(DIR == 0 ? a.tmap_x : a.tmap_y);
+    flux_ws_kernel<DIR, FREG, HREG><<<grid, 2 * T::NT, T::SMEM, s>>>(a, *tm);
+}
+
+template <int DIR> static void launch_flux_ws(const FluxArgs &a, cudaStream_t s)
+{
+    static const int split = getenv("WENO5_WS_SPLIT") ? atoi(getenv("WENO5_WS_SPLIT")) : 0;
+    if (split == 1) launch_flux_ws_t<DIR, 224, 32>(a, s);
+    else if (split == 2) launch_flux_ws_t<DIR, 208, 48>(a, s);
+    else launch_flux_ws_t<DIR, 216, 40>(a, s);
 }
 
 template <int DIR>
@@ -438,6 +694,7 @@ static void launch_flux(const FluxArgs &a, cudaStream_t s)
     // entropy branch (dual-energy mode): its state planes are not consecutive in the pool, so it takes the
     // cp.async staging, which addresses every plane through its own pointer
     if (a.branch == 1) launch_flux_t<DIR, 128, 16, 2, false, 1>(a, s);
+    else if (tma_ok && v == 5) launch_flux_ws<DIR>(a, s);
     else if (tma_ok && v == 4) launch_flux_t<DIR, 128, 16, 2, true>(a, s);
     else launch_flux_t<DIR, 128, 16, 2, false>(a, s);
 }
@@ -445,14 +702,13 @@ static void launch_flux(const FluxArgs &a, cudaStream_t s)
 void launch_flux_x(const FluxArgs &a, cudaStream_t s) { launch_flux<0>(a, s); }
 void launch_flux_y(const FluxArgs &a, cudaStream_t s) { launch_flux<1>(a, s); }
 
-// faces per march step along the sweep / lines per CTA for the active variant (host-side planning)
-int flux_chunk(int dir) { const Variant v = kVariants[flux_variant()]; return dir == 0 ? 64 : v.nt / v.yw; }
-int flux_lines_per_cta(int dir) { const Variant v = kVariants[flux_variant()]; return dir == 0 ? v.nt / 64 : v.yw; }
-int flux_uses_tma() { return flux_variant() == 4; }
+// faces per march step along the sweep / lines per CTA (host-side planning; the same for every variant)
+int flux_chunk(int dir) { return dir == 0 ? 64 : 8; }
+int flux_lines_per_cta(int dir) { return dir == 0 ? 2 : 16; }
+int flux_uses_tma() { return flux_variant() != 2; }
 void flux_box(int dir, int box[2])
 {
-    const Variant v = kVariants[flux_variant()];
-    if (dir == 0) { box[0] = 64 + 2; box[1] = v.nt / 64; } else { box[0] = v.yw; box[1] = v.nt / v.yw; }
+    if (dir == 0) { box[0] = 64 + 2; box[1] = 2; } else { box[0] = 16; box[1] = 8; }
 }
 
 // ------------------------------------------------------------------ 1-D stage update
