@@ -119,6 +119,8 @@ struct weno5_ctx {
     double *ctl = nullptr;           // device: dt, t, vxmax, vymax, tmax, steps, bad
     unsigned long long *vmax_bits = nullptr;
     unsigned long long *vmax_bits_img = nullptr;   // 3 keys of the snapshot range reduction
+    unsigned long long *vmax_next = nullptr;       // maxima of the state stage 4 is writing (fused reduction, weno5_advance)
+    bool fuse_vmax = false;                        // stage 4 also reduces the wave speeds of the new state
     double *sums = nullptr;
     double *h_ctl = nullptr;         // pinned mirror
     int side[4];                     // SideBC of x-lo, x-hi, y-lo, y-hi for this slab
@@ -323,6 +325,7 @@ static int create_ctx(const weno5_params *P, int device, int ny_local, int j_off
     CU(cudaMemsetAsync(c->ctl, 0, 8 * sizeof(double), c->stream));
     CU(cudaMalloc(&c->vmax_bits, 8 * sizeof(unsigned long long)));
     c->vmax_bits_img = c->vmax_bits + 4;
+    c->vmax_next = c->vmax_bits + 2;
     CU(cudaMalloc(&c->sums, 16 * sizeof(double)));
     CU(cudaMallocHost(&c->h_ctl, 16 * sizeof(double)));
 
@@ -541,21 +544,26 @@ extern "C" int weno5_boundaries(weno5_ctx *c)
 }
 
 // ------------------------------------------------------------------ time step
-static int enqueue_timestep(weno5_ctx *c)
+// fused = true: the maxima were accumulated by stage 4 of the previous step (ct_centers_entropy_vmax) into
+// vmax_next; no pass over the state is needed, and dt_kernel clears the accumulator for the next step
+static int enqueue_timestep(weno5_ctx *c, bool fused = false)
 {
-    launch_vmax(c->Q0.q, c->g, c->P.gamma, c->vmax_bits, c->stream);
-    c->launches += 1;
+    unsigned long long *vb = fused ? c->vmax_next : c->vmax_bits;
+    if (!fused) {
+        launch_vmax(c->Q0.q, c->g, c->P.gamma, vb, c->stream);
+        c->launches += 1;
+    }
     if (c->comm && c->nranks > 1) {
         // all NCCL work of a handle is ordered on the NCCL stream (after a still-running exchange)
         CU(cudaEventRecord(c->ev_main, c->stream));
         CU(cudaStreamWaitEvent(c->comm_stream, c->ev_main, 0));
-        NC(g_nccl.AllReduce(c->vmax_bits, c->vmax_bits, 2, ncclUint64, ncclMax, c->comm, c->comm_stream));
+        NC(g_nccl.AllReduce(vb, vb, 2, ncclUint64, ncclMax, c->comm, c->comm_stream));
         CU(cudaEventRecord(c->ev_comm, c->comm_stream));
         c->xchg_pending = true;
         if (int r = wait_exchange(c)) return r;
         c->launches += 1;
     }
-    launch_dt_from_vmax(c->vmax_bits, c->ctl, c->P.dx, c->P.dy, c->P.cfl, c->g.is1d, c->stream);
+    launch_dt_from_vmax(vb, c->ctl, c->P.dx, c->P.dy, c->P.cfl, c->g.is1d, fused ? 1 : 0, c->stream);
     c->launches += 1;
     return 0;
 }
@@ -699,7 +707,9 @@ static int enqueue_stage(weno5_ctx *c, int stage, State &cur, State &nxt)
     // cell-centred B from the new faces and, when this stage derives S (every stage with the 2-D
     // reference's E -> S -> E round trip, else stage 4 only), the ES_Switch residue in the same pass
     const bool ent = P.es_roundtrip || stage == 4;
-    if (ent) launch_ct_centers_entropy(nxt.bx, nxt.by, nxt.q, g, P.gamma, P.es_roundtrip, dtp, c->stream);
+    if (ent && stage == 4 && c->fuse_vmax)
+        launch_ct_centers_entropy_vmax(nxt.bx, nxt.by, nxt.q, g, P.gamma, P.es_roundtrip, dtp, c->side[1], c->vmax_next, c->stream);
+    else if (ent) launch_ct_centers_entropy(nxt.bx, nxt.by, nxt.q, g, P.gamma, P.es_roundtrip, dtp, c->stream);
     else launch_ct_centers(nxt.bx, nxt.by, nxt.q[C_BX], nxt.q[C_BY], g, dtp, c->stream);
     c->launches += 2;
     if (stage == 4) {                                   // boundaries!(q4, bxb4, byb4), Weno5_2D.jl:313
@@ -850,8 +860,12 @@ extern "C" int weno5_advance(weno5_ctx *c, int nsteps, double tmax, double *t, i
     double *h = c->h_ctl + 8;
     h[0] = 0.0; h[1] = t ? *t : 0.0; h[2] = 0.0; h[3] = 0.0; h[4] = tmax > 0.0 ? tmax : 0.0; h[5] = 0.0; h[6] = 0.0;
     CU(cudaMemcpyAsync(c->ctl, h, 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    // from the second step on the CFL reduction rides on stage 4 of the step before (2-D, E-only path)
+    c->fuse_vmax = !c->dual && !c->g.is1d && nsteps > 1 && !getenv("WENO5_NO_FUSED_VMAX");
+    if (c->fuse_vmax) CU(cudaMemsetAsync(c->vmax_next, 0, 2 * sizeof(unsigned long long), c->stream));
+    struct Unfuse { weno5_ctx *c; ~Unfuse() { c->fuse_vmax = false; } } unfuse{c};
     for (int s = 0; s < nsteps; ++s) {
-        if (int r = enqueue_timestep(c)) return r;
+        if (int r = enqueue_timestep(c, c->fuse_vmax && s > 0)) return r;
         if (int r = enqueue_step(c)) return r;
         launch_advance_time(c->ctl, c->stream);
         c->launches++;

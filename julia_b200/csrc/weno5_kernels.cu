@@ -1057,6 +1057,102 @@ void launch_ct_centers_entropy(const double *bxn, const double *byn, double *con
     ct_centers_entropy_kernel<<<grid, block, 0, s>>>(a, bxn, byn);
 }
 
+// Stage 4 only: the same pass also yields the wave-speed maxima of the NEW state, i.e. compute_global_vmax
+// (Weno5_2D.jl:1942-1984) of the next step's timestep() call -- the thread holds rho, M, B, S of its cell
+// anyway; the x-face averages need the right-hand neighbour, which comes through shared memory.  A block owns
+// 63 columns, its 64th thread evaluates the neighbour column redundantly (not written); at the last interior
+// column the neighbour is the ghost cell bc_fill is about to create, i.e. the image of cell G (periodic) or the
+// column itself (outflow).  Saves the separate 64 B/cell vmax pass once per step.  Same expressions as
+// vmax_kernel, bit-identical maxima.
+__global__ void ct_centers_entropy_vmax_kernel(const EntArgs a, const double *__restrict__ bxn, const double *__restrict__ byn,
+                                               int xhi_side, unsigned long long *out)
+{
+    if (a.dtp && *a.dtp == 0.0) return;
+    __shared__ double sh[7][4][64];
+    __shared__ unsigned long long sx[8], sy[8];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int i = blockIdx.x * 63 + tx + G;
+    const int j = blockIdx.y * blockDim.y + ty + G;
+    const int iend = a.NXI - G;                        // first ghost column
+    const bool row_ok = j < a.NYI - G;
+    int ie = i;
+    if (i == iend) ie = xhi_side == SIDE_PERIODIC ? G : iend - 1;
+    const bool eval = row_ok && i <= iend;
+    const bool own = row_ok && i < iend && tx < 63;
+    double rho = 1.0, mx = 0.0, my = 0.0, bx = 0.0, by = 0.0, bz = 0.0, S = 0.0;
+    if (eval) {
+        const size_t g = (size_t)ie + (size_t)a.pitch * j;
+        const size_t pitch = (size_t)a.pitch;
+        bx = (-bxn[g - 2] + 9.0 * bxn[g - 1] + 9.0 * bxn[g] - bxn[g + 1]) / 16.0;
+        by = (-byn[g - 2 * pitch] + 9.0 * byn[g - pitch] + 9.0 * byn[g] - byn[g + pitch]) / 16.0;
+        rho = a.q[C_RHO][g]; mx = a.q[C_MX][g]; my = a.q[C_MY][g];
+        const double mz = a.q[C_MZ][g];
+        bz = a.q[C_BZ][g];
+        double E2;
+        e2s_s2e(rho, mx, my, mz, bx, by, bz, a.q[C_E][g], a.gam, S, E2);
+        if (own) {
+            a.q[C_BX][g] = bx;
+            a.q[C_BY][g] = by;
+            a.q[C_S][g] = S;
+            if (a.roundtrip) a.q[C_E][g] = E2;
+        }
+    }
+    sh[0][ty][tx] = rho; sh[1][ty][tx] = mx; sh[2][ty][tx] = my; sh[3][ty][tx] = bx;
+    sh[4][ty][tx] = by; sh[5][ty][tx] = bz; sh[6][ty][tx] = S;
+    __syncthreads();
+    double vxm = 0.0, vym = 0.0;
+    if (own) {
+        const int t1 = tx + 1;
+        const double rf = (rho + sh[0][ty][t1]) / 2;
+        const double ri = fast_rcp(rf);
+        const double vx = (mx + sh[1][ty][t1]) / 2 * ri;
+        const double vy = (my + sh[2][ty][t1]) / 2 * ri;
+        const double Bx = (bx + sh[3][ty][t1]) / 2;
+        const double By = (by + sh[4][ty][t1]) / 2;
+        const double Bz = (bz + sh[5][ty][t1]) / 2;
+        const double Sf = (S + sh[6][ty][t1]) / 2;
+        const double pres = Sf * pow_gm1(rf, a.gam);
+        const double cs2 = a.gam * fabs(pres * ri);
+        const double B2 = Bx * Bx + By * By + Bz * Bz;
+        const double bbn2 = B2 * ri, bnx2 = Bx * Bx * ri, bny2 = By * By * ri;
+        const double sm = bbn2 + cs2;
+        const double rootx = fast_sqrt(fmax(0.0, sm * sm - 4 * bnx2 * cs2));
+        const double rooty = fast_sqrt(fmax(0.0, sm * sm - 4 * bny2 * cs2));
+        vxm = fabs(vx) + fast_sqrt(0.5 * (sm + rootx));
+        vym = fabs(vy) + fast_sqrt(0.5 * (sm + rooty));
+        if (sm != sm) { vxm = sm; vym = sm; }
+    }
+    unsigned long long bx_ = (unsigned long long)__double_as_longlong(vxm);
+    unsigned long long by_ = (unsigned long long)__double_as_longlong(vym);
+    if (vxm != vxm || vxm < 0.0) bx_ = ~0ull;
+    if (vym != vym || vym < 0.0) by_ = ~0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        bx_ = max(bx_, __shfl_xor_sync(0xffffffffu, bx_, o));
+        by_ = max(by_, __shfl_xor_sync(0xffffffffu, by_, o));
+    }
+    const int tid = ty * 64 + tx;
+    if ((tid & 31) == 0) { sx[tid >> 5] = bx_; sy[tid >> 5] = by_; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < 8; ++w) { bx_ = max(bx_, sx[w]); by_ = max(by_, sy[w]); }
+        atomicMax(out, bx_);
+        atomicMax(out + 1, by_);
+    }
+}
+
+void launch_ct_centers_entropy_vmax(const double *bxn, const double *byn, double *const q9[9], const Geom &g, double gam,
+                                    int roundtrip, const double *dtp, int xhi_side, unsigned long long *vmax_out,
+                                    cudaStream_t s)
+{
+    EntArgs a;
+    for (int k = 0; k < 9; ++k) a.q[k] = q9[k];
+    a.NXI = g.NXI; a.NYI = g.NYI; a.pitch = g.pitch; a.gam = gam; a.roundtrip = roundtrip;
+    a.all_cells = 0; a.dtp = dtp;
+    dim3 block(64, 4), grid((g.NXI - 2 * G + 62) / 63, (g.NYI - 2 * G + 3) / 4);
+    ct_centers_entropy_vmax_kernel<<<grid, block, 0, s>>>(a, bxn, byn, xhi_side, vmax_out);
+}
+
 void launch_entropy(double *const q9[9], const Geom &g, double gam, int roundtrip, int all_cells,
                     const double *dtp, cudaStream_t s)
 {
@@ -1199,10 +1295,13 @@ void launch_vmax_rows(const double *const q9[9], const Geom &g, double gam, unsi
 
 // timestep(), Weno5_2D.jl:1930-1940; 1-D: dt = courFac*dx/vmax (Weno5_1D.jl:55).
 // With tmax > 0 the step is shortened to land on tmax and becomes 0 once t >= tmax.
-__global__ void dt_kernel(const unsigned long long *vb, double *ctl, double dx, double dy, double cfl, int is1d)
+__global__ void dt_kernel(unsigned long long *vb, double *ctl, double dx, double dy, double cfl, int is1d, int clear)
 {
     const double vx = __longlong_as_double((long long)vb[0]);
     const double vy = __longlong_as_double((long long)vb[1]);
+    if (clear) { vb[0] = 0ull; vb[1] = 0ull; }             // accumulator of the fused stage-4 reduction: ready for the next step
+    const double t = ctl[1], tmax = ctl[4];
+    if (tmax > 0.0 && t >= tmax) { ctl[0] = 0.0; return; } // finished: the kernels of further steps return at once
     ctl[2] = vx; ctl[3] = vy;
     double dt;
     if (is1d) {
@@ -1212,18 +1311,14 @@ __global__ void dt_kernel(const unsigned long long *vb, double *ctl, double dx, 
         dt = cfl / (1 / dtx + 1 / dty);
     }
     if (!(dt > 0.0) || !(dt < 1e300)) { ctl[6] = 1.0; dt = 0.0; }
-    const double t = ctl[1], tmax = ctl[4];
-    if (tmax > 0.0) {
-        if (t >= tmax) dt = 0.0;
-        else if (t + dt > tmax) dt = tmax - t;
-    }
+    if (tmax > 0.0 && t + dt > tmax) dt = tmax - t;
     ctl[0] = dt;
 }
 
-void launch_dt_from_vmax(const unsigned long long *vmax_bits, double *ctl, double dx, double dy, double cfl,
-                         int is1d, cudaStream_t s)
+void launch_dt_from_vmax(unsigned long long *vmax_bits, double *ctl, double dx, double dy, double cfl,
+                         int is1d, int clear, cudaStream_t s)
 {
-    dt_kernel<<<1, 1, 0, s>>>(vmax_bits, ctl, dx, dy, cfl, is1d);
+    dt_kernel<<<1, 1, 0, s>>>(vmax_bits, ctl, dx, dy, cfl, is1d, clear);
 }
 
 __global__ void advance_time_kernel(double *ctl)

@@ -96,6 +96,10 @@ void launch_flux_select(const double *flag, const double *fsyE, const double *gs
                         const Geom &g, const double *dtp, cudaStream_t s);
 void launch_ct_centers_entropy(const double *bxn, const double *byn, double *const q9[9], const Geom &g, double gam,
                                int roundtrip, const double *dtp, cudaStream_t s);
+// stage 4: the same pass + wave-speed maxima of the new state (atomicMax into vmax_out[0..1])
+void launch_ct_centers_entropy_vmax(const double *bxn, const double *byn, double *const q9[9], const Geom &g, double gam,
+                                    int roundtrip, const double *dtp, int xhi_side, unsigned long long *vmax_out,
+                                    cudaStream_t s);
 void launch_entropy(double *const q9[9], const Geom &g, double gam, int roundtrip, int all_cells,
                     const double *dtp, cudaStream_t s);
 void launch_vmax(const double *const q9[9], const Geom &g, double gam, unsigned long long *vmax_bits,
@@ -103,8 +107,9 @@ void launch_vmax(const double *const q9[9], const Geom &g, double gam, unsigned 
 void launch_vmax_rows(const double *const q9[9], const Geom &g, double gam, unsigned long long *vmax_bits, int j0, int j1,
                       int zero_first, cudaStream_t s);
 // ctl[0]=dt ctl[1]=t ctl[2]=vxmax ctl[3]=vymax ctl[4]=tmax ctl[5]=steps_done ctl[6]=bad-flag
-void launch_dt_from_vmax(const unsigned long long *vmax_bits, double *ctl, double dx, double dy,
-                         double cfl, int is1d, cudaStream_t s);
+// clear = 1: zero the two maxima after reading them (accumulator of the fused stage-4 reduction)
+void launch_dt_from_vmax(unsigned long long *vmax_bits, double *ctl, double dx, double dy,
+                         double cfl, int is1d, int clear, cudaStream_t s);
 void launch_advance_time(double *ctl, cudaStream_t s);
 void launch_center2face(const double *Bx, const double *By, double *bxb, double *byb, const Geom &g,
                         cudaStream_t s);

@@ -265,6 +265,55 @@ def test_orszag_tang_full_size_invariants(n):
     assert np.isfinite(qs).all() and qs[..., 0].min() > 0
 
 
+@pytest.mark.parametrize("n,steps", [(2048, 3), (4096, 1)])
+def test_orszag_tang_full_size_parity_vs_oracle(n, steps):
+    """BASELINE config 3 (2048^2, 3 steps) and the bench / roofline size (4096^2, 1 step) against the CPU oracle on
+    the same input, every step with its own CFL time step on both sides: relative L1 <= 1e-8 on every component
+    (Orszag-Tang has degenerate faces, so L1 as north_star prescribes; the L-inf figure is printed)."""
+    g, q, bx, by = pr.orszag_tang(n)
+    with Solver(g) as s:
+        s.upload(q, bx, by)
+        t, nst = s.advance(steps)
+        qg, bxg, byg = s.download()
+    qo, bxo, byo, to = O.advance_2d(g, q, bx, by, steps, fast=True)
+    assert nst == steps and abs(t - to) <= 1e-12 * to, (t, to)
+    worst = 0.0
+    for c in ALL9:
+        a, b = interior(qg[..., c]), interior(qo[..., c])
+        scale = max(np.abs(b).mean(), 1e-3)           # Mz, Bz vanish identically in this problem
+        e1 = float(np.abs(a - b).mean() / scale)
+        worst = max(worst, float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-3)))
+        assert e1 <= 1e-8, (c, e1)
+    assert rel_l1(interior(bxg), interior(bxo)) <= 1e-8 and rel_l1(interior(byg), interior(byo)) <= 1e-8
+    print(f"orszag_tang {n}^2 x {steps}: worst relative L-inf vs oracle {worst:.3e}")
+
+
+@pytest.mark.parametrize("case", ["periodic", "outflow"])
+def test_fused_cfl_reduction_equals_stepwise(case):
+    """weno5_advance() takes the wave-speed maxima of step k+1 from stage 4 of step k (ct_centers_entropy_vmax:
+    no separate pass over the state); the result must equal timestep() -> classical_RK4_step() called step by
+    step, bit for bit -- widths that are no multiple of the kernel's 63-column blocks, both boundary types."""
+    if case == "periodic":
+        g, q, bx, by = pr.orszag_tang(100, ny=76, ysize=0.76)
+    else:
+        g, q, bx, by = pr.shock_cloud(130, 50, xsize=2.6, ysize=1.0)
+    with Solver(g) as s:
+        s.upload(q, bx, by)
+        t_adv, n = s.advance(4)
+        qa, bxa, bya = s.download()
+    assert n == 4
+    with Solver(g) as s:
+        s.upload(q, bx, by)
+        t = 0.0
+        for _ in range(4):
+            dt = s.timestep()[0]
+            s.rk4_step(dt)
+            t += dt
+        qb, bxb_, byb_ = s.download()
+    assert t_adv == t
+    assert np.array_equal(qa, qb) and np.array_equal(bxa, bxb_) and np.array_equal(bya, byb_)
+
+
 def test_tma_and_ldgsts_staging_agree_to_roundoff(tmp_path):
     """Three instantiations of the flux sweep: the warp-specialised kernel (default, WENO5_FLUX_VARIANT=5: face
     warps + helper warps, TMA staging), the single-role kernel with TMA staging (4) and with
