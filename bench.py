@@ -16,11 +16,15 @@ value   device-resident throughput: state already in HBM, K steps of weno5_advan
 e2e     the same metric through the reference-shaped call sequence with HOST buffers:
         upload(q,bxb,byb) -> timestep() -> classical_RK4_step(dt) -> download(), every step,
         pinned host memory, copies inside the timed region.
-roofline  the dominant kernel is flux_kernel<DIR> (8 launches per step); algorithmic bytes per
-        launch = 1048 B/cell-update / 8 launches * cells; duration from CUDA events
-        recorded around every flux launch inside the timed region.
+roofline  the dominant kernel is the flux sweep (flux_ws_kernel<DIR>, 8 launches per step); algorithmic
+        bytes per launch = 1048 B/cell-update / 8 launches * cells; duration from CUDA events
+        recorded around every flux launch inside the timed region.  The binding roof is the FP64 pipe
+        (bound = "fp64"); achieved/peak/frac stay the HBM figures the metric asks for.
 cpu_baseline  the C oracle (oracle/, "port": the Julia reference cannot run here), OpenMP on
         all host cores, on a bounded sample (rank 0, N=1 only).
+strong  BASELINE config 4 (Orszag-Tang 8192^2 global, 8192/N rows per GPU) timed for a few steps in the same
+        run; at N=8 also config 5 (blast wave 16384^2).  N>1 runs start with the slab bit-identity
+        pre-check (julia_b200/slabcheck.py) whose outcome is part of the line.
 """
 import argparse
 import ctypes as C
@@ -41,7 +45,10 @@ NY_PER_GPU = 4096
 ALGO_BYTES_PER_CELL_UPDATE = 1048.0
 ALGO_FLOPS_PER_CELL_UPDATE = 22.0e3          # SURVEY.md 8d (FMA = 2)
 FLUX_LAUNCHES_PER_STEP = 8
-FP64_PEAK_TFLOPS_NOMINAL = 37.2              # 148 SM x 64 DFMA/clk x 1.965 GHz
+FP64_DFMA_PER_CLK = 148 * 64                 # B200: 148 SMs x 64 DFMA per clock
+FP64_PEAK_TFLOPS_MEASURED = 37.0             # profiles/fp64_peak.txt (scripts/microbench/fp64_peak.cu on this pool's B200)
+# the CPU arm times an n x n Orszag-Tang sample, the same at every N (the environment knob exists for the host-side test)
+REF_SAMPLE_N = int(os.environ.get("WENO5_REF_SAMPLE_N", "2048"))
 
 
 def measured_peaks():
@@ -120,6 +127,7 @@ def oracle_rate(n, steps, fast=True):
 
 
 def cpu_baseline(budget_s=15.0):
+    host_threads()
     from oracle import oracle_c as O
     O.build()
     rate, _ = oracle_rate(256, 1)
@@ -141,20 +149,32 @@ def cpu_baseline(budget_s=15.0):
     return out
 
 
+def host_threads():
+    """All host cores for the CPU arm, at every N: torchrun exports OMP_NUM_THREADS=1 to its workers, which would
+    leave the oracle on one thread (round-1 SCALE record).  Set before the oracle's OpenMP runtime starts, and
+    again through libgomp in case it already has."""
+    n = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    os.environ.pop("OMP_THREAD_LIMIT", None)
+    try:
+        C.CDLL("libgomp.so.1").omp_set_num_threads(n)
+    except OSError:
+        pass
+    return n
+
+
 def run_reference(args):
     """The reference's own CPU implementation cannot run natively (Julia 0.6 source, no julia binary): this
     arm times the oracle port of it (bit-identical numerics, tests/test_reference_pin.py) on all host cores, on a
-    bounded sample of the workload."""
+    bounded sample of the workload -- the same sample and the same thread count whatever N is."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    want = host_threads()
     from oracle import oracle_c as O
     O.build()
-    rate0, _ = oracle_rate(256, 1)
-    total_steps = args.steps + args.warmup
-    budget = 90.0
-    n = int(max(256, min(2048, (rate0 * budget / max(total_steps, 1)) ** 0.5 // 64 * 64)))
     from julia_b200 import problems as pr
+    n = REF_SAMPLE_N
     g, q, bx, by = pr.orszag_tang(n)
     q, bx, by, _ = O.advance_2d(g, q, bx, by, args.warmup, fast=True)
     t0 = time.time()
@@ -162,13 +182,16 @@ def run_reference(args):
     dt = time.time() - t0
     value = n * n * args.steps / dt
     cores = O.num_threads(True)
-    sample = f"orszag_tang {n}x{n} (sample of the 4096x4096-per-GPU workload), {args.steps} RK4 steps incl. timestep"
+    sample = (f"orszag_tang {n}x{n} (bounded sample of the {NX_PER_GPU}x{NY_PER_GPU}-per-GPU workload; the rate is per "
+              f"cell-update, so it is size-normalised), {args.steps} RK4 steps incl. timestep, {cores} OpenMP threads")
     line = {
         "impl": "reference", "metric": "cell_updates_per_sec", "value": value, "unit": "cell-updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "ms_per_step_of": f"the {n}x{n} sample", "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
         "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "cell-updates/s", "cores": cores, "kind": "port", "sample": sample,
+                         "host_cpus": os.cpu_count(), "threads_requested": want},
         "e2e": {"value": value, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "no julia binary exists here (Julia 0.6 source); the reference only runs through the mechanical "
@@ -176,6 +199,8 @@ def run_reference(args):
                 "Julia, not a meaningful timing).  Timed instead: the C port of its E-branch numerics, which "
                 "tests/test_reference_pin.py shows to be bit-identical to it, OpenMP over lines, all host threads",
     }
+    if cores <= 1 and (os.cpu_count() or 1) > 1:
+        line["warning"] = "the CPU arm ran on ONE thread of a multi-core host: this line is not comparable"
     print(json.dumps(line), flush=True)
 
 
@@ -185,6 +210,8 @@ def workload_config(ngpu):
             "nx": NX_PER_GPU, "ny_global": NY_PER_GPU * ngpu, "partition": f"y-slabs x{ngpu}",
             "l2": "no flush needed: ~6.5 GB of resident planes per GPU >> 126 MB L2",
             "es_roundtrip": 1,
+            "reference_arm_sample": f"--impl reference times an orszag_tang {REF_SAMPLE_N}x{REF_SAMPLE_N} sample of this "
+                                    "workload on all host threads, at every N (rate per cell-update)",
             "note": "E <- S2E(E2S(E)) after every stage, exactly as the 2-D reference's ES_Switch does "
                     "(Weno5_2D.jl:1738,1765); --es-roundtrip 0 selects the 1-D reference's form (keeps E, ~3.5% faster)"}
 
@@ -229,9 +256,14 @@ def run_e2e(args, lib, L, s, q, bx, by, gglob, local, world, cells_global, nyl, 
         e2e_s = float(tt.item())
     bytes_dir = 11 * q.shape[0] * q.shape[1] * 8
     e2e_seq = {"value": cells_global * e2e_steps / e2e_s, "unit": "cell-updates/s", "h2d_bytes_per_step": bytes_dir,
-               "d2h_bytes_per_step": bytes_dir, "steps": e2e_steps,
+               "d2h_bytes_per_step": bytes_dir, "steps": e2e_steps, "path": "sequential",
                "calls": "weno5_upload -> weno5_timestep -> weno5_rk4_step -> weno5_download, pinned host arrays"}
     e2e = e2e_seq
+    if world > 1:
+        e2e["path_note"] = ("N > 1: every rank moves its own slab host<->device around each step (sequential calls, NCCL "
+                            "halo exchange inside the step); the pipelined single-call path (weno5_pipe_step, the N = 1 "
+                            "figure) streams ONE grid through ONE GPU and has no multi-GPU form -- compare this number "
+                            "with e2e.sequential of the N = 1 line")
 
     # single GPU: the pipelined host step (y-slabs with overlap rows; H2D, compute and D2H overlap)
     if world == 1 and nyl >= 1024:
@@ -257,6 +289,7 @@ def run_e2e(args, lib, L, s, q, bx, by, gglob, local, world, cells_global, nyl, 
         up_rows = nslab * (rows + 2 * 16 + 8)
         e2e = {"value": cells_global * psteps / pipe_s, "unit": "cell-updates/s",
                "h2d_bytes_per_step": 10 * q.shape[0] * up_rows * 8, "d2h_bytes_per_step": bytes_dir, "steps": psteps,
+               "path": "pipelined",
                "calls": "weno5_pipe_step(q0,bxb0,byb0,dt) -> (q4,bxb4,byb4,dt_next): host arrays in, host arrays out, "
                         f"{nslab} y-slabs of {rows}+32 rows on 3 streams (copies and compute overlap), pinned host arrays; "
                         "the S plane is not uploaded (output only)",
@@ -266,6 +299,71 @@ def run_e2e(args, lib, L, s, q, bx, by, gglob, local, world, cells_global, nyl, 
     for p in (pq, pbx, pby):
         lib.weno5_host_free(p)
     return e2e
+
+
+STRONG_N1_CACHE = os.path.join(ROOT, "gpurun_out", "strong_n1.json")
+
+
+def run_strong(problem, nx, ny_global, steps, rank, world, local, lib, torch, dist, sync_all, es_roundtrip):
+    """BASELINE configs 4/5: a FIXED global grid cut into world y-slabs, timed like the main leg (CUDA events on the
+    solver's stream, barrier + synchronize on both sides, max over ranks).  The N = 1 time of the same grid is left
+    in gpurun_out/strong_n1.json so that the N > 1 runs of the same session can state their efficiency."""
+    from julia_b200 import partition as pt
+    from julia_b200 import problems as pr
+    from julia_b200.solver import Solver
+    nyl = ny_global // world
+    ysz = float(ny_global) / nx
+    gglob = pr.Grid(nx=nx, ny=ny_global, xsize=1.0, ysize=ysz, bc_x=pr.PERIODIC, bc_y=pr.PERIODIC)
+    _, q, bx, by = getattr(pr, problem)(nx, ny=nyl, ysize=float(nyl) / nx, y0=float(rank) * nyl / nx)
+    s = Solver(gglob, device=local, ny_local=nyl, j_offset=rank * nyl, es_roundtrip=bool(es_roundtrip))
+    try:
+        if world > 1:
+            uid = pt.broadcast_unique_id(Solver.comm_unique_id, rank, dist)
+            s.comm_init(rank, world, uid)
+        s.upload(q, bx, by)
+        del q, bx, by
+        stream = torch.cuda.ExternalStream(lib.weno5_stream(s.h), device=torch.device("cuda", local))
+        s.advance(3)
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        _, ndone = s.advance(steps)
+        e1.record(stream)
+        sync_all()
+        ms = e0.elapsed_time(e1)
+        assert ndone == steps
+    finally:
+        s.close()
+    if world > 1:
+        tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    key = f"{problem}_{nx}x{ny_global}"
+    out = {"workload": f"{problem} {nx}x{ny_global} global, {nyl} rows per GPU, periodic", "steps": steps, "warmup": 3,
+           "ms_per_step": ms / steps, "value": nx * ny_global * steps / (ms * 1e-3), "unit": "cell-updates/s",
+           "efficiency_vs_n1": None}
+    if rank == 0:
+        cache = {}
+        try:
+            with open(STRONG_N1_CACHE) as f:
+                cache = json.load(f)
+        except (OSError, ValueError):
+            pass
+        if world == 1:
+            cache[key] = {"ms_per_step": ms / steps, "when": time.time()}
+            try:
+                os.makedirs(os.path.dirname(STRONG_N1_CACHE), exist_ok=True)
+                with open(STRONG_N1_CACHE, "w") as f:
+                    json.dump(cache, f)
+            except OSError:
+                pass
+            out["efficiency_vs_n1"] = 1.0
+        elif key in cache and time.time() - cache[key].get("when", 0) < 6 * 3600:
+            t1 = cache[key]["ms_per_step"]
+            out["efficiency_vs_n1"] = t1 / (world * ms / steps)
+            out["n1_ms_per_step"] = t1
+            out["n1_source"] = "gpurun_out/strong_n1.json, written by the N=1 run of this session"
+    return out
 
 
 def run_gpu(args):
@@ -288,6 +386,13 @@ def run_gpu(args):
     from julia_b200 import problems as pr
     from julia_b200.solver import Solver
     lib = L.load()
+
+    # N > 1: slab-decomposed results must equal the one-GPU results bit for bit (4 cases, see julia_b200/slabcheck.py)
+    slab_check = None
+    if world > 1 and not args.no_slab_check:
+        from julia_b200 import slabcheck
+        slab_check = slabcheck.run_all(rank, world, local, dist)
+        dist.barrier()
 
     nx, nyl = args.nx, args.ny
     gglob = pr.Grid(nx=nx, ny=nyl * world, xsize=1.0, ysize=float(world) * nyl / nx, bc_x=pr.PERIODIC, bc_y=pr.PERIODIC)
@@ -343,6 +448,17 @@ def run_gpu(args):
 
     if rank == 0:
         sampler.stop()
+    s.close()
+
+    strong = None
+    if args.strong_steps > 0 and (nx, nyl, args.problem) == (NX_PER_GPU, NY_PER_GPU, "orszag_tang"):
+        strong = {"config4": run_strong("orszag_tang", 8192, 8192, args.strong_steps, rank, world, local, lib, torch, dist,
+                                        sync_all, args.es_roundtrip)}
+        if world == 8:
+            strong["config5"] = run_strong("blast", 16384, 16384, args.strong_steps, rank, world, local, lib, torch, dist,
+                                           sync_all, args.es_roundtrip)
+
+    if rank == 0:
         clocks = sampler.summary(t_wall0, t_wall1)
         peak, how = measured_peaks()
         flux_avg_ms = flux_ms / max(flux_n, 1)
@@ -353,7 +469,13 @@ def run_gpu(args):
         if os.path.exists(tp):
             with open(tp) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch")
+        step_traffic, pipe_pct = None, None
+        if os.path.exists(tp):
+            with open(tp) as f:
+                tj = json.load(f)
+            step_traffic, pipe_pct = tj.get("step_dram_bytes"), tj.get("fp64_pipe_pct")
         fp64_tflops = ALGO_FLOPS_PER_CELL_UPDATE * cells_local * args.steps / (ms * 1e-3) / 1e12
+        fp64_peak_clock = (FP64_DFMA_PER_CLK * 2 * clocks["sm_mhz"] * 1e6 / 1e12) if clocks.get("sm_mhz") else None
         line = {
             "metric": "cell_updates_per_sec", "value": value, "unit": "cell-updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -363,23 +485,35 @@ def run_gpu(args):
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": how, "kernel": "flux_kernel<0|1> (x and y sweeps)",
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "traffic_source": "profiles/flux_kernel_traffic.json: dram__bytes_read+write per "
+                                                               "launch of the committed ncu --set full capture (not of this run)",
+                         "peak_source": how, "kernel": "flux_ws_kernel<0|1> (x and y sweeps)",
                          "avg_launch_ms": flux_avg_ms, "launches_timed": int(flux_n),
                          "algorithmic_bytes_per_launch": algo_bytes_launch,
                          "share_of_step": flux_ms / ms,
                          "whole_step_frac": ALGO_BYTES_PER_CELL_UPDATE * cells_local * args.steps / (ms * 1e-3) / 1e9 / peak,
-                         "fp64": {"achieved_tflops": fp64_tflops, "peak_tflops_nominal": FP64_PEAK_TFLOPS_NOMINAL,
-                                  "frac": fp64_tflops / FP64_PEAK_TFLOPS_NOMINAL,
-                                  "note": "FP64 pipe is the binding roof (SURVEY 8d): 22 kflop vs 1048 B per cell-update"}},
+                         "step_traffic": step_traffic,
+                         "fp64": {"achieved_tflops": fp64_tflops, "peak_tflops": FP64_PEAK_TFLOPS_MEASURED,
+                                  "peak_source": "measured, profiles/fp64_peak.txt",
+                                  "peak_tflops_at_sampled_clock": fp64_peak_clock,
+                                  "frac": fp64_tflops / FP64_PEAK_TFLOPS_MEASURED,
+                                  "pipe_pct_ncu": pipe_pct,
+                                  "note": "FP64 pipe is the binding roof (SURVEY 8d): 22 kflop vs 1048 B per cell-update; "
+                                          "achieved/peak/frac above are the HBM figures the metric asks for; pipe_pct_ncu = "
+                                          "sm__inst_executed_pipe_fp64 of the committed ncu capture (x, y sweep)"}},
             "sim": {"t_end": t_end},
         }
+        if strong is not None:
+            line["strong"] = strong
+        if slab_check is not None:
+            line["slab_bit_identical"] = slab_check["slab_bit_identical"]
+            line["slab_check"] = slab_check
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline()
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)
-    s.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -397,6 +531,8 @@ def main():
                     help="synthetic workload (BASELINE configs 3/4: orszag_tang, config 5: blast)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--strong-steps", type=int, default=4, help="timed steps of the strong-scaling leg (0: skip)")
+    ap.add_argument("--no-slab-check", action="store_true", help="N > 1: skip the slab bit-identity pre-check")
     ap.add_argument("--es-roundtrip", type=int, default=1, help="1: E <- S2E(E2S(E)) after every stage (2-D reference form)")
     args = ap.parse_args()
     if args.warmup < 3:

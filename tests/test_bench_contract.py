@@ -46,3 +46,20 @@ def test_cpu_baseline_object_shape():
     b = bench.cpu_baseline(budget_s=1.0)
     assert b["kind"] == "port" and b["unit"] == "cell-updates/s" and b["cores"] >= 1 and b["value"] > 0
     assert "orszag_tang" in b["sample"] and json.dumps(b)
+
+
+def test_reference_arm_uses_all_host_threads_under_torchrun():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must still use every host core, report how
+    many, and time the same sample at every N (round-1 SCALE record: 1 thread at N >= 2)."""
+    lines = {}
+    for n in (1, 4):
+        env = dict(os.environ, RANK="0", WORLD_SIZE=str(n), OMP_NUM_THREADS="1", WENO5_REF_SAMPLE_N="128")
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", str(n),
+                            "--steps", "1"], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        lines[n] = json.loads(r.stdout.strip().splitlines()[-1])
+    for n, d in lines.items():
+        assert d["impl"] == "reference" and d["n_gpus"] == n
+        assert d["cpu_baseline"]["cores"] == (os.cpu_count() or 1), d["cpu_baseline"]
+        assert "128x128" in d["cpu_baseline"]["sample"] and "warning" not in d
+    assert lines[1]["cpu_baseline"]["sample"] == lines[4]["cpu_baseline"]["sample"]
