@@ -402,6 +402,7 @@ def run_gpu(args):
         uid = pt.broadcast_unique_id(Solver.comm_unique_id, rank, dist)
         s.comm_init(rank, world, uid)
     s.upload(q, bx, by)
+    halo_mode = {0: "none (one GPU)", 1: "nccl send/recv, packed messages", 2: "peer-memory push (CUDA IPC), one kernel per stage"}[s.halo_mode()]
     stream = torch.cuda.ExternalStream(lib.weno5_stream(s.h), device=torch.device("cuda", local))
 
     def sync_all():
@@ -503,6 +504,7 @@ def run_gpu(args):
                                           "achieved/peak/frac above are the HBM figures the metric asks for; pipe_pct_ncu = "
                                           "sm__inst_executed_pipe_fp64 of the committed ncu capture (x, y sweep)"}},
             "sim": {"t_end": t_end},
+            "halo_exchange": halo_mode,
         }
         if strong is not None:
             line["strong"] = strong

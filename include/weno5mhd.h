@@ -71,6 +71,11 @@ int weno5_destroy(weno5_ctx *ctx);
  * distributed by the host program (Julia Distributed / MPI / torch.distributed). */
 int weno5_comm_unique_id(unsigned char id[128]);
 int weno5_comm_init(weno5_ctx *ctx, int rank, int nranks, const unsigned char id[128]);
+/* How the ghost rows travel: 0 no communicator, 1 NCCL send/recv through packed messages, 2 direct stores into
+ * the neighbours' ghost rows over peer memory (CUDA IPC, one process per GPU on one node; the default whenever
+ * every rank can map its neighbours -- WENO5_HALO=nccl in the environment forces 1).  The max-allreduce of the
+ * wave speeds (timestep, Weno5_2D.jl:1930) is NCCL in both modes. */
+int weno5_comm_halo_mode(const weno5_ctx *ctx);
 
 /* ---- state transfer.  Host arrays cover the LOCAL slab: (Nx, ny_local+6, 9) etc. */
 /* q/bxb/byb as produced by initial_conditions() (Weno5_2D.jl:2001) and

@@ -15,6 +15,7 @@
 // ACC = -q0 + q1 + 2 q2 accumulated while q1, q2 are read anyway.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <unistd.h>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -53,8 +54,8 @@ static int fail(int code, const char *fmt, ...)
 typedef struct ncclComm *ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 enum { ncclSuccess = 0 };
-enum { ncclFloat64 = 8, ncclUint64 = 5 };
-enum { ncclMax = 2 };
+enum { ncclFloat64 = 8, ncclUint64 = 5, ncclUint8 = 1 };
+enum { ncclMax = 2, ncclMin = 3 };
 
 struct NcclApi {
     void *h = nullptr;
@@ -64,6 +65,7 @@ struct NcclApi {
     int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
@@ -84,7 +86,7 @@ static int nccl_load()
     *(void **)(&g_nccl.field) = dlsym(h, name);                                            \
     if (!g_nccl.field) return fail(WENO5_ERR_NCCL, "libnccl lacks symbol %s", name);
     SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
-    SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(AllReduce, "ncclAllReduce")
+    SYM(Send, "ncclSend") SYM(Recv, "ncclRecv") SYM(AllReduce, "ncclAllReduce") SYM(AllGather, "ncclAllGather")
     SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
     g_nccl.h = h;
@@ -134,6 +136,14 @@ struct weno5_ctx {
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
     int up = -1, down = -1;          // neighbour ranks (-1: none)
+    // halo push over peer memory (default; NCCL send/recv is the fallback): the neighbours' plane pools and flag
+    // words mapped through CUDA IPC, a sequence number per exchange
+    bool peer_ok = false;
+    double *peer_pool_up = nullptr, *peer_pool_down = nullptr;
+    unsigned long long *peer_flags_up = nullptr, *peer_flags_down = nullptr;
+    int peer_ny_up = 0, peer_ny_down = 0;
+    unsigned long long *sync_flags = nullptr;    // [0] last push from below, [1] from above, [2] block counter
+    unsigned long long xseq = 0, peer_wait_seq = 0;
     // instrumentation
     unsigned long long launches = 0;
     bool profiling = false;
@@ -350,7 +360,13 @@ extern "C" int weno5_destroy(weno5_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
+    if (c->peer_pool_up) cudaIpcCloseMemHandle(c->peer_pool_up);
+    if (c->peer_pool_down && c->peer_pool_down != c->peer_pool_up) cudaIpcCloseMemHandle(c->peer_pool_down);
+    if (c->peer_flags_up) cudaIpcCloseMemHandle(c->peer_flags_up);
+    if (c->peer_flags_down && c->peer_flags_down != c->peer_flags_up) cudaIpcCloseMemHandle(c->peer_flags_down);
+    cudaGetLastError();
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    cudaFree(c->sync_flags);
     if (c->dual_pool) cudaFree(c->dual_pool);
     if (c->ev_main) cudaEventDestroy(c->ev_main);
     if (c->ev_comm) cudaEventDestroy(c->ev_comm);
@@ -374,6 +390,69 @@ extern "C" int weno5_comm_unique_id(unsigned char id[128])
     return 0;
 }
 
+// Map the neighbours' plane pools and flag words (CUDA IPC; one process per GPU on one node).  Every rank
+// publishes (IPC handle of its pool, IPC handle of its flag words, its rows) through an NCCL all-gather; if any
+// rank cannot map a neighbour (same process, no peer access, WENO5_HALO=nccl) ALL ranks keep the NCCL
+// send/recv exchange -- the decision is an all-reduce so that both sides of every cut use the same protocol.
+struct PeerBlob { cudaIpcMemHandle_t pool, flags; int ny_local; int pid; };
+
+static int setup_peer_halo(weno5_ctx *c)
+{
+    const int nranks = c->nranks;
+    CU(cudaMalloc(&c->sync_flags, 8 * sizeof(unsigned long long)));
+    CU(cudaMemset(c->sync_flags, 0, 8 * sizeof(unsigned long long)));
+    PeerBlob mine;
+    memset(&mine, 0, sizeof(mine));
+    int ok = getenv("WENO5_HALO") && !strcmp(getenv("WENO5_HALO"), "nccl") ? 0 : 1;
+    if (ok && (cudaIpcGetMemHandle(&mine.pool, c->pool) != cudaSuccess ||
+               cudaIpcGetMemHandle(&mine.flags, c->sync_flags) != cudaSuccess)) { cudaGetLastError(); ok = 0; }
+    mine.ny_local = c->ny_local;
+    mine.pid = (int)getpid();
+    unsigned char *d_all = nullptr;
+    CU(cudaMalloc(&d_all, (size_t)(nranks + 1) * sizeof(PeerBlob)));
+    CU(cudaMemcpy(d_all + (size_t)nranks * sizeof(PeerBlob), &mine, sizeof(mine), cudaMemcpyHostToDevice));
+    NC(g_nccl.AllGather(d_all + (size_t)nranks * sizeof(PeerBlob), d_all, sizeof(PeerBlob), ncclUint8, c->comm, c->comm_stream));
+    CU(cudaStreamSynchronize(c->comm_stream));
+    std::vector<PeerBlob> all(nranks);
+    CU(cudaMemcpy(all.data(), d_all, (size_t)nranks * sizeof(PeerBlob), cudaMemcpyDeviceToHost));
+    auto open = [&](int peer, double *&pool, unsigned long long *&flags, int &ny) {
+        if (peer < 0) return true;
+        if (peer == c->rank || all[peer].pid == mine.pid) return false;          // IPC maps other processes only
+        void *p = nullptr, *f = nullptr;
+        if (cudaIpcOpenMemHandle(&p, all[peer].pool, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return false; }
+        if (cudaIpcOpenMemHandle(&f, all[peer].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            cudaIpcCloseMemHandle(p);
+            return false;
+        }
+        pool = (double *)p; flags = (unsigned long long *)f; ny = all[peer].ny_local;
+        return true;
+    };
+    if (ok) {
+        ok = open(c->up, c->peer_pool_up, c->peer_flags_up, c->peer_ny_up) ? 1 : 0;
+        if (ok && c->down >= 0) {
+            if (c->down == c->up) {                       // two ranks, periodic: the same neighbour on both sides
+                c->peer_pool_down = c->peer_pool_up; c->peer_flags_down = c->peer_flags_up; c->peer_ny_down = c->peer_ny_up;
+            } else {
+                ok = open(c->down, c->peer_pool_down, c->peer_flags_down, c->peer_ny_down) ? 1 : 0;
+            }
+        }
+    }
+    // unanimous or not at all
+    unsigned long long *d_ok = reinterpret_cast<unsigned long long *>(d_all);
+    const unsigned long long h_ok = (unsigned long long)ok;
+    CU(cudaMemcpy(d_ok, &h_ok, sizeof(h_ok), cudaMemcpyHostToDevice));
+    NC(g_nccl.AllReduce(d_ok, d_ok, 1, ncclUint64, ncclMin, c->comm, c->comm_stream));
+    CU(cudaStreamSynchronize(c->comm_stream));
+    unsigned long long agreed = 0;
+    CU(cudaMemcpy(&agreed, d_ok, sizeof(agreed), cudaMemcpyDeviceToHost));
+    CU(cudaFree(d_all));
+    c->peer_ok = agreed != 0;
+    return 0;
+}
+
+extern "C" int weno5_comm_halo_mode(const weno5_ctx *c) { return c && c->comm ? (c->peer_ok ? 2 : 1) : 0; }
+
 extern "C" int weno5_comm_init(weno5_ctx *c, int rank, int nranks, const unsigned char id[128])
 {
     if (!c || !id) return fail(WENO5_ERR_ARG, "null argument");
@@ -394,12 +473,18 @@ extern "C" int weno5_comm_init(weno5_ctx *c, int rank, int nranks, const unsigne
     const bool per = c->P.bc_y == WENO5_BC_PERIODIC;
     c->up = rank + 1 < nranks ? rank + 1 : (per && nranks > 1 ? 0 : -1);
     c->down = rank > 0 ? rank - 1 : (per && nranks > 1 ? nranks - 1 : -1);
+    if (int r = setup_peer_halo(c)) return r;
     return 0;
 }
 
 // make the main stream wait for an exchange that is still in flight on the NCCL stream
 static int wait_exchange(weno5_ctx *c)
 {
+    if (c->peer_wait_seq) {
+        launch_halo_wait(c->sync_flags, c->down >= 0, c->up >= 0, c->peer_wait_seq, c->ctl, c->stream);
+        c->peer_wait_seq = 0;
+        c->launches += 1;
+    }
     if (c->xchg_pending) {
         CU(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
         c->xchg_pending = false;
@@ -419,6 +504,29 @@ static int exchange_rows(weno5_ctx *c, double *const planes[], int n, bool async
     static const bool overlap = getenv("WENO5_OVERLAP_XCHG") != nullptr;
     if (!overlap) async = false;
     const Geom &g = c->g;
+    if (c->peer_ok) {
+        // push the edge rows into the neighbours' ghost rows and raise their flag words; then (or later, async)
+        // wait for the neighbours' pushes of the same sequence number
+        if (int r = wait_exchange(c)) return r;           // at most one exchange in flight
+        PushArgs a;
+        memset(&a, 0, sizeof(a));
+        a.n = n; a.NYI = g.NYI; a.pitch = g.pitch;
+        for (int k = 0; k < n; ++k) { a.src[k] = planes[k]; a.plane_idx[k] = (int)((planes[k] - c->pool) / (ptrdiff_t)g.plane); }
+        a.peer_up = c->up >= 0 ? c->peer_pool_up : nullptr;
+        a.peer_down = c->down >= 0 ? c->peer_pool_down : nullptr;
+        a.plane_up = (size_t)g.pitch * (c->peer_ny_up + 2 * G);
+        a.plane_down = (size_t)g.pitch * (c->peer_ny_down + 2 * G);
+        a.NYI_down = c->peer_ny_down + 2 * G;
+        a.flag_up = c->up >= 0 ? c->peer_flags_up + 0 : nullptr;        // I am its lower neighbour
+        a.flag_down = c->down >= 0 ? c->peer_flags_down + 1 : nullptr;  // I am its upper neighbour
+        a.counter = reinterpret_cast<unsigned int *>(c->sync_flags + 2);
+        a.seq = ++c->xseq;
+        launch_halo_push(a, c->stream);
+        c->launches += 1;
+        c->peer_wait_seq = a.seq;
+        if (!async) return wait_exchange(c);
+        return 0;
+    }
     const size_t cnt = (size_t)G * g.pitch;
     CU(cudaEventRecord(c->ev_main, c->stream));
     CU(cudaStreamWaitEvent(c->comm_stream, c->ev_main, 0));
@@ -635,7 +743,7 @@ static int enqueue_stage(weno5_ctx *c, int stage, State &cur, State &nxt)
     // x sweep
     a.N = g.NXI; a.NP = g.NYI; a.bs = c->fsy;
     a.seg_len = c->segx_len; a.nseg = c->nsegx;
-    if (c->xchg_pending && !g.is1d) {
+    if ((c->xchg_pending || c->peer_wait_seq) && !g.is1d) {
         // ghost rows of `cur` are still arriving: sweep the interior rows now, the ghost rows after
         a.row_mode = 1;
         { ProfScope ps(c); launch_flux_x(a, c->stream); }

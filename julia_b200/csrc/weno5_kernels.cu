@@ -1003,6 +1003,64 @@ void launch_halo_pack(double *const planes[], int n, const Geom &g, double *up, 
     halo_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a, unpack);
 }
 
+// ------------------------------------------------------------------ halo push over peer memory (NVLink)
+// One process per GPU; at weno5_comm_init every rank maps its neighbours' plane pools (CUDA IPC).  A stage's
+// exchange is then ONE kernel that stores this slab's 4 outermost interior rows of every plane straight into
+// the neighbours' ghost rows and, once the last block is done, raises a sequence number in the neighbour's
+// flag word; the neighbour's stream waits for that number with a one-thread kernel before it touches its ghost
+// rows.  No pack / unpack passes, no staging buffers, no NCCL kernel competing for SMs.
+__global__ void halo_push_kernel(const PushArgs a)
+{
+    const size_t per = (size_t)G * a.pitch;                 // doubles per plane and direction
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < per * a.n) {
+        const int k = (int)(e / per);
+        const size_t r = e % per;
+        const double *src = a.src[k];
+        if (a.peer_up) a.peer_up[(size_t)a.plane_idx[k] * a.plane_up + r] = src[(size_t)(a.NYI - 2 * G) * a.pitch + r];
+        if (a.peer_down)
+            a.peer_down[(size_t)a.plane_idx[k] * a.plane_down + (size_t)(a.NYI_down - G) * a.pitch + r] = src[(size_t)G * a.pitch + r];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned done = atomicAdd(a.counter, 1u) + 1u;
+        if (done == gridDim.x) {
+            *a.counter = 0u;
+            __threadfence_system();
+            if (a.flag_up) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.flag_up), "l"(a.seq) : "memory");
+            if (a.flag_down) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.flag_down), "l"(a.seq) : "memory");
+        }
+    }
+}
+
+void launch_halo_push(const PushArgs &a, cudaStream_t s)
+{
+    const size_t total = (size_t)G * a.pitch * a.n;
+    halo_push_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a);
+}
+
+// flags[0]: sequence number of the last push from the lower neighbour, flags[1]: from the upper one.
+// Gives up after ~4 s (a neighbour died): raises the bad-state flag of the control block instead of hanging the GPU.
+__global__ void halo_wait_kernel(const unsigned long long *flags, int need_down, int need_up, unsigned long long seq, double *ctl)
+{
+    const long long t0 = clock64();
+    for (int side = 0; side < 2; ++side) {
+        if (!(side == 0 ? need_down : need_up)) continue;
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + side) : "memory");
+            if (v < seq && clock64() - t0 > 8000000000ll) { ctl[6] = 2.0; return; }
+        } while (v < seq);
+    }
+}
+
+void launch_halo_wait(const unsigned long long *flags, int need_down, int need_up, unsigned long long seq, double *ctl,
+                      cudaStream_t s)
+{
+    halo_wait_kernel<<<1, 1, 0, s>>>(flags, need_down, need_up, seq, ctl);
+}
+
 // ------------------------------------------------------------------ entropy variable
 // ES_Switch residue (Weno5_2D.jl:1737-1765): S = E2S(q); with roundtrip E = S2E(q,S)
 struct EntArgs { double *q[9]; int NXI, NYI, pitch; double gam; int roundtrip; int all_cells; const double *dtp; };

@@ -90,6 +90,21 @@ void launch_bc_fill(double *const planes[], int nplanes, const Geom &g, const in
                     const double *dtp, cudaStream_t s);
 void launch_halo_pack(double *const planes[], int n, const Geom &g, double *up, double *down, int has_up, int has_down,
                       int unpack, cudaStream_t s);
+// halo push over peer memory: edge rows of n planes -> the neighbours' ghost rows, then seq -> their flag words
+struct PushArgs {
+    const double *src[NCELL];    // this slab's planes
+    int plane_idx[NCELL];        // their index in the plane pool (the same on every rank)
+    int n, NYI, pitch;
+    double *peer_up, *peer_down; // neighbours' pools (nullptr: no neighbour on that side)
+    size_t plane_up, plane_down; // their plane sizes (slabs may differ by one row)
+    int NYI_down;                // rows of the lower neighbour's planes
+    unsigned long long *flag_up, *flag_down;   // upper neighbour's "from below" word, lower neighbour's "from above" word
+    unsigned int *counter;       // blocks done (local)
+    unsigned long long seq;
+};
+void launch_halo_push(const PushArgs &a, cudaStream_t s);
+void launch_halo_wait(const unsigned long long *flags, int need_down, int need_up, unsigned long long seq, double *ctl,
+                      cudaStream_t s);
 void launch_es_switch(const SwitchArgs &a, cudaStream_t s);
 // fsy/gsx of the S sweep <- E sweep on the faces of switched cells and of their low-side neighbours (:1754-1758)
 void launch_flux_select(const double *flag, const double *fsyE, const double *gsxE, double *fsyS, double *gsxS,

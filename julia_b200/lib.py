@@ -42,6 +42,7 @@ SIGNATURES = {
     "weno5_destroy": (C.c_int, [_vp]),
     "weno5_comm_unique_id": (C.c_int, [C.POINTER(C.c_ubyte)]),
     "weno5_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_ubyte)]),
+    "weno5_comm_halo_mode": (C.c_int, [_vp]),
     "weno5_upload": (C.c_int, [_vp, _dp, _dp, _dp]),
     "weno5_download": (C.c_int, [_vp, _dp, _dp, _dp]),
     "weno5_upload_1d": (C.c_int, [_vp, _dp]),

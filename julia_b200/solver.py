@@ -76,6 +76,10 @@ class Solver:
         buf = (C.c_ubyte * 128).from_buffer_copy(uid)
         L.check(self.lib.weno5_comm_init(self.h, rank, nranks, buf))
 
+    def halo_mode(self):
+        """0: no communicator, 1: NCCL send/recv, 2: direct stores into the neighbours' ghost rows (peer memory)."""
+        return int(self.lib.weno5_comm_halo_mode(self.h))
+
     # -- state
     def upload(self, q, bxb=None, byb=None):
         if self.is1d:
