@@ -147,6 +147,10 @@ typedef struct weno5_pipe weno5_pipe;
 int weno5_pipe_create(const weno5_params *params, int device, int rows_per_slab, weno5_pipe **out);
 int weno5_pipe_step(weno5_pipe *pipe, const double *q0, const double *bxb0, const double *byb0, double dt,
                     double *q4, double *bxb4, double *byb4, double *dt_next);
+/* 1 if the last weno5_pipe_step was given page-locked host arrays (weno5_host_alloc, or memory registered with
+ * cudaHostRegister): only then do its H2D / D2H copies overlap the compute.  Pageable arrays (a plain Julia
+ * Array, numpy.zeros) give correct results through driver-staged, serialised copies -- slower than weno5_step_host. */
+int weno5_pipe_overlapped(const weno5_pipe *pipe);
 int weno5_pipe_destroy(weno5_pipe *pipe);
 
 /* ---- host memory helpers (page-locked buffers make upload/download asynchronous-capable) */

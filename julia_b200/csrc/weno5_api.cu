@@ -48,6 +48,18 @@ static int fail(int code, const char *fmt, ...)
             return fail(WENO5_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+// Entry points run on the handle's device and give the caller's current device back on return (a host that
+// shares the thread with CUDA.jl or torch keeps its own device selection).
+struct DevGuard {
+    int prev = -1;
+    cudaError_t set(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+        return cudaSetDevice(dev);
+    }
+    ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 // ------------------------------------------------------------------ NCCL through dlopen
 // The library has no link-time NCCL dependency: single-GPU users (and Julia) need none, and a
 // host process that already loaded NCCL (e.g. torch) shares that copy.
@@ -238,6 +250,8 @@ extern "C" int weno5_device_count(void)
     return ok;
 }
 
+extern "C" int weno5_destroy(weno5_ctx *c);
+
 static State carve_state(double *&cur, size_t plane)
 {
     State s;
@@ -271,9 +285,11 @@ static int create_ctx(const weno5_params *P, int device, int ny_local, int j_off
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return fail(WENO5_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
-    CU(cudaSetDevice(device));
+    DevGuard dg_; CU(dg_.set(device));
 
     weno5_ctx *c = new weno5_ctx();
+    // any failure from here on releases what has been allocated so far (weno5_destroy takes a half-built handle)
+    struct Cleanup { weno5_ctx *c; ~Cleanup() { if (c) weno5_destroy(c); } } cleanup{c};
     c->P = *P;
     c->device = device;
     c->ny_local = ny_local;
@@ -301,7 +317,7 @@ static int create_ctx(const weno5_params *P, int device, int ny_local, int j_off
     // + slack: a TMA row segment of the x sweep may run up to 66 cells past the end of the last row
     if (cudaMalloc(&c->pool, (nplanes * g.plane + 1024) * sizeof(double)) != cudaSuccess) {
         cudaGetLastError();
-        delete c;
+        c->pool = nullptr;
         return fail(WENO5_ERR_CUDA, "cudaMalloc of %.2f GB failed", nplanes * g.plane * 8.0 / 1e9);
     }
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -345,6 +361,7 @@ static int create_ctx(const weno5_params *P, int device, int ny_local, int j_off
         choose_segments(g.NYI - 5, flux_chunk(1), (g.NXI + flux_lines_per_cta(1) - 1) / flux_lines_per_cta(1),
                         c->segy_len, c->nsegy);
     CU(cudaStreamSynchronize(c->stream));
+    cleanup.c = nullptr;
     *out = c;
     return 0;
 }
@@ -357,7 +374,8 @@ extern "C" int weno5_create(const weno5_params *P, int device, int ny_local, int
 extern "C" int weno5_destroy(weno5_ctx *c)
 {
     if (!c) return 0;
-    cudaSetDevice(c->device);
+    DevGuard dg_;
+    dg_.set(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
     if (c->peer_pool_up) cudaIpcCloseMemHandle(c->peer_pool_up);
@@ -460,7 +478,7 @@ extern "C" int weno5_comm_init(weno5_ctx *c, int rank, int nranks, const unsigne
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail(WENO5_ERR_ARG, "bad rank %d of %d", rank, nranks);
     if (c->dual) return fail(WENO5_ERR_ARG, "the dual-energy switch runs on undivided grids (one GPU)");
     if (int r = nccl_load()) return r;
-    CU(cudaSetDevice(c->device));
+    DevGuard dg_; CU(dg_.set(c->device));
     ncclUniqueId u;
     memcpy(u.internal, id, 128);
     NC(g_nccl.CommInitRank(&c->comm, nranks, u, rank));
@@ -588,7 +606,7 @@ extern "C" int weno5_upload(weno5_ctx *c, const double *q, const double *bxb, co
     if (!c || !q) return fail(WENO5_ERR_ARG, "null argument");
     if (c->g.is1d) return fail(WENO5_ERR_ARG, "use weno5_upload_1d for 1-D grids");
     if ((bxb == nullptr) != (byb == nullptr)) return fail(WENO5_ERR_ARG, "pass both face fields or neither");
-    CU(cudaSetDevice(c->device));
+    DevGuard dg_; CU(dg_.set(c->device));
     const size_t hp = (size_t)c->g.Nx * c->g.Ny;
     for (int k = 0; k < NCELL; ++k) if (int r = copy_plane(c, c->Q0.q[k], q + host_comp(k) * hp, nullptr)) return r;
     if (bxb) {
@@ -609,7 +627,7 @@ extern "C" int weno5_download(weno5_ctx *c, double *q, double *bxb, double *byb)
     if (!c) return fail(WENO5_ERR_ARG, "null argument");
     if (c->g.is1d) return fail(WENO5_ERR_ARG, "use weno5_download_1d for 1-D grids");
     if (!c->uploaded) return fail(WENO5_ERR_STATE, "no state on the device yet");
-    CU(cudaSetDevice(c->device));
+    DevGuard dg_; CU(dg_.set(c->device));
     const size_t hp = (size_t)c->g.Nx * c->g.Ny;
     if (q) for (int k = 0; k < NCELL; ++k) if (int r = copy_plane(c, c->Q0.q[k], nullptr, q + host_comp(k) * hp)) return r;
     if (bxb) if (int r = copy_plane(c, c->Q0.bx, nullptr, bxb)) return r;
@@ -622,7 +640,7 @@ extern "C" int weno5_upload_1d(weno5_ctx *c, const double *q)
 {
     if (!c || !q) return fail(WENO5_ERR_ARG, "null argument");
     if (!c->g.is1d) return fail(WENO5_ERR_ARG, "handle is 2-D");
-    CU(cudaSetDevice(c->device));
+    DevGuard dg_; CU(dg_.set(c->device));
     for (int k = 0; k < NCELL; ++k) if (int r = copy_plane(c, c->Q0.q[k], q + (size_t)host_comp(k) * c->g.Nx, nullptr)) return r;
     if (int r = apply_boundaries(c, c->Q0, false)) return r;
     CU(cudaStreamSynchronize(c->stream));
@@ -635,7 +653,7 @@ extern "C" int weno5_download_1d(weno5_ctx *c, double *q)
     if (!c || !q) return fail(WENO5_ERR_ARG, "null argument");
     if (!c->g.is1d) return fail(WENO5_ERR_ARG, "handle is 2-D");
     if (!c->uploaded) return fail(WENO5_ERR_STATE, "no state on the device yet");
-    CU(cudaSetDevice(c->device));
+    DevGuard dg_; CU(dg_.set(c->device));
     for (int k = 0; k < NCELL; ++k) if (int r = copy_plane(c, c->Q0.q[k], nullptr, q + (size_t)host_comp(k) * c->g.Nx)) return r;
     CU(cudaStreamSynchronize(c->stream));
     return 0;
@@ -645,7 +663,7 @@ extern "C" int weno5_boundaries(weno5_ctx *c)
 {
     if (!c) return fail(WENO5_ERR_ARG, "null argument");
     if (!c->uploaded) return fail(WENO5_ERR_STATE, "no state on the device yet");
-    CU(cudaSetDevice(c->device));
+    DevGuard dg_; CU(dg_.set(c->device));
     if (int r = apply_boundaries(c, c->Q0, true)) return r;
     CU(cudaStreamSynchronize(c->stream));
     return 0;
@@ -680,7 +698,7 @@ extern "C" int weno5_timestep(weno5_ctx *c, double *dt, double *vxmax, double *v
 {
     if (!c) return fail(WENO5_ERR_ARG, "null argument");
     if (!c->uploaded) return fail(WENO5_ERR_STATE, "no state on the device yet");
-    CU(cudaSetDevice(c->device));
+    DevGuard dg_; CU(dg_.set(c->device));
     const double zero[2] = {0.0, 0.0};
     CU(cudaMemcpyAsync(c->ctl + 4, zero, sizeof(double), cudaMemcpyHostToDevice, c->stream));   // tmax off
     if (int r = enqueue_timestep(c)) return r;
@@ -949,7 +967,7 @@ extern "C" int weno5_rk4_step(weno5_ctx *c, double dt)
     if (!c) return fail(WENO5_ERR_ARG, "null argument");
     if (!c->uploaded) return fail(WENO5_ERR_STATE, "no state on the device yet");
     if (!(dt > 0.0) || !std::isfinite(dt)) return fail(WENO5_ERR_ARG, "dt must be positive and finite (got %g)", dt);
-    CU(cudaSetDevice(c->device));
+    DevGuard dg_; CU(dg_.set(c->device));
     c->h_ctl[8] = dt;
     CU(cudaMemcpyAsync(c->ctl, c->h_ctl + 8, sizeof(double), cudaMemcpyHostToDevice, c->stream));
     if (int r = enqueue_step(c)) return r;
@@ -964,7 +982,7 @@ extern "C" int weno5_advance(weno5_ctx *c, int nsteps, double tmax, double *t, i
     if (!c) return fail(WENO5_ERR_ARG, "null argument");
     if (!c->uploaded) return fail(WENO5_ERR_STATE, "no state on the device yet");
     if (nsteps < 0) return fail(WENO5_ERR_ARG, "nsteps < 0");
-    CU(cudaSetDevice(c->device));
+    DevGuard dg_; CU(dg_.set(c->device));
     double *h = c->h_ctl + 8;
     h[0] = 0.0; h[1] = t ? *t : 0.0; h[2] = 0.0; h[3] = 0.0; h[4] = tmax > 0.0 ? tmax : 0.0; h[5] = 0.0; h[6] = 0.0;
     CU(cudaMemcpyAsync(c->ctl, h, 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -977,6 +995,7 @@ extern "C" int weno5_advance(weno5_ctx *c, int nsteps, double tmax, double *t, i
         if (int r = enqueue_step(c)) return r;
         launch_advance_time(c->ctl, c->stream);
         c->launches++;
+        if (tmax <= 0.0 && (s % 64) == 63) CU(cudaStreamSynchronize(c->stream));   // keep the launch queue bounded
         if (tmax > 0.0 && (s % 16) == 15) {               // look at the clock now and then
             CU(cudaMemcpyAsync(c->h_ctl, c->ctl, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
             CU(cudaStreamSynchronize(c->stream));
@@ -1001,7 +1020,7 @@ extern "C" int weno5_set_es_switch(weno5_ctx *c, int enable, double threshold)
     if (c->g.is1d) return fail(WENO5_ERR_ARG, "the dual-energy switch is implemented for 2-D grids");
     if (c->comm || c->ny_local != c->P.ny) return fail(WENO5_ERR_ARG, "the dual-energy switch runs on undivided grids (one GPU)");
     if (!(threshold >= 0.0)) return fail(WENO5_ERR_ARG, "threshold must be >= 0 (the reference uses 1e-5)");
-    CU(cudaSetDevice(c->device));
+    DevGuard dg_; CU(dg_.set(c->device));
     const Geom &g = c->g;
     if (!c->dual_pool) {
         const size_t n = 8 + 8 + 6 + 5;
@@ -1029,7 +1048,7 @@ extern "C" int weno5_es_switch_count(weno5_ctx *c, unsigned long long *cells)
 {
     if (!c || !cells) return fail(WENO5_ERR_ARG, "null argument");
     if (!c->dual) return fail(WENO5_ERR_STATE, "the dual-energy switch is off");
-    CU(cudaSetDevice(c->device));
+    DevGuard dg_; CU(dg_.set(c->device));
     const double *pl[1] = {c->flag};
     launch_totals(pl, 1, c->g, c->sums, c->stream);
     c->launches++;
@@ -1045,7 +1064,7 @@ extern "C" int weno5_divb(weno5_ctx *c, double *divb)
     if (!c || !divb) return fail(WENO5_ERR_ARG, "null argument");
     if (c->g.is1d) return fail(WENO5_ERR_ARG, "divB is a 2-D diagnostic");
     if (!c->uploaded) return fail(WENO5_ERR_STATE, "no state on the device yet");
-    CU(cudaSetDevice(c->device));
+    DevGuard dg_; CU(dg_.set(c->device));
     launch_divb(c->Q0.bx, c->Q0.by, c->scratch, c->g, c->P.dx, c->P.dy, c->stream);
     c->launches++;
     if (int r = copy_plane(c, c->scratch, nullptr, divb)) return r;
@@ -1057,7 +1076,7 @@ extern "C" int weno5_totals(weno5_ctx *c, double sums[11])
 {
     if (!c || !sums) return fail(WENO5_ERR_ARG, "null argument");
     if (!c->uploaded) return fail(WENO5_ERR_STATE, "no state on the device yet");
-    CU(cudaSetDevice(c->device));
+    DevGuard dg_; CU(dg_.set(c->device));
     const double *pl[11];
     for (int k = 0; k < NCELL; ++k) pl[host_comp(k)] = c->Q0.q[k];     // report in the reference's order (S, then E)
     pl[9] = c->Q0.bx; pl[10] = c->Q0.by;
@@ -1078,7 +1097,7 @@ extern "C" int weno5_arr2img(weno5_ctx *c, int component, double lo, double hi, 
     if (ncolours < 2 || ncolours > 32767) return fail(WENO5_ERR_ARG, "ncolours must be in 2..32767 (Int16 indices)");
     const Geom &g = c->g;
     if (component < 0 || component > 11 || (g.is1d && component > 8)) return fail(WENO5_ERR_ARG, "unknown component %d", component);
-    CU(cudaSetDevice(c->device));
+    DevGuard dg_; CU(dg_.set(c->device));
     const double *field;
     if (component <= 8) {
         int k = component;                         // reference order: ..., 8th = S, 9th = E
@@ -1164,8 +1183,11 @@ struct weno5_pipe {
     int device;
     int R;                    // owned rows per slab
     int W;                    // interior rows of a slab window = R + 2 PIPE_H
+    bool last_pinned = true;  // the last weno5_pipe_step got page-locked host arrays (its copies overlapped compute)
     weno5_ctx *ctx[PIPE_NCTX];
 };
+
+extern "C" int weno5_pipe_overlapped(const weno5_pipe *p) { return p && p->last_pinned ? 1 : 0; }
 
 extern "C" int weno5_pipe_destroy(weno5_pipe *p)
 {
@@ -1218,9 +1240,29 @@ extern "C" int weno5_pipe_step(weno5_pipe *p, const double *q0, const double *bx
                                double *bxb4, double *byb4, double *dt_next)
 {
     if (!p || !q0 || !bxb0 || !byb0 || !q4 || !bxb4 || !byb4) return fail(WENO5_ERR_ARG, "null argument");
-    if (q0 == q4 || bxb0 == bxb4 || byb0 == byb4) return fail(WENO5_ERR_ARG, "the pipelined step cannot run in place");
+    {
+        // inputs are read while outputs of earlier slabs are being written: no byte of an output may lie in an input
+        const weno5_params &Q = p->P;
+        const size_t np_ = (size_t)(Q.nx + 2 * WENO5_NBND) * (Q.ny + 2 * WENO5_NBND) * sizeof(double);
+        const char *in[3] = {(const char *)q0, (const char *)bxb0, (const char *)byb0};
+        const char *ou[3] = {(const char *)q4, (const char *)bxb4, (const char *)byb4};
+        const size_t sz[3] = {9 * np_, np_, np_};
+        for (int i = 0; i < 3; ++i)
+            for (int o = 0; o < 3; ++o)
+                if (in[i] < ou[o] + sz[o] && ou[o] < in[i] + sz[i])
+                    return fail(WENO5_ERR_ARG, "the pipelined step cannot run in place: an output array overlaps an input array");
+        for (int a = 0; a < 3; ++a)
+            for (int b = a + 1; b < 3; ++b)
+                if (ou[a] < ou[b] + sz[b] && ou[b] < ou[a] + sz[a]) return fail(WENO5_ERR_ARG, "output arrays overlap each other");
+        // copies from/to pageable memory are staged by the driver and do not overlap compute: note it for the caller
+        cudaPointerAttributes at;
+        bool pinned = true;
+        for (const void *ptr : {(const void *)q0, (const void *)q4})
+            if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess || at.type != cudaMemoryTypeHost) { cudaGetLastError(); pinned = false; }
+        p->last_pinned = pinned;
+    }
     if (!(dt > 0.0) || !std::isfinite(dt)) return fail(WENO5_ERR_ARG, "dt must be positive and finite (got %g)", dt);
-    CU(cudaSetDevice(p->device));
+    DevGuard dg_; CU(dg_.set(p->device));
     const weno5_params &P = p->P;
     const int ny = P.ny, Ny = ny + 2 * WENO5_NBND, Nx = P.nx + 2 * WENO5_NBND;
     const bool periodic = P.bc_y == WENO5_BC_PERIODIC;
@@ -1347,7 +1389,7 @@ extern "C" int weno5_profile(weno5_ctx *c, int enable)
 extern "C" int weno5_profile_read(weno5_ctx *c, double *flux_ms, unsigned long long *flux_launches, int reset)
 {
     if (!c) return fail(WENO5_ERR_ARG, "null argument");
-    CU(cudaSetDevice(c->device));
+    DevGuard dg_; CU(dg_.set(c->device));
     CU(cudaStreamSynchronize(c->stream));
     for (size_t k = 0; k < c->ev_used; ++k) {
         float ms = 0.f;
@@ -1366,7 +1408,7 @@ extern "C" void *weno5_stream(weno5_ctx *c) { return c ? (void *)c->stream : nul
 extern "C" int weno5_debug_fetch(weno5_ctx *c, const char *name, double *out)
 {
     if (!c || !name || !out) return fail(WENO5_ERR_ARG, "null argument");
-    CU(cudaSetDevice(c->device));
+    DevGuard dg_; CU(dg_.set(c->device));
     const std::string n(name);
     double *src = nullptr;
     if (n == "fsy") src = c->fsy;

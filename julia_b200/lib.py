@@ -61,6 +61,7 @@ SIGNATURES = {
     "weno5_step_host": (C.c_int, [_vp, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp]),
     "weno5_pipe_create": (C.c_int, [C.POINTER(Params), C.c_int, C.c_int, C.POINTER(_vp)]),
     "weno5_pipe_step": (C.c_int, [_vp, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp, _dp]),
+    "weno5_pipe_overlapped": (C.c_int, [_vp]),
     "weno5_pipe_destroy": (C.c_int, [_vp]),
     "weno5_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_ulonglong]),
     "weno5_host_free": (C.c_int, [_vp]),

@@ -202,6 +202,9 @@ class Pipe:
         if getattr(self, "h", None):
             self.lib.weno5_pipe_destroy(self.h)
             self.h = None
+            for p in getattr(self, "_pinned", []):
+                self.lib.weno5_host_free(p)
+            self._pinned = []
 
     __del__ = close
 
@@ -211,8 +214,23 @@ class Pipe:
     def __exit__(self, *a):
         self.close()
 
+    def pinned(self, shape):
+        """Page-locked Fortran-ordered float64 array (weno5_host_alloc): pass such arrays as inputs and `out` to let
+        the copies overlap the compute.  Freed with the Pipe."""
+        n = int(np.prod(shape))
+        p = C.c_void_p()
+        L.check(self.lib.weno5_host_alloc(C.byref(p), n * 8))
+        self._pinned = getattr(self, "_pinned", []) + [p]
+        buf = (C.c_double * n).from_address(p.value)
+        return np.frombuffer(buf, dtype=np.float64).reshape(shape, order="F")
+
+    def overlapped(self):
+        """True if the last step() was given page-locked arrays (only then do copies and compute overlap)."""
+        return bool(self.lib.weno5_pipe_overlapped(self.h))
+
     def step(self, q, bxb, byb, dt, out=None):
-        """(q4, bxb4, byb4, dt_next); `out` = preallocated (q4, bxb4, byb4), must not alias the inputs."""
+        """(q4, bxb4, byb4, dt_next); `out` = preallocated (q4, bxb4, byb4), no byte of which may lie in an input.
+        Pageable arrays (the default `out`) work but serialise the copies: see pinned() / overlapped()."""
         g = self.g
         q, bxb, byb = _farr(q, (g.Nx, g.Ny, 9)), _farr(bxb, (g.Nx, g.Ny)), _farr(byb, (g.Nx, g.Ny))
         if out is None:

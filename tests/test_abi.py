@@ -73,3 +73,57 @@ def test_argument_validation(built):
     assert lib.weno5_create(C.byref(bad), 0, 24, 16, C.byref(h)) == L.ERR_ARG
     assert lib.weno5_rk4_step(None, 0.1) == L.ERR_ARG
     assert b"null" in lib.weno5_last_error()
+
+
+# ------------------------------------------------------------------ struct layout, pinned from C
+def _probe(tmp_path):
+    """tests/abi/abi_probe.c compiled as C11 against the header: sizeof / offsetof of weno5_params, enum values."""
+    import json
+    exe = str(tmp_path / "abi_probe")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "abi", "abi_probe.c"), "-o", exe])
+    return json.loads(subprocess.check_output([exe], text=True))
+
+
+def test_params_layout_matches_ctypes_and_julia(tmp_path):
+    """A reordered or retyped field of weno5_params must fail here: the C layout (gcc, from the header itself) is
+    compared with the ctypes mirror, with the table committed next to the Julia module, and with the layout that
+    Julia computes for the `struct Weno5Params` text in Weno5GPU.jl (isbits struct, C layout rules)."""
+    import json
+    c = _probe(tmp_path)
+    # ctypes mirror
+    assert C.sizeof(L.Params) == c["sizeof_weno5_params"] and C.alignment(L.Params) == c["alignof_weno5_params"]
+    assert [n for n, _ in L.Params._fields_] == list(c["fields"])
+    for name, _ in L.Params._fields_:
+        d = getattr(L.Params, name)
+        assert (d.offset, d.size) == (c["fields"][name]["offset"], c["fields"][name]["size"]), name
+    assert (L.WENO5_OK, L.ERR_ARG, L.ERR_CUDA, L.ERR_NCCL, L.ERR_STATE, L.ERR_NUMERIC) == tuple(
+        c["status"][k] for k in ("OK", "ERR_ARG", "ERR_CUDA", "ERR_NCCL", "ERR_STATE", "ERR_NUMERIC"))
+    assert (L.BC_OUTFLOW, L.BC_PERIODIC, L.NBND) == (c["bc"]["OUTFLOW"], c["bc"]["PERIODIC"], c["WENO5_NBND"])
+    # committed table next to the Julia module
+    with open(os.path.join(ROOT, "julia_b200", "julia", "abi_layout.json")) as f:
+        assert json.load(f) == c
+    # the Julia struct as written
+    jl = open(os.path.join(ROOT, "julia_b200", "julia", "Weno5GPU.jl")).read()
+    body = re.search(r"struct Weno5Params\n(.*?)\nend", jl, flags=re.S).group(1)
+    fields = re.findall(r"(\w+)::(Cint|Cdouble)", body)
+    size = {"Cint": 4, "Cdouble": 8}
+    off, layout = 0, {}
+    for name, ty in fields:
+        off = (off + size[ty] - 1) // size[ty] * size[ty]
+        layout[name] = {"offset": off, "size": size[ty]}
+        off += size[ty]
+    assert layout == c["fields"]
+    assert (off + 7) // 8 * 8 == c["sizeof_weno5_params"]
+    assert "const NBnd = 3" in jl and "BC_OUTFLOW, BC_PERIODIC = Cint(0), Cint(1)" in jl
+
+
+def test_pure_c_driver_links_against_the_library(built, tmp_path):
+    """tests/abi/c_driver.c -- the ccall sequence of INTEGRATION.md in plain C -- compiles as C11 and links against
+    libweno5mhd.so alone (its -m gpu twin in test_reference_pin.py runs it on the reference's shock-cloud problem)."""
+    exe = str(tmp_path / "c_driver")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "abi", "c_driver.c"), "-o", exe, "-L", os.path.dirname(L.LIB_PATH),
+                           "-lweno5mhd", "-Wl,-rpath," + os.path.dirname(L.LIB_PATH)])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 1 and "usage" in r.stderr

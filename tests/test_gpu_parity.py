@@ -13,7 +13,7 @@ from julia_b200 import problems as pr
 from julia_b200 import solver as S
 from julia_b200.solver import Solver
 from oracle import oracle_c as O
-from util import golden, interior, rel_l1, rel_linf
+from util import degenerate_distance_2d, golden, interior, rel_l1, rel_linf
 
 pytestmark = pytest.mark.gpu
 
@@ -83,6 +83,55 @@ def test_orszag_tang_l1():
         assert rel_l1(interior(qg[..., c]), interior(qo[..., c])) <= 1e-8, c
     # vz, Bz are zero in exact arithmetic; both codes keep them at the WENO-noise level
     assert np.abs(qg[..., 3]).max() < 1e-6 and np.abs(qo[..., 3]).max() < 1e-6
+
+
+def test_error_is_confined_to_degenerate_faces():
+    """The tolerance on Orszag-Tang (1e-7 / L1) is a statement about DEGENERATE faces only -- lines where the
+    face-averaged tangential field vanishes (By = 0 at x = k/4, Bx = 0 at y = k/2) and alpha_s is the square root of
+    a round-off residual (Weno5_2D.jl:1355-1356).  Shown here, not asserted: one RK4 step at 512^2 against the
+    oracle (bit-identical to the reference, tests/test_reference_pin.py); cells farther than 8 cells (measured decay:
+    2.7e-10 on the face, 5e-11, 4e-12, 2e-12, 1e-12, 5e-13, 1e-13, 2e-14 at distance 1..7, scripts/
+    degenerate_probe.py) from every degenerate face agree to 1e-12 -- two orders below the smooth-problem tolerance
+    of north_star -- and the masked band itself stays below 1e-8.  (The reference-run goldens are 16^2 / 24^2 grids,
+    where every cell lies inside that band.)"""
+    g, q, bx, by = pr.orszag_tang(512)
+    qg, bxg, byg, dt = run_gpu(g, q, bx, by, 1)
+    qo, bxo, byo = run_oracle(g, q, bx, by, 1, dt)
+    dist = degenerate_distance_2d(q, 1e-20)
+    band = dist <= 8
+    err = np.zeros(q.shape[:2])
+    for c in (0, 1, 2, 4, 5, 7, 8):
+        err = np.maximum(err, np.abs(qg[..., c] - qo[..., c]) / np.abs(qo[..., c]).max())
+    assert (dist == 0).sum() > 0 and 0.05 < band.mean() < 0.5, band.mean()
+    print(f"degenerate-face band: {int(band.sum())} of {band.size} cells masked ({100 * band.mean():.1f} %), "
+          f"L-inf inside {err[band].max():.2e}, outside {err[~band].max():.2e}")
+    assert err[~band].max() <= 1e-12
+    assert err[band].max() <= 1e-8
+
+
+def test_brio_wu_interface_is_the_only_deviation():
+    """Brio-Wu, 1024 cells, 8 steps: the initial interface (By changes sign, Bz = 0) is the one degenerate face;
+    outside its domain of dependence (13 cells per step) GPU and oracle agree to round-off, inside to 1e-8."""
+    g, q = pr.brio_wu(1024)
+    dt, steps = 0.4 * g.dx, 8
+    with Solver(g) as s:
+        s.upload(q)
+        for _ in range(steps):
+            s.rk4_step(dt)
+        qg = s.download()
+    qo = q
+    for _ in range(steps):
+        qo = O.rk4_step_1d(g, qo, dt)
+    err = np.zeros(q.shape[0])
+    for c in (0, 1, 2, 5, 8):
+        err = np.maximum(err, np.abs(qg[:, c] - qo[:, c]) / np.abs(qo[:, c]).max())
+    mid, w = q.shape[0] // 2, 13 * steps + 1
+    band = np.zeros(q.shape[0], dtype=bool)
+    band[mid - w:mid + w] = True
+    print(f"Brio-Wu: {int(band.sum())} of {band.size} cells in the interface band, L-inf inside {err[band].max():.2e}, "
+          f"outside {err[~band].max():.2e}")
+    assert err[~band].max() <= 1e-13
+    assert err[band].max() <= 1e-8
 
 
 def test_shock_cloud_reference_problem_outflow():
@@ -372,3 +421,26 @@ def test_pipelined_host_step_is_bit_identical(case):
         s.rk4_step(dt_next)
         q_ref2 = s.download()[0]
     assert np.array_equal(q5, q_ref2)
+
+
+def test_pipelined_step_argument_checks():
+    """Partially overlapping input / output arrays are rejected (not only identical pointers); pageable arrays are
+    accepted, flagged as not overlapped, and give the same result as page-locked ones."""
+    from julia_b200.solver import Pipe
+    g, q, bx, by = pr.orszag_tang(96, ny=256, ysize=256 / 96)
+    with Pipe(g, rows_per_slab=64) as p:
+        big = np.zeros(q.size + 64)
+        qin = big[:q.size].reshape(q.shape, order="F")
+        qin[...] = q
+        qout = big[64:64 + q.size].reshape(q.shape, order="F")          # shifted view of the same buffer
+        with pytest.raises(L.Weno5Error) as e:
+            p.step(qin, bx, by, 1e-4, out=(qout, np.zeros_like(bx, order="F"), np.zeros_like(by, order="F")))
+        assert e.value.code == L.ERR_ARG and "overlap" in str(e.value)
+        q4, bx4, by4, dtn = p.step(q, bx, by, 1e-4)
+        assert not p.overlapped()
+        hq, hbx, hby = p.pinned(q.shape), p.pinned(bx.shape), p.pinned(by.shape)
+        oq, obx, oby = p.pinned(q.shape), p.pinned(bx.shape), p.pinned(by.shape)
+        hq[...], hbx[...], hby[...] = q, bx, by
+        r = p.step(hq, hbx, hby, 1e-4, out=(oq, obx, oby))
+        assert p.overlapped()
+        assert np.array_equal(r[0], q4) and np.array_equal(r[1], bx4) and np.array_equal(r[2], by4) and r[3] == dtn

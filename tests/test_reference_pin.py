@@ -371,6 +371,42 @@ def test_gpu_rk4_step_2d_vs_reference_problem(cuda, name):
 
 
 @gpu
+def test_gpu_pure_c_driver_vs_reference_problem(cuda, tmp_path):
+    """The reference driver's call sequence (WENO5_2D, Weno5_2D.jl:33-72) in plain C11 through the C ABI alone
+    (tests/abi/c_driver.c: create -> upload -> {timestep -> classical_RK4_step} x 2 -> compute_divB -> download) on
+    the reference's own 16 x 4 shock-cloud state, against the reference's own output -- the closest executable
+    stand-in for Julia's ccall."""
+    import struct
+    import subprocess
+    from julia_b200 import lib as L
+    from util import ROOT
+    d = golden("ref2d_shockcloud")
+    nx, ny, nsteps = int(d["nx"]), int(d["ny"]), len(d["dt"])
+    exe, fin, fout = str(tmp_path / "c_driver"), str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "abi", "c_driver.c"), "-o", exe, "-L", os.path.dirname(L.LIB_PATH),
+                           "-lweno5mhd", "-Wl,-rpath," + os.path.dirname(L.LIB_PATH)])
+    with open(fin, "wb") as f:
+        f.write(struct.pack("<iiidd", nx, ny, nsteps, float(d["xsize"]), float(d["ysize"])))
+        for a in (d["q0"], d["bxb0"], d["byb0"]):
+            f.write(np.asfortranarray(a, dtype=np.float64).tobytes(order="F"))
+    subprocess.check_call([exe, fin, fout])
+    raw = np.fromfile(fout, dtype=np.float64)
+    Nx, Ny = nx + 6, ny + 6
+    steps = raw[:3 * nsteps].reshape(nsteps, 3)
+    body = raw[3 * nsteps:]
+    q = body[:9 * Nx * Ny].reshape((Nx, Ny, 9), order="F")
+    bx, by, divb = (body[(9 + k) * Nx * Ny:(10 + k) * Nx * Ny].reshape((Nx, Ny), order="F") for k in range(3))
+    assert abs(steps[0, 0] - d["dt"][0]) <= 1e-12 * d["dt"][0]
+    assert abs(steps[0, 1] - d["vmax"][0][0]) <= 1e-12 * steps[0, 1] and abs(steps[0, 2] - d["vmax"][0][1]) <= 1e-12 * steps[0, 2]
+    assert abs(steps[-1, 0] - d["dt"][-1]) <= 1e-8 * d["dt"][-1]          # second dt: from the first step's own result
+    err = group_err(q[3:-3, 3:-3], d[f"q{nsteps}"][3:-3, 3:-3])
+    assert max(err.values()) <= 1e-8 * nsteps, err                        # Q3-limited like the oracle
+    assert np.abs(by - d[f"byb{nsteps}"])[3:-3, 3:-3].max() <= 1e-8 * np.abs(by).max()
+    assert np.abs(divb)[3:-3, 3:-3].max() < 1e-11 and np.abs(bx).max() > 0
+
+
+@gpu
 @pytest.mark.parametrize("name,ctor,tol_linf,tol_l1", [("ref1d_rj95_2a", pr.rj95_2a, 1e-9, 1e-11),
                                                      ("ref1d_briowu", pr.brio_wu, 1e-6, 1e-8)])
 def test_gpu_rk4_step_1d_vs_reference(cuda, name, ctor, tol_linf, tol_l1):
