@@ -111,11 +111,16 @@ int weno5_totals(weno5_ctx *ctx, double sums[11]);
  * (`dS = 1`, :1741).  With enable = 1 the step runs both branches and applies the criterion the reference
  * wrote and disabled (:1740): cells whose entropy derived from the E state differs from the advected entropy by
  * >= threshold (reference value 1e-5) take the E state, all others the S state, and the constrained-transport
- * seed fluxes follow the selection (:1754-1758).  enable = 0 (the default) is the shipped behaviour.
- * 2-D, undivided grids.  weno5_es_switch_count returns the number of interior cells that took the E state in
- * the most recent stage. */
+ * seed fluxes follow the selection (:1754-1758).  enable = 0 (the default) is the shipped 2-D behaviour.
+ * Works on y-slabs too (the flags of the neighbours' edge rows travel with the halo).
+ * 1-D grids (Weno5_1D.jl:152-258): enable = 2 is the 1-D reference AS SHIPPED -- both branches are swept, the state
+ * stays the energy branch's (:252-254) and the flags are the output (`idx`, :245); enable = 1 drops that override
+ * (entropy state by default, energy state in flagged cells).
+ * weno5_es_switch_count: interior cells of this slab flagged in the most recent stage; weno5_es_switch_mask: the
+ * flags themselves in the public array shape (Nx,Ny) / (N), 1.0 = flagged. */
 int weno5_set_es_switch(weno5_ctx *ctx, int enable, double threshold);
 int weno5_es_switch_count(weno5_ctx *ctx, unsigned long long *cells);
+int weno5_es_switch_mask(weno5_ctx *ctx, double *mask);
 
 /* ---- snapshot hook (SURVEY "next" row f4).  Arr2Img(arr, cmap; range, log) of JColorMaps.jl:92-146, which the
  * reference driver calls on q[:,:,k] and divB for its frames (Weno5_2D.jl:75-99), evaluated on the resident

@@ -135,6 +135,11 @@ struct weno5_ctx {
     unsigned long long *vmax_bits_img = nullptr;   // 3 keys of the snapshot range reduction
     unsigned long long *vmax_next = nullptr;       // maxima of the state stage 4 is writing (fused reduction, weno5_advance)
     bool fuse_vmax = false;                        // stage 4 also reduces the wave speeds of the new state
+    // one captured step (timestep + 4 stages + clock) replayed by weno5_advance: launch-bound small grids
+    // (512^2: ~25 launches of 5-40 us each) stop paying the per-launch CPU cost
+    cudaGraphExec_t step_graph = nullptr;
+    int graph_key = -1;
+    unsigned long long graph_launches = 0;
     double *sums = nullptr;
     double *h_ctl = nullptr;         // pinned mirror
     int side[4];                     // SideBC of x-lo, x-hi, y-lo, y-hi for this slab
@@ -171,6 +176,7 @@ struct weno5_ctx {
     size_t nplanes = 0;
     // dual-energy mode (weno5_set_es_switch): both branches are swept and ES_Switch selects per cell
     bool dual = false;
+    bool dual_flags_only = false;    // both branches run, the state stays the energy branch's, the flags are the output
     double es_threshold = 1e-5;
     double *dual_pool = nullptr;
     double *candE[8], *candS[8];     // candidate states: rho,Mx,My,Mz,Bz,E|S,Bx,By
@@ -312,8 +318,9 @@ static int create_ctx(const weno5_params *P, int device, int ny_local, int j_off
     if (side_lo >= 0) c->side[2] = side_lo;
     if (side_hi >= 0) c->side[3] = side_hi;
 
-    // planes: 3 states x 11 + acc 6+2+1 + rhs 7 + fsy,gsx + scratch
-    const size_t nplanes = 3 * 11 + 9 + 7 + 2 + 1;
+    // planes: 3 states x 11 + acc 6+2+1 + rhs 7 + fsy,gsx + scratch + switch flags (dual-energy mode; in the pool so
+    // that the halo push can address it)
+    const size_t nplanes = 3 * 11 + 9 + 7 + 2 + 1 + 1;
     // + slack: a TMA row segment of the x sweep may run up to 66 cells past the end of the last row
     if (cudaMalloc(&c->pool, (nplanes * g.plane + 1024) * sizeof(double)) != cudaSuccess) {
         cudaGetLastError();
@@ -334,6 +341,7 @@ static int create_ctx(const weno5_params *P, int device, int ny_local, int j_off
     c->fsy = cur; cur += g.plane;
     c->gsx = cur; cur += g.plane;
     c->scratch = cur; cur += g.plane;
+    c->flag = cur; cur += g.plane;
 
     c->nplanes = nplanes;
     if (!is1d && flux_uses_tma()) {
@@ -378,6 +386,7 @@ extern "C" int weno5_destroy(weno5_ctx *c)
     dg_.set(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
+    if (c->step_graph) cudaGraphExecDestroy(c->step_graph);
     if (c->peer_pool_up) cudaIpcCloseMemHandle(c->peer_pool_up);
     if (c->peer_pool_down && c->peer_pool_down != c->peer_pool_up) cudaIpcCloseMemHandle(c->peer_pool_down);
     if (c->peer_flags_up) cudaIpcCloseMemHandle(c->peer_flags_up);
@@ -476,7 +485,6 @@ extern "C" int weno5_comm_init(weno5_ctx *c, int rank, int nranks, const unsigne
     if (!c || !id) return fail(WENO5_ERR_ARG, "null argument");
     if (c->g.is1d) return fail(WENO5_ERR_ARG, "1-D grids cannot be decomposed");
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail(WENO5_ERR_ARG, "bad rank %d of %d", rank, nranks);
-    if (c->dual) return fail(WENO5_ERR_ARG, "the dual-energy switch runs on undivided grids (one GPU)");
     if (int r = nccl_load()) return r;
     DevGuard dg_; CU(dg_.set(c->device));
     ncclUniqueId u;
@@ -862,6 +870,7 @@ static int enqueue_stage_dual(weno5_ctx *c, int stage, State &cur, State &nxt)
     static const int sixE[6] = {C_RHO, C_MX, C_MY, C_MZ, C_BZ, C_E};
     static const int sixS[6] = {C_RHO, C_MX, C_MY, C_MZ, C_BZ, C_S};
     auto plane_of = [&](const double *p) { return (int)((p - c->pool) / (ptrdiff_t)g.plane); };
+    if (int r = wait_exchange(c)) return r;
 
     for (int br = 0; br < 2; ++br) {
         const int *six = br == 0 ? sixE : sixS;
@@ -926,9 +935,12 @@ static int enqueue_stage_dual(weno5_ctx *c, int stage, State &cur, State &nxt)
     for (int k = 0; k < 7; ++k) w.qn[k] = nxt.q[sel[k]];
     w.flag = c->flag;
     w.NXI = g.NXI; w.NYI = g.NYI; w.pitch = g.pitch; w.gam = P.gamma; w.threshold = c->es_threshold; w.dtp = dtp;
+    w.qn_by = nullptr; w.flags_only = c->dual_flags_only ? 1 : 0;
     launch_es_switch(w, c->stream);
     double *fl[1] = {c->flag};
     launch_bc_fill(fl, 1, g, c->side, dtp, c->stream);
+    // y-slabs: the switch decisions of the neighbours' edge rows select the seed fluxes of this slab's ghost-row faces
+    if (c->comm) { if (int r = exchange_rows(c, fl, 1)) return r; }
     launch_flux_select(c->flag, c->fsy, c->gsx, c->fsyS, c->gsxS, g, dtp, c->stream);
 
     // constrained transport with the selected seed fluxes (:175-180)
@@ -942,12 +954,74 @@ static int enqueue_stage_dual(weno5_ctx *c, int stage, State &cur, State &nxt)
     }
     launch_bc_fill(nxt.q, NCELL, g, c->side, dtp, c->stream);
     c->launches++;
+    if (c->comm) { if (int r = exchange_rows(c, nxt.q, NCELL)) return r; }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// 1-D twin (Weno5_1D.jl:152-236): per stage the energy sweep and the entropy sweep of the switched state, the two
+// RK candidates, ES_Switch (:238-258).  candE/candS hold rho,Mx,My,Mz,Bz,E|S,(unused),By.
+static int enqueue_stage_dual_1d(weno5_ctx *c, int stage, State &cur, State &nxt)
+{
+    static const double ck[4] = {0.5, 0.5, 1.0, 1.0 / 6.0};
+    const weno5_params &P = c->P;
+    const Geom &g = c->g;
+    const double *dtp = c->ctl;
+    for (int br = 0; br < 2; ++br) {
+        FluxArgs a;
+        memset(&a, 0, sizeof(a));
+        for (int k = 0; k < 7; ++k) a.qc[k] = cur.q[k];
+        a.qc[7] = cur.q[br == 0 ? C_E : C_S];
+        for (int k = 0; k < 7; ++k) a.rhs[k] = c->rhs[k];
+        a.dtp = dtp;
+        a.c_dx = ck[stage - 1] / P.dx;
+        a.stage = stage;
+        a.gam = P.gamma; a.eps = P.eps; a.g2 = (P.gamma - 2.0) / (P.gamma - 1.0);
+        a.is1d = 1;
+        a.pitch = g.pitch;
+        a.branch = br;
+        a.N = g.NXI; a.NP = g.NYI; a.bs = c->fsy;
+        a.seg_len = c->segx_len; a.nseg = c->nsegx;
+        launch_flux_x(a, c->stream);
+        double *qn7[7]; const double *base7[7]; double *acc7[7];
+        double **cand = br == 0 ? c->candE : c->candS;
+        const int en = br == 0 ? C_E : C_S;
+        const int seven[7] = {C_RHO, C_MX, C_MY, C_MZ, C_BZ, en, C_BY};
+        for (int k = 0; k < 7; ++k) {
+            qn7[k] = k < 6 ? cand[k] : cand[7];
+            base7[k] = c->Q0.q[seven[k]];
+            acc7[k] = br == 0 ? (k < 6 ? c->acc[k] : c->acc_by1d) : (k < 6 ? c->accS[k] : c->tbx);
+        }
+        launch_update_1d(a, qn7, base7, acc7, c->stream);
+        c->launches += 2;
+    }
+    SwitchArgs w;
+    for (int k = 0; k < 8; ++k) { w.ce[k] = c->candE[k]; w.cs[k] = c->candS[k]; }
+    w.ce[6] = w.cs[6] = c->Q0.q[C_BX];                     // Bx is constant in 1-D (Weno5_1D.jl:771)
+    static const int sel[7] = {C_RHO, C_MX, C_MY, C_MZ, C_BZ, C_S, C_E};
+    for (int k = 0; k < 7; ++k) w.qn[k] = nxt.q[sel[k]];
+    w.qn_by = nxt.q[C_BY];
+    w.flag = c->flag;
+    w.NXI = g.NXI; w.NYI = g.NYI; w.pitch = g.pitch; w.gam = P.gamma; w.threshold = c->es_threshold; w.dtp = dtp;
+    w.flags_only = c->dual_flags_only ? 1 : 0;
+    launch_es_switch(w, c->stream);
+    if (nxt.q[C_BX] != c->Q0.q[C_BX])
+        CU(cudaMemcpyAsync(nxt.q[C_BX], c->Q0.q[C_BX], g.plane * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    launch_bc_fill(nxt.q, NCELL, g, c->side, dtp, c->stream);
+    c->launches += 2;
     CU(cudaGetLastError());
     return 0;
 }
 
 static int enqueue_step(weno5_ctx *c)
 {
+    if (c->dual && c->g.is1d) {
+        if (int r = enqueue_stage_dual_1d(c, 1, c->Q0, c->QA)) return r;
+        if (int r = enqueue_stage_dual_1d(c, 2, c->QA, c->QB)) return r;
+        if (int r = enqueue_stage_dual_1d(c, 3, c->QB, c->QA)) return r;
+        if (int r = enqueue_stage_dual_1d(c, 4, c->QA, c->Q0)) return r;
+        return 0;
+    }
     if (c->dual) {
         if (int r = enqueue_stage_dual(c, 1, c->Q0, c->QA)) return r;
         if (int r = enqueue_stage_dual(c, 2, c->QA, c->QB)) return r;
@@ -977,6 +1051,30 @@ extern "C" int weno5_rk4_step(weno5_ctx *c, double dt)
     return 0;
 }
 
+// Capture one step of the device-resident loop (no host interaction inside: dt, t and the maxima live in device
+// memory, the state ping-pong returns to Q0 every step) into a CUDA graph.
+static int build_step_graph(weno5_ctx *c, int key)
+{
+    if (c->step_graph && c->graph_key == key) return 0;
+    if (c->step_graph) { cudaGraphExecDestroy(c->step_graph); c->step_graph = nullptr; }
+    cudaGraph_t g = nullptr;
+    CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    const unsigned long long l0 = c->launches;
+    int r = enqueue_timestep(c, c->fuse_vmax);
+    if (!r) r = enqueue_step(c);
+    if (!r) { launch_advance_time(c->ctl, c->stream); c->launches++; }
+    const cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+    c->graph_launches = c->launches - l0;
+    c->launches = l0;
+    if (r) { if (g) cudaGraphDestroy(g); return r; }
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(WENO5_ERR_CUDA, "stream capture of one step failed: %s", cudaGetErrorString(e)); }
+    const cudaError_t ei = cudaGraphInstantiate(&c->step_graph, g, 0);
+    cudaGraphDestroy(g);
+    if (ei != cudaSuccess) { cudaGetLastError(); c->step_graph = nullptr; return fail(WENO5_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ei)); }
+    c->graph_key = key;
+    return 0;
+}
+
 extern "C" int weno5_advance(weno5_ctx *c, int nsteps, double tmax, double *t, int *nsteps_done)
 {
     if (!c) return fail(WENO5_ERR_ARG, "null argument");
@@ -990,11 +1088,19 @@ extern "C" int weno5_advance(weno5_ctx *c, int nsteps, double tmax, double *t, i
     c->fuse_vmax = !c->dual && !c->g.is1d && nsteps > 1 && !getenv("WENO5_NO_FUSED_VMAX");
     if (c->fuse_vmax) CU(cudaMemsetAsync(c->vmax_next, 0, 2 * sizeof(unsigned long long), c->stream));
     struct Unfuse { weno5_ctx *c; ~Unfuse() { c->fuse_vmax = false; } } unfuse{c};
+    // steps 2.. replay a captured graph (one GPU, no per-launch profiling events)
+    const bool use_graph = !c->comm && !c->profiling && nsteps > 2 && !getenv("WENO5_NO_GRAPH");
     for (int s = 0; s < nsteps; ++s) {
-        if (int r = enqueue_timestep(c, c->fuse_vmax && s > 0)) return r;
-        if (int r = enqueue_step(c)) return r;
-        launch_advance_time(c->ctl, c->stream);
-        c->launches++;
+        if (use_graph && s > 0) {
+            if (int r = build_step_graph(c, (c->fuse_vmax ? 1 : 0) | (c->dual ? 2 : 0) | (c->P.es_roundtrip ? 4 : 0) | (c->dual_flags_only ? 8 : 0))) return r;
+            CU(cudaGraphLaunch(c->step_graph, c->stream));
+            c->launches += c->graph_launches;
+        } else {
+            if (int r = enqueue_timestep(c, c->fuse_vmax && s > 0)) return r;
+            if (int r = enqueue_step(c)) return r;
+            launch_advance_time(c->ctl, c->stream);
+            c->launches++;
+        }
         if (tmax <= 0.0 && (s % 64) == 63) CU(cudaStreamSynchronize(c->stream));   // keep the launch queue bounded
         if (tmax > 0.0 && (s % 16) == 15) {               // look at the clock now and then
             CU(cudaMemcpyAsync(c->h_ctl, c->ctl, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -1016,14 +1122,15 @@ extern "C" int weno5_advance(weno5_ctx *c, int nsteps, double tmax, double *t, i
 extern "C" int weno5_set_es_switch(weno5_ctx *c, int enable, double threshold)
 {
     if (!c) return fail(WENO5_ERR_ARG, "null argument");
+    if (c->step_graph) { cudaGraphExecDestroy(c->step_graph); c->step_graph = nullptr; c->graph_key = -1; }   // threshold is baked in
     if (!enable) { c->dual = false; return 0; }
-    if (c->g.is1d) return fail(WENO5_ERR_ARG, "the dual-energy switch is implemented for 2-D grids");
-    if (c->comm || c->ny_local != c->P.ny) return fail(WENO5_ERR_ARG, "the dual-energy switch runs on undivided grids (one GPU)");
+    if (enable != 1 && enable != 2) return fail(WENO5_ERR_ARG, "enable must be 0 (off), 1 (live switch) or 2 (flags only)");
+    if (enable == 2 && !c->g.is1d) return fail(WENO5_ERR_ARG, "flags-only mode is the 1-D reference's behaviour (Weno5_1D.jl:252-254); 2-D grids take 0 or 1");
     if (!(threshold >= 0.0)) return fail(WENO5_ERR_ARG, "threshold must be >= 0 (the reference uses 1e-5)");
     DevGuard dg_; CU(dg_.set(c->device));
     const Geom &g = c->g;
     if (!c->dual_pool) {
-        const size_t n = 8 + 8 + 6 + 5;
+        const size_t n = 8 + 8 + 6 + 4;
         if (cudaMalloc(&c->dual_pool, n * g.plane * sizeof(double)) != cudaSuccess) {
             cudaGetLastError();
             return fail(WENO5_ERR_CUDA, "cudaMalloc of %.2f GB for the dual-energy planes failed", n * g.plane * 8.0 / 1e9);
@@ -1037,10 +1144,22 @@ extern "C" int weno5_set_es_switch(weno5_ctx *c, int enable, double threshold)
         c->gsxS = cur; cur += g.plane;
         c->tbx = cur; cur += g.plane;
         c->tby = cur; cur += g.plane;
-        c->flag = cur; cur += g.plane;
     }
     c->dual = true;
+    c->dual_flags_only = enable == 2;
     c->es_threshold = threshold;
+    return 0;
+}
+
+// the flags of the last stage in the public array shape (Nx,Ny) / (N): 1.0 where |S(E) - S| >= threshold
+// (the reference's `idx`, Weno5_1D.jl:245, as a mask)
+extern "C" int weno5_es_switch_mask(weno5_ctx *c, double *mask)
+{
+    if (!c || !mask) return fail(WENO5_ERR_ARG, "null argument");
+    if (!c->dual) return fail(WENO5_ERR_STATE, "the dual-energy switch is off");
+    DevGuard dg_; CU(dg_.set(c->device));
+    if (int r = copy_plane(c, c->flag, nullptr, mask)) return r;
+    CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
 

@@ -1229,26 +1229,31 @@ void launch_entropy(double *const q9[9], const Geom &g, double gam, int roundtri
 __global__ void es_switch_kernel(const SwitchArgs a)
 {
     if (a.dtp && *a.dtp == 0.0) return;
+    const bool d1 = a.NYI == 1;                                  // 1-D: Weno5_1D.jl:238-258
     const int i = blockIdx.x * blockDim.x + threadIdx.x + G;
-    const int j = blockIdx.y * blockDim.y + threadIdx.y + G;
-    if (i >= a.NXI - G || j >= a.NYI - G) return;
+    const int j = d1 ? 0 : blockIdx.y * blockDim.y + threadIdx.y + G;
+    if (i >= a.NXI - G || (!d1 && j >= a.NYI - G)) return;
     const size_t g = (size_t)i + (size_t)a.pitch * j;
     double e[8], s[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) { e[k] = a.ce[k][g]; s[k] = a.cs[k][g]; }
     const double SE = e2s(e[0], e[1], e[2], e[3], e[6], e[7], e[4], e[5], a.gam);
     const bool bad = fabs(SE - s[5]) >= a.threshold;
-    const double rho = bad ? e[0] : s[0], mx = bad ? e[1] : s[1], my = bad ? e[2] : s[2], mz = bad ? e[3] : s[3];
-    const double bz = bad ? e[4] : s[4], S = bad ? SE : s[5], bx = bad ? e[6] : s[6], by = bad ? e[7] : s[7];
+    // flags_only (the 1-D reference as shipped, :252-254): the energy state everywhere, the flags are the output
+    const bool takeE = bad || a.flags_only;
+    const double rho = takeE ? e[0] : s[0], mx = takeE ? e[1] : s[1], my = takeE ? e[2] : s[2], mz = takeE ? e[3] : s[3];
+    const double bz = takeE ? e[4] : s[4], S = takeE ? SE : s[5], bx = takeE ? e[6] : s[6], by = takeE ? e[7] : s[7];
     a.qn[0][g] = rho; a.qn[1][g] = mx; a.qn[2][g] = my; a.qn[3][g] = mz; a.qn[4][g] = bz;
     a.qn[5][g] = S;
-    a.qn[6][g] = s2e(rho, mx, my, mz, bx, by, bz, S, a.gam);
+    a.qn[6][g] = a.flags_only ? e[5] : s2e(rho, mx, my, mz, bx, by, bz, S, a.gam);
+    if (a.qn_by) a.qn_by[g] = by;                                // 1-D: By is a flux-advanced component
     a.flag[g] = bad ? 1.0 : 0.0;
 }
 
 void launch_es_switch(const SwitchArgs &a, cudaStream_t s)
 {
-    dim3 block(64, 4), grid((a.NXI - 2 * G + 63) / 64, (a.NYI - 2 * G + 3) / 4);
+    dim3 block(64, 4), grid((a.NXI - 2 * G + 63) / 64, a.NYI > 1 ? (a.NYI - 2 * G + 3) / 4 : 1);
+    if (a.NYI == 1) block = dim3(256, 1), grid = dim3((a.NXI - 2 * G + 255) / 256, 1);
     es_switch_kernel<<<grid, block, 0, s>>>(a);
 }
 

@@ -72,10 +72,12 @@ struct SwitchArgs {
     const double *ce[8];         // E candidate: rho,Mx,My,Mz,Bz,E,Bx,By
     const double *cs[8];         // S candidate: rho,Mx,My,Mz,Bz,S,Bx,By
     double *qn[7];               // selected state: rho,Mx,My,Mz,Bz,S,E
-    double *flag;                // 1.0 where the E state was taken
+    double *flag;                // 1.0 where |S(E) - S| >= threshold
     int NXI, NYI, pitch;
     double gam, threshold;
     const double *dtp;
+    double *qn_by;               // 1-D only: selected By (flux-advanced there); nullptr in 2-D
+    int flags_only;              // 1: keep the energy state everywhere, only record the flags (Weno5_1D.jl:252-254)
 };
 
 void launch_flux_x(const FluxArgs &a, cudaStream_t s);

@@ -55,6 +55,7 @@ SIGNATURES = {
     "weno5_totals": (C.c_int, [_vp, _dp]),
     "weno5_set_es_switch": (C.c_int, [_vp, C.c_int, C.c_double]),
     "weno5_es_switch_count": (C.c_int, [_vp, C.POINTER(C.c_ulonglong)]),
+    "weno5_es_switch_mask": (C.c_int, [_vp, _dp]),
     "weno5_arr2img": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_short), _dp]),
     "weno5_classical_rk4_step_2d": (C.c_int, [C.POINTER(Params), _dp, _dp, _dp, C.c_double, _dp, _dp, _dp]),
     "weno5_classical_rk4_step_1d": (C.c_int, [C.POINTER(Params), _dp, C.c_double, _dp]),

@@ -19,6 +19,9 @@ CASES = {
     "blast_512x1024": ("blast", 512, 0, 2, 3),
     "orszag_tang_1024row_slabs": ("orszag_tang", 256, 1024, 1, 2),
     "shock_cloud_outflow": ("shock_cloud", 256, 0, 2, 3),
+    # dual-energy mode (both branches + live ES_Switch, Weno5_2D.jl:1734-1768): the switch flags of the neighbours' edge
+    # rows travel with the halo
+    "blast_dual_energy": ("blast", 256, 0, 2, 2, True),
 }
 
 
@@ -30,7 +33,8 @@ def _problem(name, nx, ny):
 
 def run_case(case, rank, world, local, dist):
     """Returns (max |difference|, max |dt difference|) on rank 0, (None, None) elsewhere."""
-    ctor, nx, rows, steps, adv = CASES[case]
+    ctor, nx, rows, steps, adv = CASES[case][:5]
+    dual = len(CASES[case]) > 5 and CASES[case][5]
     ny = rows * world if rows else 1024
     g, q, bx, by = _problem(ctor, nx, ny)
     off, nl = pt.slab(g.ny, world, rank)
@@ -38,6 +42,8 @@ def run_case(case, rank, world, local, dist):
     uid = pt.broadcast_unique_id(Solver.comm_unique_id, rank, dist)
     with Solver(g, device=local, ny_local=nl, j_offset=off) as s:
         s.comm_init(rank, world, uid)
+        if dual:
+            s.set_es_switch(True, 1e-5)
         cut = lambda x: pt.cut_slab(x, off, nl, periodic=periodic)       # noqa: E731
         s.upload(cut(q), cut(bx), cut(by))
         dts = []
@@ -53,6 +59,8 @@ def run_case(case, rank, world, local, dist):
     if rank != 0:
         return None, None
     with Solver(g, device=local) as s1:
+        if dual:
+            s1.set_es_switch(True, 1e-5)
         s1.upload(q, bx, by)
         dts1 = []
         for _ in range(steps):

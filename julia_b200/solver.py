@@ -136,8 +136,15 @@ class Solver:
     # -- dual-energy mode
     def set_es_switch(self, enable=True, threshold=1e-5):
         """Run both the E and the S sweeps every stage and let ES_Switch (Weno5_2D.jl:1734) choose per cell
-        with the criterion the reference wrote and disabled (:1740): |S(E) - S| >= threshold -> E state."""
-        L.check(self.lib.weno5_set_es_switch(self.h, 1 if enable else 0, float(threshold)))
+        with the criterion the reference wrote and disabled (:1740): |S(E) - S| >= threshold -> E state.
+        enable = 2 (1-D grids): the 1-D reference as shipped -- energy state everywhere, the flags are the output."""
+        L.check(self.lib.weno5_set_es_switch(self.h, int(enable) if enable in (0, 1, 2) else (1 if enable else 0), float(threshold)))
+
+    def es_switch_mask(self):
+        """1.0 where |S(E) - S| >= threshold in the last stage (the reference's `idx`, Weno5_1D.jl:245, as a mask)."""
+        m = np.zeros((self.Nx,) if self.is1d else (self.Nx, self.Ny), order="F")
+        L.check(self.lib.weno5_es_switch_mask(self.h, L.dptr(m)))
+        return m
 
     def es_switch_count(self):
         n = C.c_ulonglong()

@@ -775,6 +775,61 @@ def classical_RK4_step_1d(q, dt, P):
     return q4
 
 
+def classical_RK4_step_1d_dual(q, dt, P, threshold=1e-5, live=True):
+    """Weno5_1D.jl:152-236 with BOTH branches, as the reference runs them: every stage sweeps the switched state
+    once in energy variables (weno5_flux_difference_E, :728) and once in entropy variables
+    (weno5_flux_difference_S, :441), and ES_Switch (:238-258) flags the cells with |S(E) - S| >= threshold.
+    live = False is the code as shipped -- the flags are computed and returned (`idx`), the state is overridden by
+    the energy branch (:252-254); live = True drops those three override lines: entropy state by default, energy
+    state in flagged cells.  Returns (q4, flag of the last stage)."""
+    def sweep(q9, branch):
+        cols = [0, 1, 2, 3, 4, 5, 6, 8] if branch == "E" else [0, 1, 2, 3, 4, 5, 6, 7]
+        qb = np.ascontiguousarray(q9[:, None, cols])
+        if branch == "E":
+            u = primitives_E(qb, P.gam)
+            F = fluxes_E(qb, u)
+        else:
+            u = primitives_S(qb, P.gam)
+            F = fluxes_S(qb, u)
+        a = eigenvalues(u, P.gam)
+        dF, _ = weno5_face_flux(qb, a, F, P.gam, P.eps, P.bc_x, variant="1d", branch=branch)
+        N = q9.shape[0]
+        Q = np.zeros((N, 8))
+        i = np.arange(NB, N - NB)
+        for c_out, c_in in ((0, 0), (1, 1), (2, 2), (3, 3), (5, 4), (6, 5), (7, 6)):
+            Q[i, c_out] = dF[i, 0, c_in] - dF[i - 1, 0, c_in]
+        return qb[:, 0, :], Q
+
+    def switch(qE, qS):
+        qSE = qE.copy()
+        qSE[:, 7] = E2S(qE, P.gam)
+        bad = np.abs(qSE[:, 7] - qS[:, 7]) >= threshold
+        q9 = np.zeros((qE.shape[0], 9))
+        q9[:, 0:8] = np.where(bad[:, None], qSE, qS)
+        q9[:, 8] = S2E(q9[:, 0:8], P.gam)
+        if not live:
+            q9[:, 0:7] = qE[:, 0:7]
+            q9[:, 7] = E2S(qE, P.gam)
+            q9[:, 8] = qE[:, 7]
+        boundaries_1d(q9, P)
+        return q9, bad
+
+    q0E, Q0E = sweep(q, "E")
+    q0S, Q0S = sweep(q, "S")
+    q1, _ = switch(q0E - 1 / 2 * dt / P.dx * Q0E, q0S - 1 / 2 * dt / P.dx * Q0S)
+    q1E, Q1E = sweep(q1, "E")
+    q1S, Q1S = sweep(q1, "S")
+    q2, _ = switch(q0E - 1 / 2 * dt / P.dx * Q1E, q0S - 1 / 2 * dt / P.dx * Q1S)
+    q2E, Q2E = sweep(q2, "E")
+    q2S, Q2S = sweep(q2, "S")
+    q3, _ = switch(q0E - dt / P.dx * Q2E, q0S - dt / P.dx * Q2S)
+    q3E, Q3E = sweep(q3, "E")
+    q3S, Q3S = sweep(q3, "S")
+    q4, bad = switch(1 / 3 * (-q0E + q1E + 2 * q2E + q3E - 1 / 2 * dt / P.dx * Q3E),
+                     1 / 3 * (-q0S + q1S + 2 * q2S + q3S - 1 / 2 * dt / P.dx * Q3S))
+    return q4, bad
+
+
 def compute_global_vmax_1d(q, P):
     """Weno5_1D.jl:1038-1074."""
     vx, _ = compute_global_vmax(q[:, None, :], P)

@@ -23,6 +23,12 @@ are called unmodified; what the harness does around them is stated per case:
                      restored (the only source edit, see DUAL_PATCH), so that the S branch is live: periodic blast
                      wave 16x16 (2 steps) and the shock-cloud problem (1 step); `nbad` = cells switched to E per stage.
 
+  ref1d_switch       Weno5_1D as shipped on RJ95-2a (N = 64+6, 4 steps): q per step AND `idx`, the list of cells whose
+                     entropy-branch candidate differs from the energy branch by |S(E) - S| >= 1e-5 in the last stage
+                     (ES_Switch, Weno5_1D.jl:238-258 -- it evolves E only but still runs the S sweeps for this list).
+  ref1d_dual_live    the same with the three "E only" override lines of ES_Switch (:252-254) removed (DUAL_PATCH_1D),
+                     i.e. the switch as the author wrote it above them: S state by default, E state where flagged.
+
   ref_arr2img        "next" row f4: Arr2Img (JColorMaps.jl:92-146, the only function translated from that file) on
                      fields of the shock-cloud result with an identity colour table.
 
@@ -51,6 +57,9 @@ GEN = os.path.join(tempfile.gettempdir(), "weno5_jl2py_ref")
 # The one source edit any case makes (case_dual only): the reference's own commented-out switching criterion
 # (Weno5_2D.jl:1740-1741) is restored, i.e. `#dS = abs.(...)` is uncommented and the override `dS = 1` dropped.
 DUAL_PATCH = (("#dS = abs.(q_SE[:,:,8] - q_S[:,:,8])", "dS = abs.(q_SE[:,:,8] - q_S[:,:,8])"), ("\ndS = 1\n", "\n"))
+
+
+DUAL_PATCH_1D = (("    q[:,1:7] = q_E[:,1:7] # E only\n    q[:,8] = E2S(q_E)\n    q[:,9] = q_E[:,8]\n", ""),)
 
 
 def load(name, patch=(), tag="", only=None):
@@ -124,6 +133,26 @@ def case_1d(m1):
     qs, dts = run_1d(m1, np.asfortranarray(q0.reshape(70, 9)), 8)
     save("ref1d_briowu", q=qs, dt=dts, nx=64, gamma=2.0, oob=oob())
     configure_1d(m1, 256, 5.0 / 3.0)
+
+
+def case_1d_switch():
+    """The 1-D ES_Switch: `idx` of the shipped code, and the live switch (override lines removed)."""
+    for name, patch, tag in (("ref1d_switch", (), ""), ("ref1d_dual_live", DUAL_PATCH_1D, "_live")):
+        m1 = load("Weno5_1D", patch=patch, tag=tag)
+        reset_oob()
+        configure_1d(m1, 64, 5.0 / 3.0)
+        q = m1.initial_conditions()
+        qs, dts, idxs = [np.array(q)], [], []
+        for _ in range(4):
+            vxmax = m1.compute_global_vmax(q)
+            dt = m1.courFac * m1.dx / vxmax
+            q, idx, omega = m1.classical_RK4_step(q, dt)
+            qs.append(np.array(q))
+            dts.append(float(dt))
+            flag = np.zeros(q.shape[0])
+            flag[np.asarray(idx, dtype=int).ravel() - 1] = 1.0          # Julia indices are 1-based
+            idxs.append(flag)
+        save(name, q=np.stack(qs), dt=np.array(dts), flag=np.stack(idxs), nx=64, gamma=5.0 / 3.0, oob=oob())
 
 
 # ------------------------------------------------------------------------------------------ 2-D
@@ -315,11 +344,13 @@ def case_arr2img():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["functions", "1d", "shockcloud", "periodic", "dual", "arr2img"]
+    which = sys.argv[1:] or ["functions", "1d", "1d_switch", "shockcloud", "periodic", "dual", "arr2img"]
     os.makedirs(OUT, exist_ok=True)
     t0 = time.time()
     if "1d" in which:
         case_1d(load("Weno5_1D"))
+    if "1d_switch" in which:
+        case_1d_switch()
     if set(which) & {"functions", "shockcloud", "periodic"}:
         m2 = load("Weno5_2D")
         if "functions" in which:
