@@ -15,7 +15,8 @@
 # same entry points and is what the test-suite drives.
 module Weno5GPU
 
-export Weno5Params, Solver, upload!, download, boundaries!, timestep, classical_RK4_step, set_es_switch!, es_switch_count, arr2img,
+export Weno5Params, Solver, upload!, download, boundaries!, timestep, classical_RK4_step, set_es_switch!, es_switch_count, es_switch_mask, comm_halo_mode,
+       pinned_array, free_pinned, pipe_overlapped, arr2img,
        classical_RK4_step!, advance!, compute_divB, compute_global_vmax, interpolateB_center2face,
        state2conserved, WENO5_2D, WENO5_1D, Pipe, pipe_step!
 
@@ -74,6 +75,8 @@ function comm_unique_id()
 end
 comm_init!(s::Solver, rank::Integer, nranks::Integer, id::Vector{UInt8}) =
     check(ccall((:weno5_comm_init, libweno5), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), s.h, rank, nranks, id))
+"0: no communicator, 1: ghost rows through NCCL send/recv, 2: stored straight into the neighbours' ghost rows over peer memory."
+comm_halo_mode(s::Solver) = Int(ccall((:weno5_comm_halo_mode, libweno5), Cint, (Ptr{Cvoid},), s.h))
 
 # ---- state transfer
 function upload!(s::Solver, q::Array{Float64,3}, bxb::Array{Float64,2}, byb::Array{Float64,2})
@@ -116,10 +119,19 @@ classical_RK4_step!(s::Solver, dt::Real) = check(ccall((:weno5_rk4_step, libweno
 """
 Dual-energy mode: run the E sweeps and the entropy-variable S sweeps (weno5_flux_difference_S, Weno5_2D.jl:361)
 every stage and let ES_Switch (:1734) choose per cell with the criterion the reference wrote and disabled
-(:1740): |S(E) - S| >= threshold takes the E state.  `enable = false` is the shipped behaviour.
+(:1740): |S(E) - S| >= threshold takes the E state.  `enable = false` (0) is the shipped 2-D behaviour.
+1-D grids: `enable = 2` is Weno5_1D.jl as shipped -- both branches swept, energy state kept (:252-254), the flags
+(`idx`, :245) available through `es_switch_mask`; `enable = true` (1) drops that override.
 """
-set_es_switch!(s::Solver, enable::Bool=true; threshold::Real=1e-5) =
-    check(ccall((:weno5_set_es_switch, libweno5), Cint, (Ptr{Cvoid}, Cint, Cdouble), s.h, enable ? 1 : 0, threshold))
+set_es_switch!(s::Solver, enable::Union{Bool,Integer}=true; threshold::Real=1e-5) =
+    check(ccall((:weno5_set_es_switch, libweno5), Cint, (Ptr{Cvoid}, Cint, Cdouble), s.h, Cint(enable), threshold))
+"1.0 where |S(E) - S| >= threshold in the last stage; `find(mask .> 0)` is the reference's `idx` (Weno5_1D.jl:245)."
+function es_switch_mask(s::Solver)
+    Nx, Ny = dims(s)
+    mask = is1d(s) ? zeros(Nx) : zeros(Nx, Ny)
+    check(ccall((:weno5_es_switch_mask, libweno5), Cint, (Ptr{Cvoid}, Ptr{Float64}), s.h, mask))
+    return mask
+end
 function es_switch_count(s::Solver)
     n = Ref{Culonglong}(0)
     check(ccall((:weno5_es_switch_count, libweno5), Cint, (Ptr{Cvoid}, Ref{Culonglong}), s.h, n))
@@ -172,7 +184,9 @@ end
 """
 Pipelined host -> host classical_RK4_step (weno5_pipe_*): the grid streams through the GPU in y-slabs
 so that upload, compute and download overlap.  `pipe_step!(pipe, q, bxb, byb, dt, q4, bxb4, byb4)`
-fills the preallocated outputs (which must not alias the inputs) and returns timestep(q4).
+fills the preallocated outputs (no byte of which may lie in an input) and returns timestep(q4).
+The copies overlap the compute only for page-locked arrays: take them from `pinned_array` (weno5_host_alloc);
+ordinary `Array`s are pageable -- correct results, serialised copies (`pipe_overlapped(pipe)` tells which it was).
 """
 mutable struct Pipe
     h::Ptr{Cvoid}
@@ -193,6 +207,17 @@ function pipe_step!(p::Pipe, q::Array{Float64,3}, bxb::Array{Float64,2}, byb::Ar
                 p.h, q, bxb, byb, dt, q4, bxb4, byb4, dtn))
     return dtn[]
 end
+
+"1 if the last pipe_step! got page-locked arrays (its copies overlapped the compute)."
+pipe_overlapped(p::Pipe) = ccall((:weno5_pipe_overlapped, libweno5), Cint, (Ptr{Cvoid},), p.h) == 1
+
+"Page-locked Float64 array of the given shape (weno5_host_alloc); release it with `free_pinned` (weno5_host_free)."
+function pinned_array(dims::Integer...)
+    ptr = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:weno5_host_alloc, libweno5), Cint, (Ref{Ptr{Cvoid}}, Culonglong), ptr, 8 * prod(dims)))
+    return unsafe_wrap(Array, Ptr{Float64}(ptr[]), dims; own=false)
+end
+free_pinned(a::Array{Float64}) = ccall((:weno5_host_free, libweno5), Cint, (Ptr{Cvoid},), pointer(a))
 
 function interpolateB_center2face(p::Weno5Params, q::Array{Float64,3})
     s = Solver(p); upload!(s, q); _, bxb, byb = download(s); return bxb, byb
