@@ -220,7 +220,8 @@ static void choose_segments(int nfaces, int NS, int strips, int &seg_len, int &n
     const int chunks = (nfaces + NS - 1) / NS;
     static const int waves = getenv("WENO5_WAVES") ? atoi(getenv("WENO5_WAVES")) : 4;
     static const int minper = getenv("WENO5_MINPER") ? atoi(getenv("WENO5_MINPER")) : 4;
-    int want = (waves * 296 + strips - 1) / strips;
+    const int resident = flux_resident_ctas();
+    int want = (waves * resident + strips - 1) / strips;
     if (want < 1) want = 1;
     // among want .. 2*want segments per line take the count whose last wave of CTAs is fullest: cost model
     // (waves of 296 resident CTAs) x (chunks per segment + 1 for the prologue); at 4096^2 this picks 8 segments
@@ -230,7 +231,7 @@ static void choose_segments(int nfaces, int NS, int strips, int &seg_len, int &n
     for (int k = want; k <= 2 * want; ++k) {
         const int perk = (chunks + k - 1) / k;
         if (perk < minper && k > want) break;
-        const long nwaves = ((long)k * strips + 295) / 296;
+        const long nwaves = ((long)k * strips + resident - 1) / resident;
         const long cost = nwaves * (perk + 1);
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = k; }
     }

@@ -624,10 +624,305 @@ __global__ void __launch_bounds__(256, 2) flux_ws_kernel(const FluxArgs a, const
     }
 }
 
+// ------------------------------------------------------------------ TMEM-stash flux kernel (3 warps per sub-partition)
+// What caps the FP64 pipe at ~73 % is thread-level parallelism: a face needs ~250 live registers, so a sub-partition
+// holds two warps, and a dependent DFMA issues only every 8 cycles.  Blackwell's tensor memory is idle in this
+// kernel (no MMA anywhere): 256 KB per SM that tcgen05.st / tcgen05.ld move to and from registers, each warp owning
+// the 32 lanes of its quadrant -- a per-thread stash with register-file-like addressing.  This variant parks the
+// 28 minus-side differences (needed only after the stencil has streamed by) and the 17 back-projection coefficients
+// there: 45 doubles = 90 of the CTA's 128 TMEM columns per thread.  That brings the kernel from 248 to <= 168
+// registers WITHOUT local-memory spills (which is what sank the 168-register build of round 1: its spills
+// overflowed the L1 left over next to 200 KB of shared memory), so THREE 128-thread CTAs are resident per SM:
+// 3 warps per sub-partition.  Same phases and arithmetic as flux_kernel.
+__device__ __forceinline__ void tm_st(unsigned taddr, double v)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"((unsigned)__double2loint(v)),
+                 "r"((unsigned)__double2hiint(v))
+                 : "memory");
+}
+template <int ND> __device__ __forceinline__ void tm_ld(unsigned taddr, double v[ND]);
+template <> __device__ __forceinline__ void tm_ld<4>(unsigned taddr, double v[4])
+{
+    unsigned r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = __hiloint2double((int)r[2 * k + 1], (int)r[2 * k]);
+}
+template <> __device__ __forceinline__ void tm_ld<8>(unsigned taddr, double v[8])
+{
+    unsigned r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __hiloint2double((int)r[2 * k + 1], (int)r[2 * k]);
+}
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+constexpr int TM_COLS = 128;                     // TMEM columns per CTA (power of two >= 90)
+constexpr int TM_Q0 = 0;                         // [7 fields][4] minus-side differences: columns 0..55
+constexpr int TM_BACK0 = 56;                     // 17 (+ 7 padding) back-projection coefficients: columns 56..103
+
+// the face flux with the stash in TMEM (difference-first form, see face_flux_diff); every lane of the warp must
+// call it (tcgen05.ld / .st are warp-collective)
+template <class Loader>
+__device__ __forceinline__ void face_flux_tmem(const FaceCoef &c, const double amax[7], double eps, Loader load, unsigned tb, double Fs[7])
+{
+    double P[4][7];
+    double Fa[7], qa[7], comb[7];
+    const double epsq = 0.25 * eps;
+    load(0, Fa, qa);
+    auto kstep = [&](const int k) {
+        double Fb[7], qb[7], dF[7], dq[7], dw[7], dv[7];
+        load(k, Fb, qb);
+#pragma unroll
+        for (int m = 0; m < 7; ++m) {
+            dF[m] = Fb[m] - Fa[m];
+            dq[m] = qb[m] - qa[m];
+            if (k == 1) comb[m] = -Fb[m];
+            if (k == 2) comb[m] = fma(7.0, Fb[m], comb[m]);
+            if (k == 3) comb[m] = fma(7.0, Fb[m], comb[m]);
+            if (k == 4) comb[m] = comb[m] - Fb[m];
+            Fa[m] = Fb[m]; qa[m] = qb[m];
+        }
+        project(c, dF, dw);
+        project(c, dq, dv);
+#pragma unroll
+        for (int m = 0; m < 7; ++m) {
+            if (k <= 4) P[k - 1][m] = fma(amax[m], dv[m], dw[m]);
+            if (k >= 2) tm_st(tb + TM_Q0 + (m * 4 + (k - 2)) * 2, fma(-amax[m], dv[m], dw[m]));
+        }
+    };
+    kstep(1); kstep(2); kstep(3); kstep(4);
+    kstep(5);
+    double first[7];
+    project(c, comb, first);
+#pragma unroll
+    for (int m = 0; m < 7; ++m) {
+        const double second6 = weno_phi6(P[0][m], P[1][m], P[2][m], P[3][m], epsq);
+        Fs[m] = fma(first[m], 1.0 / 12.0, (-1.0 / 6.0) * second6);
+    }
+    tm_wait_st();
+#pragma unroll
+    for (int m = 0; m < 7; ++m) {
+        double Q[4];
+        tm_ld<4>(tb + TM_Q0 + m * 8, Q);
+        const double third6 = weno_phi6(Q[3], Q[2], Q[1], Q[0], epsq);
+        Fs[m] = fma(1.0 / 6.0, third6, Fs[m]);
+    }
+}
+
+template <int DIR> struct TmTile {
+    static constexpr int NT = 128, YW = 16;
+    static constexpr int NS = DIR == 0 ? 64 : NT / YW;
+    static constexpr int NPB = DIR == 0 ? NT / 64 : YW;
+    static constexpr int RS = DIR == 0 ? (NS + 5 + 15) / 16 * 16 : NS + 5;      // x: 80 (bank-conflict-free wrap), y: 13
+    static constexpr int CBS = RS * NPB;
+    static constexpr int FBS = (NS + 1) * NPB;
+    static constexpr int BOX_X = DIR == 0 ? NS + 2 : NPB, BOX_Y = DIR == 0 ? NPB : NS;
+    static constexpr int FST = BOX_X * BOX_Y;
+    static constexpr int OFFQ = (CQ_COUNT * CBS + 7 * FBS + 15) / 16 * 16;
+    static constexpr int STQ = 8 * FST;
+    static constexpr int STU = DIR == 0 ? 0 : 18 * FST;
+    static constexpr int SMEM = (OFFQ + (STQ + 15) / 16 * 16 + STU) * (int)sizeof(double) + 32;
+    __device__ static __forceinline__ int sti(int s, int p, int e) { return DIR == 0 ? p * BOX_X + s + e : s * NPB + p; }
+    __device__ static __forceinline__ int cbi(int slot, int p) { return DIR == 0 ? p * RS + slot : slot * NPB + p; }
+    __device__ static __forceinline__ int fbi(int slot, int p) { return DIR == 0 ? p * (NS + 1) + slot : slot * NPB + p; }
+};
+
+template <int DIR>
+__global__ void __launch_bounds__(128, 3) flux_tm_kernel(const FluxArgs a, const __grid_constant__ FluxMaps tmap)
+{
+    using T = TmTile<DIR>;
+    constexpr int NT = T::NT, NS = T::NS, NPB = T::NPB, RS = T::RS, CBS = T::CBS, FBS = T::FBS;
+    extern __shared__ __align__(128) double sm[];
+    double *cb = sm;
+    double *fb = sm + CQ_COUNT * CBS;
+    double *stq = sm + T::OFFQ;
+    double *stu = stq + (T::STQ + 15) / 16 * 16;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(stu + T::STU);   // [0] state, [1] operands
+    unsigned *tmem_base = reinterpret_cast<unsigned *>(bars + 2);
+
+    const double dt = *a.dtp;
+    if (dt == 0.0) return;
+
+    const int t = threadIdx.x;
+    const int s = DIR == 0 ? (t % NS) : (t / NPB);
+    const int p = DIR == 0 ? (t / NS) : (t % NPB);
+    const int line = blockIdx.x * NPB + p;
+    const int seg = blockIdx.y;
+    const int fA = 2 + seg * a.seg_len;
+    const int fB = min(fA + a.seg_len, a.N - 3);
+    const int fStart = seg == 0 ? fA : fA - 1;
+    const bool line_ok = line >= G && line < a.NP - G;
+    bool row_sel = true;
+    if (DIR == 0 && a.row_mode != 0) {
+        const int l0 = blockIdx.x * NPB, l1 = min(l0 + NPB, a.NP) - 1;
+        const bool any_interior = l1 >= G && l0 < a.NP - G;
+        const bool any_ghost = l0 < G || l1 >= a.NP - G;
+        if (a.row_mode == 1 ? !any_interior : !any_ghost) return;
+        row_sel = (line >= G && line < a.NP - G) == (a.row_mode == 1);
+    }
+
+    // tensor memory: warp 0 allocates the CTA's columns; every warp addresses the 32 lanes of its own quadrant
+    if (t < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base)), "r"(TM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (t == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const unsigned tb = *tmem_base + ((unsigned)((t >> 5) * 32) << 16);
+
+    unsigned phq = 0, phu = 0;
+    if (t == 0) tma_issue_state<DIR, NT, T::YW>(a, &tmap, stq, &bars[0], fStart + 3);
+    for (int e = t; e < 5 * NPB; e += NT) {
+        const int sl = DIR == 0 ? e % 5 : e / NPB;
+        const int pp = DIR == 0 ? e / 5 : e % NPB;
+        const size_t g = cell_index<DIR>(a, fStart - 2 + sl, blockIdx.x * NPB + pp);
+        double q[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) q[k] = __ldg(a.qc[perm<DIR>(k)] + g);
+        cell_store<CBS, 0>(a, cb, q, T::cbi(sl, pp));
+    }
+
+    int r0 = 0;
+    for (int s0 = fStart; s0 < fB; s0 += NS) {
+        int sl[6];
+        {
+            int r = r0 + s;
+            if (r >= RS) r -= RS;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { sl[k] = r; r = (r + 1 == RS) ? 0 : r + 1; }
+        }
+        // ---------------- cell phase
+        mbar_wait(&bars[0], phq); phq ^= 1u;
+        {
+            const int si = T::sti(s, p, (s0 + 3) & 1);
+            double q[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) q[k] = stq[perm<DIR>(k) * T::FST + si];
+            cell_store<CBS, 0>(a, cb, q, T::cbi(sl[5], p));
+        }
+        __syncthreads();
+
+        const bool upd_ok = (s0 + s > fStart) && (s0 + s < fB) && (s0 + s >= G) && (s0 + s < a.N - G) && line_ok && row_sel;
+        if (t == 0) {
+            if constexpr (DIR == 1) tma_issue_operands<NT, T::YW>(a, &tmap, stu, &bars[1], s0);
+            if (s0 + NS < fB) tma_issue_state<DIR, NT, T::YW>(a, &tmap, stq, &bars[0], s0 + NS + 3);
+        }
+
+        // ---------------- face phase: every lane computes (warp-collective TMEM accesses); faces past the segment
+        // work on whatever the ring holds and store nothing
+        const int f = s0 + s;
+        {
+            const int iL = T::cbi(sl[2], p), iR = T::cbi(sl[3], p);
+            double amax[7];
+            face_amax(cb[CQ_V1 * CBS + iL], cb[CQ_LF * CBS + iL], cb[CQ_LA * CBS + iL], cb[CQ_LS * CBS + iL],
+                      cb[CQ_V1 * CBS + iR], cb[CQ_LF * CBS + iR], cb[CQ_LA * CBS + iR], cb[CQ_LS * CBS + iR], amax);
+            FaceCoef fc;
+            face_coefficients(cb[CQ_Q0 * CBS + iL], cb[CQ_Q0 * CBS + iR], cb[CQ_V1 * CBS + iL], cb[CQ_V1 * CBS + iR],
+                              cb[CQ_V2 * CBS + iL], cb[CQ_V2 * CBS + iR], cb[CQ_V3 * CBS + iL], cb[CQ_V3 * CBS + iR],
+                              cb[CQ_B1 * CBS + iL], cb[CQ_B1 * CBS + iR], cb[(CQ_Q0 + 4) * CBS + iL],
+                              cb[(CQ_Q0 + 4) * CBS + iR], cb[(CQ_Q0 + 5) * CBS + iL], cb[(CQ_Q0 + 5) * CBS + iR],
+                              cb[(CQ_Q0 + 6) * CBS + iL], cb[(CQ_Q0 + 6) * CBS + iR], a.gam, a.g2, fc);
+            {
+                // the back-projection coefficients are cold until the stencil has streamed by: park them in TMEM
+                BackCoef bc;
+                split_back(fc, bc);
+                const double *bv = reinterpret_cast<const double *>(&bc);
+#pragma unroll
+                for (int k = 0; k < 17; ++k) tm_st(tb + TM_BACK0 + 2 * k, bv[k]);
+            }
+            auto load = [&](int k, double F[7], double x[7]) {
+                const int ii = T::cbi(sl[k], p);
+#pragma unroll
+                for (int m = 0; m < 7; ++m) {
+                    F[m] = cb[(CQ_F0 + m) * CBS + ii];
+                    x[m] = cb[(CQ_Q0 + m) * CBS + ii];
+                }
+            };
+            double fh[7], Fs[7];
+            face_flux_tmem(fc, amax, a.eps, load, tb, Fs);
+            {
+                BackCoef bc;
+                double *bv = reinterpret_cast<double *>(&bc);
+                tm_ld<8>(tb + TM_BACK0, bv);
+                tm_ld<8>(tb + TM_BACK0 + 16, bv + 8);
+                double last[4];
+                tm_ld<4>(tb + TM_BACK0 + 32, last);
+                bv[16] = last[0];
+                back_project(bc, Fs, fh);
+            }
+            if (f < fB) {
+                const int io = T::fbi(s + 1, p);
+#pragma unroll
+                for (int m = 0; m < 7; ++m) fb[m * FBS + io] = fh[m];
+                if (line < a.NP && row_sel && (seg == 0 || f >= fA)) {
+                    constexpr int TV = DIR == 0 ? CQ_V2 : CQ_V3;
+                    const double bv2 = cb[CQ_B1 * CBS + iL] * cb[TV * CBS + iL] + cb[CQ_B1 * CBS + iR] * cb[TV * CBS + iR];
+                    const size_t g = DIR == 0 ? (size_t)f + (size_t)a.pitch * line : (size_t)line + (size_t)a.pitch * f;
+                    a.bs[g] = fma(0.5, bv2, fh[DIR == 0 ? 4 : 5]);
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---------------- update phase
+        {
+            const int c = s0 + s;
+            if constexpr (DIR == 1) { mbar_wait(&bars[1], phu); phu ^= 1u; }
+            if (upd_ok) {
+                const int i0 = T::fbi(s, p), i1 = T::fbi(s + 1, p);
+                const size_t g = DIR == 0 ? (size_t)c + (size_t)a.pitch * line : (size_t)line + (size_t)a.pitch * c;
+                if constexpr (DIR == 0) {
+                    constexpr int fi[6] = {0, 1, 2, 3, 5, 6};
+#pragma unroll
+                    for (int m = 0; m < 6; ++m) a.rhs[m][g] = fb[fi[m] * FBS + i1] - fb[fi[m] * FBS + i0];
+                } else {
+                    constexpr int fi[6] = {0, 3, 1, 2, 4, 6};
+                    const int ic = T::cbi(sl[2], p);
+                    const double cx = a.c_dx * dt, cy = a.c_dy * dt;
+#pragma unroll
+                    for (int m = 0; m < 6; ++m) {
+                        const double dfy = fb[fi[m] * FBS + i1] - fb[fi[m] * FBS + i0];
+                        const double qcen = cb[(CQ_Q0 + fi[m]) * CBS + ic];
+                        const double rxm = stu[m * T::FST + t];
+                        double b = a.stage <= 3 ? stu[(6 + m) * T::FST + t] : 0.0;
+                        const double acm = a.stage >= 3 ? stu[(12 + m) * T::FST + t] : 0.0;
+                        if (a.stage == 2) a.acc[m][g] = qcen - b;
+                        if (a.stage == 3) a.acc[m][g] = fma(2.0, qcen, acm);
+                        if (a.stage == 4) b = (acm + qcen) * (1.0 / 3.0);
+                        a.qn[m][g] = fma(-cx, rxm, fma(-cy, dfy, b));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        for (int e = t; e < 7 * NPB; e += NT) {
+            const int m = e / NPB, pp = e % NPB;
+            fb[m * FBS + T::fbi(0, pp)] = fb[m * FBS + T::fbi(NS, pp)];
+        }
+        r0 += NS;
+        while (r0 >= RS) r0 -= RS;
+    }
+    __syncthreads();
+    if (t < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_base), "r"(TM_COLS));
+}
+
 // Launch variants, chosen once per process by WENO5_FLUX_VARIANT (development knob; the default is the
 // fastest measured on B200):
 //   2: flux_kernel, cp.async (LDGSTS) staging     4: flux_kernel, TMA tensor-map staging
-//   5: flux_ws_kernel, warp-specialised, TMA staging (default)
+//   5: flux_ws_kernel, warp-specialised, TMA staging
+//   6: flux_tm_kernel, TMEM stash, 3 CTAs per SM, TMA staging
 // All: x tile 2 rows x 64 faces, y tile 8 face rows x 16 columns per march step, 2 CTAs per SM.
 // 1-D grids, the entropy branch and contexts without tensor maps always take flux_kernel with cp.async.
 static int flux_variant()
@@ -636,7 +931,7 @@ static int flux_variant()
     if (v < 0) {
         const char *e = getenv("WENO5_FLUX_VARIANT");
         v = e ? atoi(e) : W5_DEFAULT_VARIANT;
-        if (v != 2 && v != 4 && v != 5) v = W5_DEFAULT_VARIANT;
+        if (v != 2 && v != 4 && v != 5 && v != 6) v = W5_DEFAULT_VARIANT;
     }
     return v;
 }
@@ -686,6 +981,16 @@ template <int DIR> static void launch_flux_ws(const FluxArgs &a, cudaStream_t s)
     else launch_flux_ws_t<DIR, 224, 32>(a, s);       // measured: 15.05 ms/step (216/40: 15.25, 208/48: 15.22)
 }
 
+template <int DIR> static void launch_flux_tm(const FluxArgs &a, cudaStream_t s)
+{
+    using T = TmTile<DIR>;
+    static_assert((T::SMEM + 1024) * 3 <= 227 * 1024, "shared memory budget (3 CTAs per SM)");
+    ensure_smem<flux_tm_kernel<DIR>>(T::SMEM);
+    dim3 grid((a.NP + T::NPB - 1) / T::NPB, a.nseg, 1);
+    const FluxMaps *tm = reinterpret_cast<const FluxMaps *>(DIR == 0 ? a.tmap_x : a.tmap_y);
+    flux_tm_kernel<DIR><<<grid, T::NT, T::SMEM, s>>>(a, *tm);
+}
+
 template <int DIR>
 static void launch_flux(const FluxArgs &a, cudaStream_t s)
 {
@@ -694,6 +999,7 @@ static void launch_flux(const FluxArgs &a, cudaStream_t s)
     // entropy branch (dual-energy mode): its state planes are not consecutive in the pool, so it takes the
     // cp.async staging, which addresses every plane through its own pointer
     if (a.branch == 1) launch_flux_t<DIR, 128, 16, 2, false, 1>(a, s);
+    else if (tma_ok && v == 6) launch_flux_tm<DIR>(a, s);
     else if (tma_ok && v == 5) launch_flux_ws<DIR>(a, s);
     else if (tma_ok && v == 4) launch_flux_t<DIR, 128, 16, 2, true>(a, s);
     else launch_flux_t<DIR, 128, 16, 2, false>(a, s);
@@ -706,6 +1012,7 @@ void launch_flux_y(const FluxArgs &a, cudaStream_t s) { launch_flux<1>(a, s); }
 int flux_chunk(int dir) { return dir == 0 ? 64 : 8; }
 int flux_lines_per_cta(int dir) { return dir == 0 ? 2 : 16; }
 int flux_uses_tma() { return flux_variant() != 2; }
+int flux_resident_ctas() { return (flux_variant() == 6 ? 3 : 2) * 148; }
 void flux_box(int dir, int box[2])
 {
     if (dir == 0) { box[0] = 64 + 2; box[1] = 2; } else { box[0] = 16; box[1] = 8; }

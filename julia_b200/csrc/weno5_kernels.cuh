@@ -139,6 +139,7 @@ void launch_arr2img(const double *field, const Geom &g, double lo, double hi, in
 int flux_chunk(int dir);          // faces per march step of the active launch variant
 int flux_lines_per_cta(int dir);  // lines across the sweep per CTA
 int flux_uses_tma();              // 1 if the active variant stages through TMA tensor maps
+int flux_resident_ctas();         // CTAs of the flux kernel resident on the GPU at a time (wave planning)
 void flux_box(int dir, int box[2]);   // TMA box (cells along x, rows along y) of one march step
 
 }  // namespace w5

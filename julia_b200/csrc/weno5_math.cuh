@@ -298,6 +298,48 @@ W5_HD void project(const FaceCoef &c, const double x[7], double w[7])
     w[3] = fma(c.ke_n, n, x[0]);
 }
 
+// Two vectors through the same projection, statement by statement in lock-step.  On B200 a DFMA whose three
+// sources are three different vector registers takes ~3 cycles of the FP64 pipe's 2-cycle slot -- the register
+// file delivers two 64-bit operands per slot (scripts/microbench/fp64_operands.cu: 0.325 instead of 0.5 warp
+// instructions per cycle) -- unless one source comes from the operand-reuse cache, i.e. the previous instruction read
+// the same register in the same position.  Projecting dF and dq with the same coefficients back to back gives
+// every second multiply-add that reuse.  Same operations and rounding as two project() calls.
+W5_HD void project_pair(const FaceCoef &c, const double x[7], const double y[7], double w[7], double v[7])
+{
+    double nx = fma(-c.hv2, x[0], -x[6]), ny = fma(-c.hv2, y[0], -y[6]);
+    nx = fma(c.Bz, x[5], nx); ny = fma(c.Bz, y[5], ny);
+    nx = fma(c.By, x[4], nx); ny = fma(c.By, y[4], ny);
+    nx = fma(c.vz, x[3], nx); ny = fma(c.vz, y[3], ny);
+    nx = fma(c.vy, x[2], nx); ny = fma(c.vy, y[2], ny);
+    nx = fma(c.vx, x[1], nx); ny = fma(c.vx, y[1], ny);
+    double tx = c.btz * x[5], ty = c.btz * y[5];
+    tx = fma(c.bty, x[4], tx); ty = fma(c.bty, y[4], ty);
+    double ux = c.btz * x[3], uy = c.btz * y[3];
+    ux = fma(c.bty, x[2], ux); uy = fma(c.bty, y[2], uy);
+    double pfx = c.kf_t * tx, pfy = c.kf_t * ty;
+    pfx = fma(c.kf_n, nx, pfx); pfy = fma(c.kf_n, ny, pfy);
+    double mfx = c.kf_u * ux, mfy = c.kf_u * uy;
+    mfx = fma(c.kf_2, x[1], mfx); mfy = fma(c.kf_2, y[1], mfy);
+    mfx = fma(c.kf_1, x[0], mfx); mfy = fma(c.kf_1, y[0], mfy);
+    double psx = c.ks_t * tx, psy = c.ks_t * ty;
+    psx = fma(c.ks_n, nx, psx); psy = fma(c.ks_n, ny, psy);
+    double msx = c.ks_u * ux, msy = c.ks_u * uy;
+    msx = fma(c.ks_2, x[1], msx); msy = fma(c.ks_2, y[1], msy);
+    msx = fma(c.ks_1, x[0], msx); msy = fma(c.ks_1, y[0], msy);
+    double Ax = c.ka_4 * x[3], Ay = c.ka_4 * y[3];
+    Ax = fma(c.ka_3, x[2], Ax); Ay = fma(c.ka_3, y[2], Ay);
+    Ax = fma(c.ka_1, x[0], Ax); Ay = fma(c.ka_1, y[0], Ay);
+    double Bx = c.kb_6 * x[5], By = c.kb_6 * y[5];
+    Bx = fma(c.kb_5, x[4], Bx); By = fma(c.kb_5, y[4], By);
+    w[0] = pfx + mfx; v[0] = pfy + mfy;
+    w[6] = pfx - mfx; v[6] = pfy - mfy;
+    w[2] = psx + msx; v[2] = psy + msy;
+    w[4] = psx - msx; v[4] = psy - msy;
+    w[1] = Ax + Bx;   v[1] = Ay + By;
+    w[5] = Ax - Bx;   v[5] = Ay - By;
+    w[3] = fma(c.ke_n, nx, x[0]); v[3] = fma(c.ke_n, ny, y[0]);
+}
+
 // Back-projection coefficients only (the part of FaceCoef that is cold during the stencil
 // streaming); kept separate so that a kernel can park them in shared memory.
 struct BackCoef {
@@ -588,8 +630,12 @@ W5_HD void face_flux_diff(const FaceCoef &c, const double amax[7], double eps, L
             if (k == 4) comb[m] = comb[m] - Fb[m];
             Fa[m] = Fb[m]; qa[m] = qb[m];
         }
-        project_br<BR>(c, dF, dw);
-        project_br<BR>(c, dq, dv);
+        if constexpr (BR == 0) {
+            project_pair(c, dF, dq, dw, dv);
+        } else {
+            project_br<BR>(c, dF, dw);
+            project_br<BR>(c, dq, dv);
+        }
 #pragma unroll
         for (int m = 0; m < 7; ++m) {
             if (k <= 4) P[k - 1][m] = fma(amax[m], dv[m], dw[m]);

@@ -364,9 +364,9 @@ def test_fused_cfl_reduction_equals_stepwise(case):
 
 
 def test_tma_and_ldgsts_staging_agree_to_roundoff(tmp_path):
-    """Three instantiations of the flux sweep: the warp-specialised kernel (default, WENO5_FLUX_VARIANT=5: face
-    warps + helper warps, TMA staging), the single-role kernel with TMA staging (4) and with
-    cp.async (2).  The arithmetic is the same source, but they are separate
+    """Four instantiations of the flux sweep: the warp-specialised kernel (WENO5_FLUX_VARIANT=5: face
+    warps + helper warps, TMA staging), the TMEM-stash kernel (6: 168 registers, 3 CTAs per SM), the single-role
+    kernel with TMA staging (4) and with cp.async (2).  The arithmetic is the same source, but they are separate
     template instantiations and ptxas contracts a few multiply-adds of the difference-first projection
     differently (measured 2.7e-15 after 3 steps; the 12-projection form, -DW5_FACE_PLAIN, is bit-equal):
     results agree to round-off.  Runs on one GPU vs slabs and the pipelined host step use ONE
@@ -383,13 +383,13 @@ def test_tma_and_ldgsts_staging_agree_to_roundoff(tmp_path):
         "s = Solver(g); s.upload(q, bx, by); s.advance(3); out = s.download()\n"
         "np.savez(sys.argv[1], q=out[0], bx=out[1], by=out[2])\n" % ROOT)
     res = {}
-    for variant in ("5", "4", "2"):
+    for variant in ("5", "6", "4", "2"):
         out = str(tmp_path / f"v{variant}.npz")
         env = dict(os.environ, WENO5_FLUX_VARIANT=variant)
         subprocess.check_call([sys.executable, "-c", code, out], env=env)
         res[variant] = np.load(out)
     for k in ("q", "bx", "by"):
-        for other in ("4", "2"):
+        for other in ("6", "4", "2"):
             assert np.abs(res["5"][k] - res[other][k]).max() <= 1e-13 * np.abs(res["5"][k]).max(), (k, other)
     assert np.isfinite(res["5"]["q"]).all()
 
