@@ -363,6 +363,18 @@ def run_strong(problem, nx, ny_global, steps, rank, world, local, lib, torch, di
             out["efficiency_vs_n1"] = t1 / (world * ms / steps)
             out["n1_ms_per_step"] = t1
             out["n1_source"] = "gpurun_out/strong_n1.json, written by the N=1 run of this session"
+        else:
+            # no N=1 run on this box in this session: the committed N=1 measurement of the same leg (another box of
+            # the same pool), labelled as such
+            try:
+                with open(os.path.join(ROOT, "profiles", "r2_logs", "strong_n1_committed.json")) as f:
+                    ref = json.load(f).get(key)
+            except (OSError, ValueError):
+                ref = None
+            if ref:
+                out["efficiency_vs_committed_n1"] = ref["ms_per_step"] / (world * ms / steps)
+                out["n1_ms_per_step"] = ref["ms_per_step"]
+                out["n1_source"] = "profiles/r2_logs/strong_n1_committed.json (N=1 measured in an earlier run, not on this box)"
     return out
 
 
