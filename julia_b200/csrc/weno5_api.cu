@@ -1037,6 +1037,9 @@ static int enqueue_step(weno5_ctx *c)
     return 0;
 }
 
+// 1-D, energy branch, line fits one cluster: the whole step loop runs in one cluster-resident kernel
+static bool use_line1d(const weno5_ctx *c) { return c->g.is1d && !c->dual && !c->profiling && line1d_chunk(c->g.NXI) > 0; }
+
 extern "C" int weno5_rk4_step(weno5_ctx *c, double dt)
 {
     if (!c) return fail(WENO5_ERR_ARG, "null argument");
@@ -1045,7 +1048,12 @@ extern "C" int weno5_rk4_step(weno5_ctx *c, double dt)
     DevGuard dg_; CU(dg_.set(c->device));
     c->h_ctl[8] = dt;
     CU(cudaMemcpyAsync(c->ctl, c->h_ctl + 8, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    if (int r = enqueue_step(c)) return r;
+    if (use_line1d(c)) {
+        CU(launch_line1d(c->Q0.q, c->ctl, c->g, c->side, 1, dt, c->P.dx, c->P.gamma, c->P.eps, c->P.cfl, c->stream));
+        c->launches++;
+    } else {
+        if (int r = enqueue_step(c)) return r;
+    }
     if (int r = wait_exchange(c)) return r;
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());
@@ -1085,6 +1093,12 @@ extern "C" int weno5_advance(weno5_ctx *c, int nsteps, double tmax, double *t, i
     double *h = c->h_ctl + 8;
     h[0] = 0.0; h[1] = t ? *t : 0.0; h[2] = 0.0; h[3] = 0.0; h[4] = tmax > 0.0 ? tmax : 0.0; h[5] = 0.0; h[6] = 0.0;
     CU(cudaMemcpyAsync(c->ctl, h, 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (use_line1d(c) && nsteps > 0) {
+        // (:51-71 of Weno5_1D.jl: vmax -> dt -> classical_RK4_step, until nstep / tmax) inside ONE kernel
+        CU(launch_line1d(c->Q0.q, c->ctl, c->g, c->side, nsteps, 0.0, c->P.dx, c->P.gamma, c->P.eps, c->P.cfl, c->stream));
+        c->launches++;
+        nsteps = 0;
+    }
     // from the second step on the CFL reduction rides on stage 4 of the step before (2-D, E-only path)
     c->fuse_vmax = !c->dual && !c->g.is1d && nsteps > 1 && !getenv("WENO5_NO_FUSED_VMAX");
     if (c->fuse_vmax) CU(cudaMemsetAsync(c->vmax_next, 0, 2 * sizeof(unsigned long long), c->stream));

@@ -136,6 +136,11 @@ void launch_totals(const double *const planes[], int nplanes, const Geom &g, dou
 // Arr2Img (JColorMaps.jl:92-146) up to the colour-table lookup; keys: 3 x u64 scratch, rng: 2 doubles (range used)
 void launch_arr2img(const double *field, const Geom &g, double lo, double hi, int log_scale, int ncolours,
                     unsigned long long *keys, short *out, double *rng, cudaStream_t s);
+// 1-D solver as one cluster-resident kernel (weno5_line1d.cu): cells per CTA, or 0 if the line does not fit;
+// nsteps CFL steps of the driver loop (fixed_dt <= 0) or one classical_RK4_step with the given dt
+int line1d_chunk(int N);
+cudaError_t launch_line1d(double *const q9[NCELL], double *ctl, const Geom &g, const int side[4], int nsteps, double fixed_dt,
+                          double dx, double gam, double eps, double cfl, cudaStream_t s);
 int flux_chunk(int dir);          // faces per march step of the active launch variant
 int flux_lines_per_cta(int dir);  // lines across the sweep per CTA
 int flux_uses_tma();              // 1 if the active variant stages through TMA tensor maps

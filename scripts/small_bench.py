@@ -1,5 +1,6 @@
 """ms/step of the launch-bound configurations (BASELINE configs 1 and 2, plus 1024^2 / 2048^2), device-resident
-weno5_advance, with and without the captured-graph replay (WENO5_NO_GRAPH=1)."""
+weno5_advance, with and without the captured-graph replay (WENO5_NO_GRAPH=1).  The 1-D line runs as one
+cluster-resident kernel (weno5_line1d.cu); WENO5_NO_LINE1D=1 in the environment gives the multi-kernel figures."""
 import os
 import sys
 import time
@@ -31,7 +32,7 @@ def run(name, make, steps):
             out[graph] = (time.perf_counter() - t0) / steps * 1e3
     cells = g.nx * g.ny
     print(f"{name:28s} {cells:9d} cells: {out[0]:8.4f} ms/step enqueued, {out[1]:8.4f} ms/step graph replay "
-          f"({cells / out[1] / 1e3:.3e} cell-updates/s)")
+          f"({cells / (out[1] * 1e-3):.3e} cell-updates/s)")
 
 
 if __name__ == "__main__":

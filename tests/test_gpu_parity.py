@@ -198,6 +198,46 @@ def test_1d_config1_shock_tube_1024():
 
 
 # ------------------------------------------------------------------ API behaviour
+@pytest.mark.parametrize("case", ["rj95_1024", "briowu_200", "periodic_300_ragged"])
+def test_cluster_1d_kernel_matches_multi_kernel_path(case, monkeypatch):
+    """The 1-D solver as one cluster-resident kernel (weno5_line1d.cu: 8 CTAs, DSMEM halos, step loop and CFL
+    reduction inside the kernel) against the same run through the multi-kernel path (WENO5_NO_LINE1D): same device
+    functions and update formulas, so round-off agreement (separate instantiations: ptxas may contract a few
+    multiply-adds differently), identical step count and time."""
+    if case == "rj95_1024":
+        g, q = pr.rj95_2a(1024)
+    elif case == "briowu_200":
+        g, q = pr.brio_wu(200)
+    else:
+        g = pr.Grid(nx=300, ny=1, xsize=1.0, bc_x=pr.PERIODIC)
+        x = g.xc()
+        q = np.zeros((g.Nx, 9), order="F")
+        for i in range(g.Nx):
+            s_, c_ = np.sin(2 * np.pi * x[i]), np.cos(2 * np.pi * x[i])
+            q[i] = pr.state2conserved(1.0 + 0.2 * s_, 0.5 + 0.1 * c_, 0.1 * s_, -0.1 * c_, 0.75, 0.3 + 0.1 * c_, 0.2 * s_,
+                                      1.0 + 0.1 * s_, g.gam)
+    res = {}
+    for mode in ("cluster", "multi"):
+        if mode == "multi":
+            monkeypatch.setenv("WENO5_NO_LINE1D", "1")
+        else:
+            monkeypatch.delenv("WENO5_NO_LINE1D", raising=False)
+        with Solver(g) as s:
+            s.upload(q)
+            l0 = s.launch_count()
+            t, n = s.advance(7)
+            adv_launches = s.launch_count() - l0
+            dt = s.timestep()[0]
+            s.rk4_step(dt)
+            res[mode] = (s.download(), t, n, adv_launches)
+    (qa, ta, na, la), (qb, tb, nb, lb) = res["cluster"], res["multi"]
+    assert na == nb == 7 and abs(ta - tb) <= 1e-14 * tb
+    assert la == 1 and lb > 50                     # one launch for the whole loop vs ~15 per step
+    for c in range(9):
+        scale = max(np.abs(qb[:, c]).max(), 1e-3)
+        assert np.abs(qa[:, c] - qb[:, c]).max() <= 1e-12 * scale, (case, c)
+
+
 def test_one_shot_call_equals_handle_path():
     g, q, bx, by = pr.random_state(40, 24, seed=9)
     dt = 0.4 * O.timestep_2d(g, q)[0]
