@@ -414,7 +414,10 @@ def run_gpu(args):
         uid = pt.broadcast_unique_id(Solver.comm_unique_id, rank, dist)
         s.comm_init(rank, world, uid)
     s.upload(q, bx, by)
-    halo_mode = {0: "none (one GPU)", 1: "nccl send/recv, packed messages", 2: "peer-memory push (CUDA IPC), one kernel per stage"}[s.halo_mode()]
+    halo_mode = {0: "none (one GPU)", 1: "nccl send/recv, packed messages; nccl all-reduce",
+                 2: "peer-memory push (CUDA IPC), one kernel per stage; nccl all-reduce",
+                 3: "peer-memory push (CUDA IPC), one kernel per stage, waited for inside the next x sweep; "
+                    "all-reduce over peer memory inside the dt kernel"}[s.halo_mode()]
     stream = torch.cuda.ExternalStream(lib.weno5_stream(s.h), device=torch.device("cuda", local))
 
     def sync_all():

@@ -71,11 +71,14 @@ int weno5_destroy(weno5_ctx *ctx);
  * distributed by the host program (Julia Distributed / MPI / torch.distributed). */
 int weno5_comm_unique_id(unsigned char id[128]);
 int weno5_comm_init(weno5_ctx *ctx, int rank, int nranks, const unsigned char id[128]);
-/* How the ghost rows travel: 0 no communicator, 1 NCCL send/recv through packed messages, 2 direct stores into
- * the neighbours' ghost rows over peer memory (CUDA IPC, one process per GPU on one node; the default whenever
- * every rank can map its neighbours -- WENO5_HALO=nccl in the environment forces 1).  The max-allreduce of the
- * wave speeds (timestep, Weno5_2D.jl:1930) is NCCL in both modes. */
+/* How the ranks talk: 0 no communicator; 1 NCCL send/recv of packed ghost-row messages and an NCCL max-all-reduce of
+ * the wave speeds (timestep, Weno5_2D.jl:1930); 2 ghost rows stored straight into the neighbours' planes over peer
+ * memory (CUDA IPC, one process per GPU on one node), all-reduce still NCCL; 3 (the default whenever every rank can
+ * map the others) additionally the all-reduce as a peer-memory exchange inside the dt kernel.  WENO5_HALO=nccl in the
+ * environment forces 1, WENO5_ALLREDUCE=nccl forces 2. */
 int weno5_comm_halo_mode(const weno5_ctx *ctx);
+/* weno5_destroy of a handle that passed weno5_comm_init is COLLECTIVE over its ranks in mode 2 (every rank unmaps its
+ * neighbours' memory before anyone frees its own). */
 
 /* ---- state transfer.  Host arrays cover the LOCAL slab: (Nx, ny_local+6, 9) etc. */
 /* q/bxb/byb as produced by initial_conditions() (Weno5_2D.jl:2001) and

@@ -159,7 +159,11 @@ struct weno5_ctx {
     double *peer_pool_up = nullptr, *peer_pool_down = nullptr;
     unsigned long long *peer_flags_up = nullptr, *peer_flags_down = nullptr;
     int peer_ny_up = 0, peer_ny_down = 0;
-    unsigned long long *sync_flags = nullptr;    // [0] last push from below, [1] from above, [2] block counter
+    unsigned long long *sync_flags = nullptr;    // [0] last push from below, [1] from above, [2] block counter, [8..] all-reduce slots
+    unsigned long long *share_slots[SHARE_MAX_RANKS] = {};   // every rank's all-reduce slot array (own included), or null
+    std::vector<void *> ipc_opened;              // everything cudaIpcOpenMemHandle returned (closed in weno5_destroy)
+    bool share_ok = false;                       // the dt all-reduce runs over peer memory inside dt_kernel
+    unsigned long long share_seq = 0;
     unsigned long long xseq = 0, peer_wait_seq = 0;
     // instrumentation
     unsigned long long launches = 0;
@@ -388,11 +392,17 @@ extern "C" int weno5_destroy(weno5_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
     if (c->step_graph) cudaGraphExecDestroy(c->step_graph);
-    if (c->peer_pool_up) cudaIpcCloseMemHandle(c->peer_pool_up);
-    if (c->peer_pool_down && c->peer_pool_down != c->peer_pool_up) cudaIpcCloseMemHandle(c->peer_pool_down);
-    if (c->peer_flags_up) cudaIpcCloseMemHandle(c->peer_flags_up);
-    if (c->peer_flags_down && c->peer_flags_down != c->peer_flags_up) cudaIpcCloseMemHandle(c->peer_flags_down);
+    for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
+    c->ipc_opened.clear();
     cudaGetLastError();
+    if (c->comm && c->peer_ok && c->nranks > 1 && c->comm_stream && g_nccl.AllReduce) {
+        // the neighbours map this rank's pool and flag words: nobody frees before everybody has unmapped (CUDA leaves
+        // freeing exported memory that is still mapped elsewhere undefined) -- a barrier over the communicator, which
+        // makes weno5_destroy collective for handles that passed weno5_comm_init
+        if (g_nccl.AllReduce(c->vmax_bits, c->vmax_bits, 1, ncclUint64, ncclMax, c->comm, c->comm_stream) == ncclSuccess)
+            cudaStreamSynchronize(c->comm_stream);
+        cudaGetLastError();
+    }
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     cudaFree(c->sync_flags);
     if (c->dual_pool) cudaFree(c->dual_pool);
@@ -427,8 +437,8 @@ struct PeerBlob { cudaIpcMemHandle_t pool, flags; int ny_local; int pid; };
 static int setup_peer_halo(weno5_ctx *c)
 {
     const int nranks = c->nranks;
-    CU(cudaMalloc(&c->sync_flags, 8 * sizeof(unsigned long long)));
-    CU(cudaMemset(c->sync_flags, 0, 8 * sizeof(unsigned long long)));
+    CU(cudaMalloc(&c->sync_flags, (8 + SHARE_SLOT_WORDS) * sizeof(unsigned long long)));
+    CU(cudaMemset(c->sync_flags, 0, (8 + SHARE_SLOT_WORDS) * sizeof(unsigned long long)));
     PeerBlob mine;
     memset(&mine, 0, sizeof(mine));
     int ok = getenv("WENO5_HALO") && !strcmp(getenv("WENO5_HALO"), "nccl") ? 0 : 1;
@@ -443,17 +453,26 @@ static int setup_peer_halo(weno5_ctx *c)
     CU(cudaStreamSynchronize(c->comm_stream));
     std::vector<PeerBlob> all(nranks);
     CU(cudaMemcpy(all.data(), d_all, (size_t)nranks * sizeof(PeerBlob), cudaMemcpyDeviceToHost));
+    // flag words of every rank (halo flags of the neighbours, all-reduce slots of everybody), mapped once each
+    std::vector<unsigned long long *> flags_of(nranks, nullptr);
+    auto open_flags = [&](int peer) -> unsigned long long * {
+        if (peer == c->rank) return c->sync_flags;
+        if (flags_of[peer]) return flags_of[peer];
+        if (all[peer].pid == mine.pid) return nullptr;                           // IPC maps other processes only
+        void *f = nullptr;
+        if (cudaIpcOpenMemHandle(&f, all[peer].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        c->ipc_opened.push_back(f);
+        return flags_of[peer] = (unsigned long long *)f;
+    };
     auto open = [&](int peer, double *&pool, unsigned long long *&flags, int &ny) {
         if (peer < 0) return true;
-        if (peer == c->rank || all[peer].pid == mine.pid) return false;          // IPC maps other processes only
-        void *p = nullptr, *f = nullptr;
+        if (peer == c->rank || all[peer].pid == mine.pid) return false;
+        flags = open_flags(peer);
+        if (!flags) return false;
+        void *p = nullptr;
         if (cudaIpcOpenMemHandle(&p, all[peer].pool, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return false; }
-        if (cudaIpcOpenMemHandle(&f, all[peer].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-            cudaGetLastError();
-            cudaIpcCloseMemHandle(p);
-            return false;
-        }
-        pool = (double *)p; flags = (unsigned long long *)f; ny = all[peer].ny_local;
+        c->ipc_opened.push_back(p);
+        pool = (double *)p; ny = all[peer].ny_local;
         return true;
     };
     if (ok) {
@@ -466,20 +485,27 @@ static int setup_peer_halo(weno5_ctx *c)
             }
         }
     }
-    // unanimous or not at all
+    // all-reduce over peer memory: needs every rank's slot array
+    int share = ok && nranks <= SHARE_MAX_RANKS && !(getenv("WENO5_ALLREDUCE") && !strcmp(getenv("WENO5_ALLREDUCE"), "nccl")) ? 1 : 0;
+    for (int r = 0; share && r < nranks; ++r) {
+        unsigned long long *f = open_flags(r);
+        if (!f) share = 0; else c->share_slots[r] = f + 8;
+    }
+    // unanimous or not at all (bit 0: halo push, bit 1: all-reduce)
     unsigned long long *d_ok = reinterpret_cast<unsigned long long *>(d_all);
-    const unsigned long long h_ok = (unsigned long long)ok;
+    const unsigned long long h_ok = (unsigned long long)(ok && share ? 3 : (ok ? 1 : 0));
     CU(cudaMemcpy(d_ok, &h_ok, sizeof(h_ok), cudaMemcpyHostToDevice));
     NC(g_nccl.AllReduce(d_ok, d_ok, 1, ncclUint64, ncclMin, c->comm, c->comm_stream));
     CU(cudaStreamSynchronize(c->comm_stream));
     unsigned long long agreed = 0;
     CU(cudaMemcpy(&agreed, d_ok, sizeof(agreed), cudaMemcpyDeviceToHost));
     CU(cudaFree(d_all));
-    c->peer_ok = agreed != 0;
+    c->peer_ok = (agreed & 1ull) != 0;
+    c->share_ok = agreed == 3ull;
     return 0;
 }
 
-extern "C" int weno5_comm_halo_mode(const weno5_ctx *c) { return c && c->comm ? (c->peer_ok ? 2 : 1) : 0; }
+extern "C" int weno5_comm_halo_mode(const weno5_ctx *c) { return c && c->comm ? (c->peer_ok ? (c->share_ok ? 3 : 2) : 1) : 0; }
 
 extern "C" int weno5_comm_init(weno5_ctx *c, int rank, int nranks, const unsigned char id[128])
 {
@@ -505,6 +531,16 @@ extern "C" int weno5_comm_init(weno5_ctx *c, int rank, int nranks, const unsigne
 }
 
 // make the main stream wait for an exchange that is still in flight on the NCCL stream
+// the main stream waits for work queued on the NCCL stream (all-reduce of the wave speeds, NCCL halo exchange)
+static int wait_comm_event(weno5_ctx *c)
+{
+    if (c->xchg_pending) {
+        CU(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
+        c->xchg_pending = false;
+    }
+    return 0;
+}
+
 static int wait_exchange(weno5_ctx *c)
 {
     if (c->peer_wait_seq) {
@@ -529,7 +565,10 @@ static int exchange_rows(weno5_ctx *c, double *const planes[], int n, bool async
     // on B200 the NCCL kernel running beside flux_x cost more (0.5 ms/step) than the 0.23 ms/step the
     // serialized packed exchange takes.  WENO5_OVERLAP_XCHG=1 turns it on.
     static const bool overlap = getenv("WENO5_OVERLAP_XCHG") != nullptr;
-    if (!overlap) async = false;
+    // peer push + a flux kernel whose ghost-row strips wait for the flag words themselves: the wait is left to the
+    // next stage's x sweep (enqueue_stage), hidden behind its interior rows
+    const bool inkernel = c->peer_ok && c->have_tmap && !c->dual && flux_waits_in_kernel();
+    if (!overlap && !inkernel) async = false;
     const Geom &g = c->g;
     if (c->peer_ok) {
         // push the edge rows into the neighbours' ghost rows and raise their flag words; then (or later, async)
@@ -637,6 +676,7 @@ extern "C" int weno5_download(weno5_ctx *c, double *q, double *bxb, double *byb)
     if (c->g.is1d) return fail(WENO5_ERR_ARG, "use weno5_download_1d for 1-D grids");
     if (!c->uploaded) return fail(WENO5_ERR_STATE, "no state on the device yet");
     DevGuard dg_; CU(dg_.set(c->device));
+    if (int r = wait_exchange(c)) return r;
     const size_t hp = (size_t)c->g.Nx * c->g.Ny;
     if (q) for (int k = 0; k < NCELL; ++k) if (int r = copy_plane(c, c->Q0.q[k], nullptr, q + host_comp(k) * hp)) return r;
     if (bxb) if (int r = copy_plane(c, c->Q0.bx, nullptr, bxb)) return r;
@@ -688,17 +728,22 @@ static int enqueue_timestep(weno5_ctx *c, bool fused = false)
         launch_vmax(c->Q0.q, c->g, c->P.gamma, vb, c->stream);
         c->launches += 1;
     }
-    if (c->comm && c->nranks > 1) {
+    ShareArgs share;
+    const bool peer_reduce = c->comm && c->nranks > 1 && c->share_ok;
+    if (peer_reduce) {
+        share.n = c->nranks; share.rank = c->rank; share.seq = ++c->share_seq;
+        for (int r = 0; r < SHARE_MAX_RANKS; ++r) share.slots[r] = c->share_slots[r];
+    } else if (c->comm && c->nranks > 1) {
         // all NCCL work of a handle is ordered on the NCCL stream (after a still-running exchange)
         CU(cudaEventRecord(c->ev_main, c->stream));
         CU(cudaStreamWaitEvent(c->comm_stream, c->ev_main, 0));
         NC(g_nccl.AllReduce(vb, vb, 2, ncclUint64, ncclMax, c->comm, c->comm_stream));
         CU(cudaEventRecord(c->ev_comm, c->comm_stream));
         c->xchg_pending = true;
-        if (int r = wait_exchange(c)) return r;
+        if (int r = wait_comm_event(c)) return r;       // (a halo push still in flight stays pending: dt needs no ghost rows)
         c->launches += 1;
     }
-    launch_dt_from_vmax(vb, c->ctl, c->P.dx, c->P.dy, c->P.cfl, c->g.is1d, fused ? 1 : 0, c->stream);
+    launch_dt_from_vmax(vb, c->ctl, c->P.dx, c->P.dy, c->P.cfl, c->g.is1d, fused ? 1 : 0, peer_reduce ? &share : nullptr, c->stream);
     c->launches += 1;
     return 0;
 }
@@ -770,7 +815,16 @@ static int enqueue_stage(weno5_ctx *c, int stage, State &cur, State &nxt)
     // x sweep
     a.N = g.NXI; a.NP = g.NYI; a.bs = c->fsy;
     a.seg_len = c->segx_len; a.nseg = c->nsegx;
-    if ((c->xchg_pending || c->peer_wait_seq) && !g.is1d) {
+    if (c->peer_wait_seq && !c->xchg_pending && !g.is1d && c->have_tmap && flux_waits_in_kernel()) {
+        // ghost rows of `cur` are still arriving over peer memory: the sweep's ghost-row strips run last and wait for
+        // the neighbours' flag words inside the kernel
+        a.wait_flags = c->sync_flags; a.wait_seq = c->peer_wait_seq;
+        a.wait_lo = c->down >= 0; a.wait_hi = c->up >= 0; a.wait_err = c->ctl;
+        c->peer_wait_seq = 0;
+        { ProfScope ps(c); launch_flux_x(a, c->stream); }
+        a.wait_flags = nullptr;
+        c->launches++; c->prof_launches += c->profiling;
+    } else if ((c->xchg_pending || c->peer_wait_seq) && !g.is1d) {
         // ghost rows of `cur` are still arriving: sweep the interior rows now, the ghost rows after
         a.row_mode = 1;
         { ProfScope ps(c); launch_flux_x(a, c->stream); }

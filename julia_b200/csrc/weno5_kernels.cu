@@ -148,12 +148,13 @@ struct FluxMaps { CUtensorMap m8, m6, m4, m2; };
 // TMA path, executed by one thread: stage the raw state of the chunk whose first new cell is c0.
 // The 8 state planes are consecutive in the pool, so ONE box carries all of them.
 template <int DIR, int NT, int YW>
-__device__ __forceinline__ void tma_issue_state(const FluxArgs &a, const FluxMaps *tm, double *stq, unsigned long long *bar, int c0)
+__device__ __forceinline__ void tma_issue_state(const FluxArgs &a, const FluxMaps *tm, double *stq, unsigned long long *bar, int c0,
+                                                int strip = (int)blockIdx.x)
 {
     using T = Tile<DIR, NT, YW>;
     mbar_expect_tx(bar, 8 * T::FST * (unsigned)sizeof(double));
-    const int bx = DIR == 0 ? c0 - (c0 & 1) : (int)blockIdx.x * T::NPB;
-    const int by = DIR == 0 ? (int)blockIdx.x * T::NPB : c0;
+    const int bx = DIR == 0 ? c0 - (c0 & 1) : strip * T::NPB;
+    const int by = DIR == 0 ? strip * T::NPB : c0;
     tma_load_box(stq, &tm->m8, bx, by, a.qc_plane[0], bar);
 }
 
@@ -454,8 +455,17 @@ __global__ void __launch_bounds__(256, 2) flux_ws_kernel(const FluxArgs a, const
     const int t = threadIdx.x & (NT - 1);
     const int s = DIR == 0 ? (t % NS) : (t / NPB);
     const int p = DIR == 0 ? (t / NS) : (t % NPB);
-    const int line = blockIdx.x * NPB + p;
-    const int seg = blockIdx.y;
+    // x sweep of a y-slab whose ghost rows are still arriving (halo push of the previous stage): the strips that
+    // hold ghost rows are mapped to the LAST blocks of the grid and wait for the neighbours' flag words themselves,
+    // so the interior of the sweep hides the exchange (no separate wait kernel, no split launch)
+    int strip = blockIdx.x, seg = blockIdx.y;
+    if (DIR == 0 && a.wait_flags != nullptr) {
+        const int L = blockIdx.x + gridDim.x * blockIdx.y;
+        strip = L / gridDim.y + 2;
+        seg = L % gridDim.y;
+        if (strip >= (int)gridDim.x) strip -= gridDim.x;
+    }
+    const int line = strip * NPB + p;
     const int fA = 2 + seg * a.seg_len;
     const int fB = min(fA + a.seg_len, a.N - 3);
     const int fStart = seg == 0 ? fA : fA - 1;
@@ -464,7 +474,7 @@ __global__ void __launch_bounds__(256, 2) flux_ws_kernel(const FluxArgs a, const
     const bool line_ok = line >= G && line < a.NP - G;
     bool row_sel = true;
     if (DIR == 0 && a.row_mode != 0) {
-        const int l0 = blockIdx.x * NPB, l1 = min(l0 + NPB, a.NP) - 1;
+        const int l0 = strip * NPB, l1 = min(l0 + NPB, a.NP) - 1;
         const bool any_interior = l1 >= G && l0 < a.NP - G;
         const bool any_ghost = l0 < G || l1 >= a.NP - G;
         if (a.row_mode == 1 ? !any_interior : !any_ghost) return;
@@ -472,6 +482,19 @@ __global__ void __launch_bounds__(256, 2) flux_ws_kernel(const FluxArgs a, const
     }
 
     if (threadIdx.x == 0) {
+        if (DIR == 0 && a.wait_flags != nullptr) {
+            const int l0 = strip * NPB, l1 = l0 + NPB - 1;
+            const bool need[2] = {a.wait_lo && l0 < G, a.wait_hi && l1 >= a.NP - G};
+            const long long t0 = clock64();
+            for (int side = 0; side < 2; ++side) {
+                if (!need[side]) continue;
+                unsigned long long v;
+                do {
+                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.wait_flags + side) : "memory");
+                    if (v < a.wait_seq && clock64() - t0 > 8000000000ll) { a.wait_err[6] = 2.0; break; }   // neighbour died
+                } while (v < a.wait_seq);
+            }
+        }
         mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
         mbar_init(&bars[2], NT); mbar_init(&bars[3], NT); mbar_init(&bars[4], NT); mbar_init(&bars[5], NT);
         mbar_fence_init();
@@ -539,14 +562,14 @@ __global__ void __launch_bounds__(256, 2) flux_ws_kernel(const FluxArgs a, const
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(HREG));
         unsigned phq = 0, phu = 0;
         if (t == 0) {
-            tma_issue_state<DIR, NT, T::YW>(a, &tmap, stq, &bars[0], fStart + 3);
+            tma_issue_state<DIR, NT, T::YW>(a, &tmap, stq, &bars[0], fStart + 3, strip);
             if constexpr (DIR == 1) tma_issue_operands<NT, T::YW>(a, &tmap, stu, &bars[1], fStart);
         }
         // the 5 leading stencil cells of the segment, straight from global memory -> ring slots 0..4
         for (int e = t; e < 5 * NPB; e += NT) {
             const int sl = DIR == 0 ? e % 5 : e / NPB;
             const int pp = DIR == 0 ? e / 5 : e % NPB;
-            const size_t g = cell_index<DIR>(a, fStart - 2 + sl, blockIdx.x * NPB + pp);
+            const size_t g = cell_index<DIR>(a, fStart - 2 + sl, strip * NPB + pp);
             double q[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) q[k] = __ldg(a.qc[perm<DIR>(k)] + g);
@@ -617,7 +640,7 @@ __global__ void __launch_bounds__(256, 2) flux_ws_kernel(const FluxArgs a, const
                 rc += NS;
                 if (rc >= RS) rc -= RS;
                 helper_sync();                   // stq consumed
-                if (t == 0 && n + 2 < nsteps) tma_issue_state<DIR, NT, T::YW>(a, &tmap, stq, &bars[0], c0 + NS);
+                if (t == 0 && n + 2 < nsteps) tma_issue_state<DIR, NT, T::YW>(a, &tmap, stq, &bars[0], c0 + NS, strip);
             }
             if (n + 1 < nsteps) mbar_arrive(&bars[2 + ((n + 1) & 1)]);
         }
@@ -1013,6 +1036,7 @@ int flux_chunk(int dir) { return dir == 0 ? 64 : 8; }
 int flux_lines_per_cta(int dir) { return dir == 0 ? 2 : 16; }
 int flux_uses_tma() { return flux_variant() != 2; }
 int flux_resident_ctas() { return (flux_variant() == 6 ? 3 : 2) * 148; }
+int flux_waits_in_kernel() { return flux_variant() == 5 && !getenv("WENO5_NO_INKERNEL_WAIT"); }
 void flux_box(int dir, int box[2])
 {
     if (dir == 0) { box[0] = 64 + 2; box[1] = 2; } else { box[0] = 16; box[1] = 8; }
@@ -1665,11 +1689,45 @@ void launch_vmax_rows(const double *const q9[9], const Geom &g, double gam, unsi
 
 // timestep(), Weno5_2D.jl:1930-1940; 1-D: dt = courFac*dx/vmax (Weno5_1D.jl:55).
 // With tmax > 0 the step is shortened to land on tmax and becomes 0 once t >= tmax.
-__global__ void dt_kernel(unsigned long long *vb, double *ctl, double dx, double dy, double cfl, int is1d, int clear)
+// With a communicator whose ranks map each other's flag words (peer memory, weno5_comm_init) the max-all-reduce
+// of the two wave speeds happens right here: lane r stores this rank's two bit patterns and the sequence number into
+// rank r's slot array (over NVLink for r != own rank), then waits for rank r's entry in the local array, and a warp
+// maximum finishes the reduction -- no NCCL kernel, no hop to a second stream and back.  Slots are double-buffered by
+// sequence parity: a rank can be at most one reduction ahead of the slowest (it needs everybody's entry to finish).
+__global__ void dt_kernel(unsigned long long *vb, double *ctl, double dx, double dy, double cfl, int is1d, int clear, const ShareArgs sh)
 {
-    const double vx = __longlong_as_double((long long)vb[0]);
-    const double vy = __longlong_as_double((long long)vb[1]);
+    const int lane = threadIdx.x;
+    unsigned long long b0 = vb[0], b1 = vb[1];
+    if (sh.n > 1) {
+        const int par = (int)(sh.seq & 1ull);
+        unsigned long long m0 = 0ull, m1 = 0ull;
+        if (lane < sh.n) {
+            unsigned long long *dst = sh.slots[lane] + (size_t)(par * 32 + sh.rank) * 4;
+            dst[0] = b0; dst[1] = b1;
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst + 2), "l"(sh.seq) : "memory");
+            const unsigned long long *src = sh.slots[sh.rank] + (size_t)(par * 32 + lane) * 4;
+            const long long t0 = clock64();
+            unsigned long long v;
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src + 2) : "memory");
+                if (v < sh.seq && clock64() - t0 > 8000000000ll) { ctl[6] = 2.0; break; }      // a rank never arrived
+            } while (v < sh.seq);
+            m0 = *(volatile const unsigned long long *)(src + 0);
+            m1 = *(volatile const unsigned long long *)(src + 1);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            m0 = max(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+            m1 = max(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+        }
+        b0 = m0; b1 = m1;
+    }
+    __syncwarp();
+    if (lane != 0) return;
+    const double vx = __longlong_as_double((long long)b0);
+    const double vy = __longlong_as_double((long long)b1);
     if (clear) { vb[0] = 0ull; vb[1] = 0ull; }             // accumulator of the fused stage-4 reduction: ready for the next step
+    else if (sh.n > 1) { vb[0] = b0; vb[1] = b1; }
     const double t = ctl[1], tmax = ctl[4];
     if (tmax > 0.0 && t >= tmax) { ctl[0] = 0.0; return; } // finished: the kernels of further steps return at once
     ctl[2] = vx; ctl[3] = vy;
@@ -1686,9 +1744,11 @@ __global__ void dt_kernel(unsigned long long *vb, double *ctl, double dx, double
 }
 
 void launch_dt_from_vmax(unsigned long long *vmax_bits, double *ctl, double dx, double dy, double cfl,
-                         int is1d, int clear, cudaStream_t s)
+                         int is1d, int clear, const ShareArgs *share, cudaStream_t s)
 {
-    dt_kernel<<<1, 1, 0, s>>>(vmax_bits, ctl, dx, dy, cfl, is1d, clear);
+    ShareArgs none;
+    none.n = 0; none.rank = 0; none.seq = 0;
+    dt_kernel<<<1, 32, 0, s>>>(vmax_bits, ctl, dx, dy, cfl, is1d, clear, share ? *share : none);
 }
 
 __global__ void advance_time_kernel(double *ctl)

@@ -45,6 +45,12 @@ struct FluxArgs {
     int is1d;
     int row_mode;            // x sweep: 0 all rows, 1 interior rows only, 2 ghost rows only (halo-exchange overlap)
     int branch;              // 0: E branch (qc[7] = E), 1: S branch (qc[7] = S; weno5_flux_difference_S, Weno5_2D.jl:361)
+    // x sweep on a y-slab whose ghost rows are still in flight: the strips with ghost rows wait for flags[0] (rows
+    // from the lower neighbour) / flags[1] (upper) >= wait_seq inside the kernel; nullptr: nothing to wait for
+    const unsigned long long *wait_flags;
+    unsigned long long wait_seq;
+    int wait_lo, wait_hi;
+    double *wait_err;        // control block: [6] = 2 if a neighbour never arrived
     // TMA staging: plane indices into the pool (z coordinate of the 3-D tensor maps) and the maps
     // themselves (host pointers; copied into the kernel's parameter space at launch)
     int qc_plane[8], rhs_plane[7], base_plane[6], acc_plane[6];
@@ -124,9 +130,14 @@ void launch_vmax(const double *const q9[9], const Geom &g, double gam, unsigned 
 void launch_vmax_rows(const double *const q9[9], const Geom &g, double gam, unsigned long long *vmax_bits, int j0, int j1,
                       int zero_first, cudaStream_t s);
 // ctl[0]=dt ctl[1]=t ctl[2]=vxmax ctl[3]=vymax ctl[4]=tmax ctl[5]=steps_done ctl[6]=bad-flag
+// max-all-reduce of the two wave speeds over peer memory inside dt_kernel: slots[r] = rank r's slot array
+// ([2 parities][32 ranks][4 words]: vx bits, vy bits, sequence number), own rank included
+struct ShareArgs { int n, rank; unsigned long long seq; unsigned long long *slots[8]; };
+constexpr int SHARE_MAX_RANKS = 8;
+constexpr int SHARE_SLOT_WORDS = 2 * 32 * 4;
 // clear = 1: zero the two maxima after reading them (accumulator of the fused stage-4 reduction)
 void launch_dt_from_vmax(unsigned long long *vmax_bits, double *ctl, double dx, double dy,
-                         double cfl, int is1d, int clear, cudaStream_t s);
+                         double cfl, int is1d, int clear, const ShareArgs *share, cudaStream_t s);
 void launch_advance_time(double *ctl, cudaStream_t s);
 void launch_center2face(const double *Bx, const double *By, double *bxb, double *byb, const Geom &g,
                         cudaStream_t s);
@@ -144,6 +155,7 @@ cudaError_t launch_line1d(double *const q9[NCELL], double *ctl, const Geom &g, c
 int flux_chunk(int dir);          // faces per march step of the active launch variant
 int flux_lines_per_cta(int dir);  // lines across the sweep per CTA
 int flux_uses_tma();              // 1 if the active variant stages through TMA tensor maps
+int flux_waits_in_kernel();       // 1 if the x sweep of the active variant can wait for the halo flags itself
 int flux_resident_ctas();         // CTAs of the flux kernel resident on the GPU at a time (wave planning)
 void flux_box(int dir, int box[2]);   // TMA box (cells along x, rows along y) of one march step
 

@@ -75,7 +75,7 @@ function comm_unique_id()
 end
 comm_init!(s::Solver, rank::Integer, nranks::Integer, id::Vector{UInt8}) =
     check(ccall((:weno5_comm_init, libweno5), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), s.h, rank, nranks, id))
-"0: no communicator, 1: ghost rows through NCCL send/recv, 2: stored straight into the neighbours' ghost rows over peer memory."
+"0: no communicator, 1: NCCL send/recv + all-reduce, 2: ghost rows stored straight into the neighbours' planes over peer memory, 3: also the dt all-reduce over peer memory."
 comm_halo_mode(s::Solver) = Int(ccall((:weno5_comm_halo_mode, libweno5), Cint, (Ptr{Cvoid},), s.h))
 
 # ---- state transfer

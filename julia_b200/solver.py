@@ -77,7 +77,8 @@ class Solver:
         L.check(self.lib.weno5_comm_init(self.h, rank, nranks, buf))
 
     def halo_mode(self):
-        """0: no communicator, 1: NCCL send/recv, 2: direct stores into the neighbours' ghost rows (peer memory)."""
+        """0: no communicator, 1: NCCL send/recv + NCCL all-reduce, 2: direct stores into the neighbours' ghost rows
+        (peer memory), 3: that and the dt all-reduce over peer memory."""
         return int(self.lib.weno5_comm_halo_mode(self.h))
 
     # -- state

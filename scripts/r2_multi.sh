@@ -10,6 +10,7 @@ run() { # tag, env...
      bench.py --gpus $N --steps 20 --warmup 3 --e2e-steps 0 --no-cpu --strong-steps 0 --no-slab-check > gpurun_out/r2_bench_n${N}_$tag.log 2>&1
   echo "$tag: $(grep -o '"ms_per_step": [0-9.]*' gpurun_out/r2_bench_n${N}_$tag.log | head -1) $(grep -o '"halo_exchange": "[^"]*"' gpurun_out/r2_bench_n${N}_$tag.log)"
 }
-run peer X=1
-run peer_overlap WENO5_OVERLAP_XCHG=1
+run peer_all X=1
+run peer_nccl_allreduce WENO5_ALLREDUCE=nccl
+run peer_wait_kernel WENO5_NO_INKERNEL_WAIT=1
 run nccl WENO5_HALO=nccl
