@@ -77,8 +77,9 @@ int weno5_comm_init(weno5_ctx *ctx, int rank, int nranks, const unsigned char id
  * map the others) additionally the all-reduce as a peer-memory exchange inside the dt kernel.  WENO5_HALO=nccl in the
  * environment forces 1, WENO5_ALLREDUCE=nccl forces 2. */
 int weno5_comm_halo_mode(const weno5_ctx *ctx);
-/* weno5_destroy of a handle that passed weno5_comm_init is COLLECTIVE over its ranks in mode 2 (every rank unmaps its
- * neighbours' memory before anyone frees its own). */
+/* weno5_destroy of a handle whose memory other ranks map (modes 2, 3) first unmaps what it mapped itself and then
+ * waits -- at most 2 s -- until the other ranks have unmapped it: destroy the handles of all ranks around the same
+ * time, like the communicator they share. */
 
 /* ---- state transfer.  Host arrays cover the LOCAL slab: (Nx, ny_local+6, 9) etc. */
 /* q/bxb/byb as produced by initial_conditions() (Weno5_2D.jl:2001) and

@@ -162,6 +162,7 @@ struct weno5_ctx {
     unsigned long long *sync_flags = nullptr;    // [0] last push from below, [1] from above, [2] block counter, [8..] all-reduce slots
     unsigned long long *share_slots[SHARE_MAX_RANKS] = {};   // every rank's all-reduce slot array (own included), or null
     std::vector<void *> ipc_opened;              // everything cudaIpcOpenMemHandle returned (closed in weno5_destroy)
+    std::vector<unsigned long long *> peer_flag_maps;   // the flag words among them: [3] counts who maps that rank
     bool share_ok = false;                       // the dt all-reduce runs over peer memory inside dt_kernel
     unsigned long long share_seq = 0;
     unsigned long long xseq = 0, peer_wait_seq = 0;
@@ -392,15 +393,24 @@ extern "C" int weno5_destroy(weno5_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
     if (c->step_graph) cudaGraphExecDestroy(c->step_graph);
+    // CUDA leaves freeing exported memory that another process still maps undefined.  Every importer is counted in
+    // word [3] of the exporter's flag words: un-count and unmap what this rank mapped, then wait (at most 2 s: a
+    // peer that died must not hang the survivors) until nobody maps this rank's memory any more.
+    if (c->stream) {
+        for (unsigned long long *f : c->peer_flag_maps) launch_peer_count(f + 3, -1, c->stream);
+        cudaStreamSynchronize(c->stream);
+    }
     for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     c->ipc_opened.clear();
+    c->peer_flag_maps.clear();
     cudaGetLastError();
-    if (c->comm && c->peer_ok && c->nranks > 1 && c->comm_stream && g_nccl.AllReduce) {
-        // the neighbours map this rank's pool and flag words: nobody frees before everybody has unmapped (CUDA leaves
-        // freeing exported memory that is still mapped elsewhere undefined) -- a barrier over the communicator, which
-        // makes weno5_destroy collective for handles that passed weno5_comm_init
-        if (g_nccl.AllReduce(c->vmax_bits, c->vmax_bits, 1, ncclUint64, ncclMax, c->comm, c->comm_stream) == ncclSuccess)
-            cudaStreamSynchronize(c->comm_stream);
+    if (c->sync_flags && c->stream) {
+        for (int it = 0; it < 2000; ++it) {
+            unsigned long long n = 0;
+            if (cudaMemcpyAsync(&n, c->sync_flags + 3, sizeof(n), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) break;
+            if (cudaStreamSynchronize(c->stream) != cudaSuccess || n == 0) break;
+            usleep(1000);
+        }
         cudaGetLastError();
     }
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
@@ -462,6 +472,8 @@ static int setup_peer_halo(weno5_ctx *c)
         void *f = nullptr;
         if (cudaIpcOpenMemHandle(&f, all[peer].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return nullptr; }
         c->ipc_opened.push_back(f);
+        c->peer_flag_maps.push_back((unsigned long long *)f);
+        launch_peer_count((unsigned long long *)f + 3, 1, c->comm_stream);      // counted as an importer of that rank
         return flags_of[peer] = (unsigned long long *)f;
     };
     auto open = [&](int peer, double *&pool, unsigned long long *&flags, int &ny) {

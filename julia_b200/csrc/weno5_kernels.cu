@@ -1386,6 +1386,15 @@ __global__ void halo_wait_kernel(const unsigned long long *flags, int need_down,
     }
 }
 
+// importer bookkeeping: word [3] of a rank's flag words counts the processes that currently map its memory
+__global__ void peer_count_kernel(unsigned long long *counter, long long delta)
+{
+    atomicAdd_system(counter, (unsigned long long)delta);
+    __threadfence_system();
+}
+
+void launch_peer_count(unsigned long long *counter, long long delta, cudaStream_t s) { peer_count_kernel<<<1, 1, 0, s>>>(counter, delta); }
+
 void launch_halo_wait(const unsigned long long *flags, int need_down, int need_up, unsigned long long seq, double *ctl,
                       cudaStream_t s)
 {

@@ -111,6 +111,7 @@ struct PushArgs {
     unsigned long long seq;
 };
 void launch_halo_push(const PushArgs &a, cudaStream_t s);
+void launch_peer_count(unsigned long long *counter, long long delta, cudaStream_t s);
 void launch_halo_wait(const unsigned long long *flags, int need_down, int need_up, unsigned long long seq, double *ctl,
                       cudaStream_t s);
 void launch_es_switch(const SwitchArgs &a, cudaStream_t s);
