@@ -243,7 +243,10 @@ static void choose_segments(int nfaces, int NS, int strips, int &seg_len, int &n
     int per = (chunks + best - 1) / best;
     if (per < minper) per = minper;
     if (per > chunks) per = chunks;
-    seg_len = per * NS;
+    // every segment but the first starts one face early (its first cell needs both faces): with segments of
+    // per * NS - 1 owned faces that extra face fits into `per` march steps instead of costing a step of its own
+    // (measured on an 8192 x 1024 slab: 35 -> 34 steps per segment incl. prologue)
+    seg_len = per < chunks ? per * NS - 1 : per * NS;
     nseg = (nfaces + seg_len - 1) / seg_len;
 }
 
