@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(256, 2) flux_ws_kernel(const FluxArgs a, const
                 unsigned long long v;
                 do {
                     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.wait_flags + side) : "memory");
-                    if (v < a.wait_seq && clock64() - t0 > 8000000000ll) { a.wait_err[6] = 2.0; break; }   // neighbour died
+                    if (v < a.wait_seq && clock64() - t0 > 20000000000ll) { a.wait_err[6] = 2.0; break; }   // neighbour died
                 } while (v < a.wait_seq);
             }
         }
@@ -1372,7 +1372,7 @@ void launch_halo_push(const PushArgs &a, cudaStream_t s)
 }
 
 // flags[0]: sequence number of the last push from the lower neighbour, flags[1]: from the upper one.
-// Gives up after ~4 s (a neighbour died): raises the bad-state flag of the control block instead of hanging the GPU.
+// Gives up after ~10 s (a neighbour died): raises the bad-state flag of the control block instead of hanging the GPU.
 __global__ void halo_wait_kernel(const unsigned long long *flags, int need_down, int need_up, unsigned long long seq, double *ctl)
 {
     const long long t0 = clock64();
@@ -1381,7 +1381,7 @@ __global__ void halo_wait_kernel(const unsigned long long *flags, int need_down,
         unsigned long long v;
         do {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + side) : "memory");
-            if (v < seq && clock64() - t0 > 8000000000ll) { ctl[6] = 2.0; return; }
+            if (v < seq && clock64() - t0 > 20000000000ll) { ctl[6] = 2.0; return; }
         } while (v < seq);
     }
 }
@@ -1719,7 +1719,7 @@ __global__ void dt_kernel(unsigned long long *vb, double *ctl, double dx, double
             unsigned long long v;
             do {
                 asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(src + 2) : "memory");
-                if (v < sh.seq && clock64() - t0 > 8000000000ll) { ctl[6] = 2.0; break; }      // a rank never arrived
+                if (v < sh.seq && clock64() - t0 > 20000000000ll) { ctl[6] = 2.0; break; }      // a rank never arrived
             } while (v < sh.seq);
             m0 = *(volatile const unsigned long long *)(src + 0);
             m1 = *(volatile const unsigned long long *)(src + 1);
