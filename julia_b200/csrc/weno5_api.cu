@@ -570,20 +570,16 @@ static int wait_exchange(weno5_ctx *c)
     return 0;
 }
 
-// send the 4 outermost interior rows, receive the 4 ghost rows, for each plane.  Runs on the NCCL
-// stream after everything queued so far on the main stream; with `async` the main stream does not
-// wait (the caller overlaps independent work and calls wait_exchange before touching ghost rows).
+// send the 4 outermost interior rows, receive the 4 ghost rows, for each plane: a push over peer memory on the main
+// stream, or (fallback) packed NCCL messages on the NCCL stream.  With `async` (peer path only) nothing waits here:
+// the next x sweep does, inside the kernel; whoever else touches ghost rows calls wait_exchange first.
 static int exchange_rows(weno5_ctx *c, double *const planes[], int n, bool async = false)
 {
     if (!c->comm || (c->up < 0 && c->down < 0)) return 0;
-    // The overlap of the exchange with the interior x sweep is implemented (async) but OFF by default:
-    // on B200 the NCCL kernel running beside flux_x cost more (0.5 ms/step) than the 0.23 ms/step the
-    // serialized packed exchange takes.  WENO5_OVERLAP_XCHG=1 turns it on.
-    static const bool overlap = getenv("WENO5_OVERLAP_XCHG") != nullptr;
     // peer push + a flux kernel whose ghost-row strips wait for the flag words themselves: the wait is left to the
-    // next stage's x sweep (enqueue_stage), hidden behind its interior rows
+    // next stage's x sweep (enqueue_stage), hidden behind its interior rows; every other combination waits here
     const bool inkernel = c->peer_ok && c->have_tmap && !c->dual && flux_waits_in_kernel();
-    if (!overlap && !inkernel) async = false;
+    if (!inkernel) async = false;
     const Geom &g = c->g;
     if (c->peer_ok) {
         // push the edge rows into the neighbours' ghost rows and raise their flag words; then (or later, async)
@@ -839,21 +835,8 @@ static int enqueue_stage(weno5_ctx *c, int stage, State &cur, State &nxt)
         { ProfScope ps(c); launch_flux_x(a, c->stream); }
         a.wait_flags = nullptr;
         c->launches++; c->prof_launches += c->profiling;
-    } else if ((c->xchg_pending || c->peer_wait_seq) && !g.is1d) {
-        // ghost rows of `cur` are still arriving: sweep the interior rows now, the ghost rows after
-        a.row_mode = 1;
-        { ProfScope ps(c); launch_flux_x(a, c->stream); }
-        if (int r = wait_exchange(c)) return r;
-        // only 8 rows are left: cut them into single-chunk segments so that they fill the machine
-        // instead of 4 CTAs marching the whole row length
-        a.row_mode = 2;
-        a.seg_len = flux_chunk(0);
-        a.nseg = (g.NXI - 5 + a.seg_len - 1) / a.seg_len;
-        launch_flux_x(a, c->stream);
-        a.row_mode = 0;
-        a.seg_len = c->segx_len; a.nseg = c->nsegx;
-        c->launches += 2; c->prof_launches += c->profiling;
     } else {
+        if (int r = wait_exchange(c)) return r;          // an exchange still in flight (NCCL path, other flux variants)
         { ProfScope ps(c); launch_flux_x(a, c->stream); }
         c->launches++; c->prof_launches += c->profiling;
     }

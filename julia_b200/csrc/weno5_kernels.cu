@@ -205,16 +205,6 @@ __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a, const 
     const int fStart = seg == 0 ? fA : fA - 1;
 
     const bool line_ok = a.is1d ? (line == 0) : (line >= G && line < a.NP - G);
-    // halo-exchange overlap (x sweep on y-slabs): interior rows are swept while the ghost rows are
-    // still in flight, the 2 x 4 ghost rows in a second launch
-    bool row_sel = true;
-    if (DIR == 0 && a.row_mode != 0) {
-        const int l0 = blockIdx.x * NPB, l1 = min(l0 + NPB, a.NP) - 1;
-        const bool any_interior = l1 >= G && l0 < a.NP - G;
-        const bool any_ghost = l0 < G || l1 >= a.NP - G;
-        if (a.row_mode == 1 ? !any_interior : !any_ghost) return;
-        row_sel = (line >= G && line < a.NP - G) == (a.row_mode == 1);
-    }
 
     unsigned phq = 0, phu = 0;                   // mbarrier phase parities
     if constexpr (TMA) {
@@ -266,7 +256,7 @@ __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a, const 
 
         // ---------------- asynchronous copies that fly under the face phase:
         // group A = this chunk's RK operands (y sweep), group B = the next chunk's state
-        const bool upd_ok = (s0 + s > fStart) && (s0 + s < fB) && (s0 + s >= G) && (s0 + s < a.N - G) && line_ok && row_sel;
+        const bool upd_ok = (s0 + s > fStart) && (s0 + s < fB) && (s0 + s >= G) && (s0 + s < a.N - G) && line_ok;
         if constexpr (TMA) {
             if (t == 0) {
                 if constexpr (DIR == 1) tma_issue_operands<NT, YW>(a, &tmap, stu, &bars[1], s0);
@@ -339,7 +329,7 @@ __global__ void __launch_bounds__(NT, MINB) flux_kernel(const FluxArgs a, const 
             for (int m = 0; m < 7; ++m) fb[m * FBS + io] = fh[m];
             // CT seed flux, Weno5_2D.jl:1005-1008: x sweep -> fsy (tangential comp 2),
             // y sweep -> gsx (tangential comp 3 of the rotated frame)
-            if (!a.is1d && line < a.NP && row_sel && (seg == 0 || f >= fA)) {
+            if (!a.is1d && line < a.NP && (seg == 0 || f >= fA)) {
                 constexpr int TV = DIR == 0 ? CQ_V2 : CQ_V3;
                 const double bv = cb[CQ_B1 * CBS + iL] * cb[TV * CBS + iL] + cb[CQ_B1 * CBS + iR] * cb[TV * CBS + iR];
                 const size_t g = DIR == 0 ? (size_t)f + (size_t)a.pitch * line : (size_t)line + (size_t)a.pitch * f;
@@ -472,14 +462,6 @@ __global__ void __launch_bounds__(256, 2) flux_ws_kernel(const FluxArgs a, const
     const int nsteps = (fB - fStart + NS - 1) / NS;
 
     const bool line_ok = line >= G && line < a.NP - G;
-    bool row_sel = true;
-    if (DIR == 0 && a.row_mode != 0) {
-        const int l0 = strip * NPB, l1 = min(l0 + NPB, a.NP) - 1;
-        const bool any_interior = l1 >= G && l0 < a.NP - G;
-        const bool any_ghost = l0 < G || l1 >= a.NP - G;
-        if (a.row_mode == 1 ? !any_interior : !any_ghost) return;
-        row_sel = (line >= G && line < a.NP - G) == (a.row_mode == 1);
-    }
 
     if (threadIdx.x == 0) {
         if (DIR == 0 && a.wait_flags != nullptr) {
@@ -546,7 +528,7 @@ __global__ void __launch_bounds__(256, 2) flux_ws_kernel(const FluxArgs a, const
 #pragma unroll
                 for (int m = 0; m < 7; ++m) fb[m * FBS + io] = fh[m];
                 // CT seed flux, Weno5_2D.jl:1005-1008
-                if (line < a.NP && row_sel && (seg == 0 || f >= fA)) {
+                if (line < a.NP && (seg == 0 || f >= fA)) {
                     constexpr int TV = DIR == 0 ? CQ_V2 : CQ_V3;
                     const double bv = cb[CQ_B1 * CBS + iL] * cb[TV * CBS + iL] + cb[CQ_B1 * CBS + iR] * cb[TV * CBS + iR];
                     const size_t g = DIR == 0 ? (size_t)f + (size_t)a.pitch * line : (size_t)line + (size_t)a.pitch * f;
@@ -585,7 +567,7 @@ __global__ void __launch_bounds__(256, 2) flux_ws_kernel(const FluxArgs a, const
                 if constexpr (DIR == 1) { mbar_wait(&bars[1], phu); phu ^= 1u; }
                 const int s0 = fStart + m1 * NS;
                 const int c = s0 + s;
-                const bool upd_ok = (c > fStart) && (c < fB) && (c >= G) && (c < a.N - G) && line_ok && row_sel;
+                const bool upd_ok = (c > fStart) && (c < fB) && (c >= G) && (c < a.N - G) && line_ok;
                 const double *fbu = fb + bu * 7 * FBS;
                 if (upd_ok) {
                     const int i0 = T::fbi(s, p), i1 = T::fbi(s + 1, p);
@@ -785,14 +767,6 @@ __global__ void __launch_bounds__(128, 3) flux_tm_kernel(const FluxArgs a, const
     const int fB = min(fA + a.seg_len, a.N - 3);
     const int fStart = seg == 0 ? fA : fA - 1;
     const bool line_ok = line >= G && line < a.NP - G;
-    bool row_sel = true;
-    if (DIR == 0 && a.row_mode != 0) {
-        const int l0 = blockIdx.x * NPB, l1 = min(l0 + NPB, a.NP) - 1;
-        const bool any_interior = l1 >= G && l0 < a.NP - G;
-        const bool any_ghost = l0 < G || l1 >= a.NP - G;
-        if (a.row_mode == 1 ? !any_interior : !any_ghost) return;
-        row_sel = (line >= G && line < a.NP - G) == (a.row_mode == 1);
-    }
 
     // tensor memory: warp 0 allocates the CTA's columns; every warp addresses the 32 lanes of its own quadrant
     if (t < 32) {
@@ -837,7 +811,7 @@ __global__ void __launch_bounds__(128, 3) flux_tm_kernel(const FluxArgs a, const
         }
         __syncthreads();
 
-        const bool upd_ok = (s0 + s > fStart) && (s0 + s < fB) && (s0 + s >= G) && (s0 + s < a.N - G) && line_ok && row_sel;
+        const bool upd_ok = (s0 + s > fStart) && (s0 + s < fB) && (s0 + s >= G) && (s0 + s < a.N - G) && line_ok;
         if (t == 0) {
             if constexpr (DIR == 1) tma_issue_operands<NT, T::YW>(a, &tmap, stu, &bars[1], s0);
             if (s0 + NS < fB) tma_issue_state<DIR, NT, T::YW>(a, &tmap, stq, &bars[0], s0 + NS + 3);
@@ -889,7 +863,7 @@ __global__ void __launch_bounds__(128, 3) flux_tm_kernel(const FluxArgs a, const
                 const int io = T::fbi(s + 1, p);
 #pragma unroll
                 for (int m = 0; m < 7; ++m) fb[m * FBS + io] = fh[m];
-                if (line < a.NP && row_sel && (seg == 0 || f >= fA)) {
+                if (line < a.NP && (seg == 0 || f >= fA)) {
                     constexpr int TV = DIR == 0 ? CQ_V2 : CQ_V3;
                     const double bv2 = cb[CQ_B1 * CBS + iL] * cb[TV * CBS + iL] + cb[CQ_B1 * CBS + iR] * cb[TV * CBS + iR];
                     const size_t g = DIR == 0 ? (size_t)f + (size_t)a.pitch * line : (size_t)line + (size_t)a.pitch * f;

@@ -43,7 +43,6 @@ struct FluxArgs {
     double gam, eps;
     double g2;               // (gam-2)/(gam-1), a constant of the run (face_coefficients)
     int is1d;
-    int row_mode;            // x sweep: 0 all rows, 1 interior rows only, 2 ghost rows only (halo-exchange overlap)
     int branch;              // 0: E branch (qc[7] = E), 1: S branch (qc[7] = S; weno5_flux_difference_S, Weno5_2D.jl:361)
     // x sweep on a y-slab whose ghost rows are still in flight: the strips with ghost rows wait for flags[0] (rows
     // from the lower neighbour) / flags[1] (upper) >= wait_seq inside the kernel; nullptr: nothing to wait for
