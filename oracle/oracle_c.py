@@ -19,6 +19,12 @@ class OrcParams(C.Structure):
                 ("bc_x", C.c_int), ("bc_y", C.c_int), ("variant", C.c_int)]
 
 
+class OrcParams3(C.Structure):
+    _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("dx", C.c_double), ("dy", C.c_double),
+                ("dz", C.c_double), ("gam", C.c_double), ("cfl", C.c_double), ("eps", C.c_double),
+                ("bc_x", C.c_int), ("bc_y", C.c_int), ("bc_z", C.c_int)]
+
+
 def build(force=False):
     libs = [os.path.join(_HERE, n) for n in ("liboracle.so", "liboracle_fast.so")]
     src = os.path.join(_HERE, "weno5_oracle.c")
@@ -48,6 +54,13 @@ def lib(fast=False):
         L.orc_sweep_2d_S.argtypes = [pp, dp, C.c_int, dp, dp]
         L.orc_rk4_step_2d_dual.argtypes = [pp, dp, dp, dp, C.c_double, C.c_double, dp, dp, dp, C.POINTER(C.c_long)]
         L.orc_num_threads.restype = C.c_int
+        p3 = C.POINTER(OrcParams3)
+        L.orc_rk4_step_3d.argtypes = [p3, dp, dp, dp, dp, C.c_double, C.c_int, dp, dp, dp, dp]
+        L.orc_timestep_3d.argtypes = [p3, dp, dp, dp]
+        L.orc_divb_3d.argtypes = [p3, dp, dp, dp, dp]
+        L.orc_center2face_3d.argtypes = [p3, dp, dp, dp, dp]
+        L.orc_boundaries_3d.argtypes = [p3, dp, dp, dp, dp]
+        L.orc_advance_3d.argtypes = [p3, dp, dp, dp, dp, C.c_int, C.c_int, dp]
         _libs[key] = L
     return _libs[key]
 
@@ -169,3 +182,63 @@ def vmax_1d(g, q):
 
 def num_threads(fast=True):
     return lib(fast).orc_num_threads()
+
+
+# ----------------------------------------------------------------------------- 3-D extension
+def params3(g):
+    """g: julia_b200.problems3d.Grid3D."""
+    return OrcParams3(g.nx, g.ny, g.nz, g.dx, g.dy, g.dz, g.gam, g.cfl, g.eps, int(g.bc_x), int(g.bc_y), int(g.bc_z))
+
+
+def rk4_step_3d(g, q, bxb, byb, bzb, dt, roundtrip=True, fast=False):
+    q, bxb, byb, bzb = _f(q), _f(bxb), _f(byb), _f(bzb)
+    q4 = np.zeros_like(q, order="F")
+    b4 = [np.zeros_like(bxb, order="F") for _ in range(3)]
+    P = params3(g)
+    rc = lib(fast).orc_rk4_step_3d(C.byref(P), _p(q), _p(bxb), _p(byb), _p(bzb), float(dt), int(bool(roundtrip)),
+                                   _p(q4), _p(b4[0]), _p(b4[1]), _p(b4[2]))
+    assert rc == 0
+    return q4, b4[0], b4[1], b4[2]
+
+
+def timestep_3d(g, q, fast=False):
+    q = _f(q)
+    dt = C.c_double()
+    vm = (C.c_double * 3)()
+    P = params3(g)
+    lib(fast).orc_timestep_3d(C.byref(P), _p(q), C.byref(dt), vm)
+    return dt.value, [float(v) for v in vm]
+
+
+def advance_3d(g, q, bxb, byb, bzb, nsteps, roundtrip=True, fast=False):
+    q, bxb, byb, bzb = (_f(a).copy(order="F") for a in (q, bxb, byb, bzb))
+    t = C.c_double(0.0)
+    P = params3(g)
+    rc = lib(fast).orc_advance_3d(C.byref(P), _p(q), _p(bxb), _p(byb), _p(bzb), int(nsteps), int(bool(roundtrip)),
+                                  C.byref(t))
+    assert rc == 0
+    return q, bxb, byb, bzb, t.value
+
+
+def divb_3d(g, bxb, byb, bzb):
+    bxb, byb, bzb = _f(bxb), _f(byb), _f(bzb)
+    d = np.zeros_like(bxb, order="F")
+    P = params3(g)
+    lib().orc_divb_3d(C.byref(P), _p(bxb), _p(byb), _p(bzb), _p(d))
+    return d
+
+
+def center2face_3d(g, q):
+    q = _f(q)
+    b = [np.zeros(q.shape[:3], order="F") for _ in range(3)]
+    P = params3(g)
+    lib().orc_center2face_3d(C.byref(P), _p(q), _p(b[0]), _p(b[1]), _p(b[2]))
+    return b
+
+
+def boundaries_3d(g, q=None, a=None, b=None, c=None):
+    P = params3(g)
+    nul = C.POINTER(C.c_double)()
+    for x in (q, a, b, c):
+        assert x is None or (x.flags.f_contiguous and x.dtype == np.float64)
+    lib().orc_boundaries_3d(C.byref(P), *[(_p(x) if x is not None else nul) for x in (q, a, b, c)])

@@ -977,3 +977,347 @@ int orc_num_threads(void)
     return 1;
 #endif
 }
+
+/* ================================================================== 3-D extension
+ * The reference has no 3-D solver; its classical_RK4_step docstring (Weno5_2D.jl:113-123) states the design:
+ * the scheme is dimensionally unsplit, "the Roe solver / Weno functions are inherently the same for 1D, 2D and
+ * 3D" and every direction is swept with the same functions on a rotated state.  This section extends
+ * classical_RK4_step accordingly: a third sweep along z in the frame (z,x,y) (the cyclic continuation of
+ * rotate_state, :1897-1927), flux differences of rho, M, E from all three sweeps, and constrained transport of
+ * all three face fields from the edge-centred EMFs built of the six transport fluxes (the 3-D form of
+ * corner_fluxes :319-342 and of the face updates :150-151, Ryu et al. 1998 eqs. 3.11-3.13):
+ *   x sweep: f_y = bs2 (By vx), f_z = bs3 (Bz vx)   at faces (i+1/2,j,k)
+ *   y sweep: g_z = bs2 (Bz vy), g_x = bs3 (Bx vy)   at faces (i,j+1/2,k)
+ *   z sweep: h_x = bs2 (Bx vz), h_y = bs3 (By vz)   at faces (i,j,k+1/2)
+ *   Ox[i,j,k] = (h_y[i,j,k] + h_y[i,j+1,k] - g_z[i,j,k] - g_z[i,j,k+1]) / 2      edge (i,j+1/2,k+1/2)
+ *   Oy[i,j,k] = (f_z[i,j,k] + f_z[i,j,k+1] - h_x[i,j,k] - h_x[i+1,j,k]) / 2      edge (i+1/2,j,k+1/2)
+ *   Oz[i,j,k] = (g_x[i,j,k] + g_x[i+1,j,k] - f_y[i,j,k] - f_y[i,j+1,k]) / 2      edge (i+1/2,j+1/2,k)  (= the 2-D Ox)
+ *   bxb -= c dt ((Oz - Oz[j-1])/dy - (Oy - Oy[k-1])/dz),  byb -= c dt ((Ox - Ox[k-1])/dz - (Oz - Oz[i-1])/dx),
+ *   bzb -= c dt ((Oy - Oy[i-1])/dx - (Ox - Ox[j-1])/dy).
+ * Pinned by reduction: a state that does not depend on one coordinate (and has no field or velocity along it)
+ * reproduces orc_rk4_step_2d in each of the three orientations (tests/test_oracle3d.py).
+ * Layout: q[i + Nx*(j + Ny*(k + Nz*c))], c as in 2-D; bxb, byb, bzb [Nx,Ny,Nz]. */
+
+typedef struct {
+    int nx, ny, nz;
+    double dx, dy, dz, gam, cfl, eps;
+    int bc_x, bc_y, bc_z;
+} orc_params3;
+
+#define ID3(i, j, k) ((size_t)(i) + (size_t)Nx * ((size_t)(j) + (size_t)Ny * (size_t)(k)))
+
+/* ghost fill of one volume along one axis (the 3-D continuation of fill_axis_x/y) */
+static void fill_axis3(double *f, int Nx, int Ny, int Nz, int axis, int bc)
+{
+    const int N[3] = {Nx, Ny, Nz};
+    const size_t st[3] = {1, (size_t)Nx, (size_t)Nx * Ny};
+    const int a1 = (axis + 1) % 3, a2 = (axis + 2) % 3;
+    const int n = N[axis] - 2 * NB;
+#pragma omp parallel for schedule(static)
+    for (int v = 0; v < N[a2]; ++v)
+        for (int u = 0; u < N[a1]; ++u) {
+            double *l = f + st[a1] * u + st[a2] * v;
+            for (int g = 0; g < NB; ++g) {
+                if (bc == 1) {
+                    l[st[axis] * g] = l[st[axis] * (n + g)];
+                    l[st[axis] * (N[axis] - NB + g)] = l[st[axis] * (NB + g)];
+                } else {
+                    l[st[axis] * g] = l[st[axis] * NB];
+                    l[st[axis] * (N[axis] - NB + g)] = l[st[axis] * (N[axis] - NB - 1)];
+                }
+            }
+        }
+}
+
+static void boundaries_q3(double *q, int ncomp, const orc_params3 *P)
+{
+    const int Nx = P->nx + 2 * NB, Ny = P->ny + 2 * NB, Nz = P->nz + 2 * NB;
+    const size_t vol = (size_t)Nx * Ny * Nz;
+    for (int c = 0; c < ncomp; ++c) {
+        fill_axis3(q + c * vol, Nx, Ny, Nz, 0, P->bc_x);
+        fill_axis3(q + c * vol, Nx, Ny, Nz, 1, P->bc_y);
+        fill_axis3(q + c * vol, Nx, Ny, Nz, 2, P->bc_z);
+    }
+}
+
+/* the flux / face-array rules of boundaries! (Weno5_2D.jl:1704-1729) per axis: low side, high side, rim */
+static void boundaries_flux3(double *f, const orc_params3 *P)
+{
+    const int Nx = P->nx + 2 * NB, Ny = P->ny + 2 * NB, Nz = P->nz + 2 * NB;
+    const int N[3] = {Nx, Ny, Nz}, bc[3] = {P->bc_x, P->bc_y, P->bc_z};
+    const size_t st[3] = {1, (size_t)Nx, (size_t)Nx * Ny};
+    for (int pass = 0; pass < 3; ++pass)          /* 0: low sides, 1: high sides, 2: zero rims */
+        for (int axis = 0; axis < 3; ++axis) {
+            const int a1 = (axis + 1) % 3, a2 = (axis + 2) % 3;
+            if (bc[axis] == 1) { if (pass == 0) fill_axis3(f, Nx, Ny, Nz, axis, 1); continue; }
+            for (int v = 0; v < N[a2]; ++v)
+                for (int u = 0; u < N[a1]; ++u) {
+                    double *l = f + st[a1] * u + st[a2] * v;
+                    const size_t s = st[axis];
+                    const int n = N[axis];
+                    if (pass == 0) { l[s * 1] = l[s * 2]; l[0] = l[s * 2]; }
+                    else if (pass == 1) { l[s * (n - 2)] = l[s * (n - 3)]; l[s * (n - 1)] = l[s * (n - 3)]; }
+                    else { l[0] = 0.0; l[s * (n - 1)] = 0.0; }
+                }
+        }
+}
+
+/* One directional sweep of the E branch on the volume.  q: 8 volumes [rho,Mx,My,Mz,Bx,By,Bz,E]; dq: 5 volumes
+ * [rho,Mx,My,Mz,E] (zeroed here; fhat differences, not yet divided by the cell size); bsA, bsB: the two transport
+ * fluxes of the direction (table above).  Lines one ghost cell beyond the interior are swept too, like the 2-D
+ * sweeps do for fsy/gsx. */
+static void sweep3(const orc_params3 *P, const double *q, int dir, double *dq, double *bsA, double *bsB)
+{
+    const int Nx = P->nx + 2 * NB, Ny = P->ny + 2 * NB, Nz = P->nz + 2 * NB;
+    const size_t vol = (size_t)Nx * Ny * Nz;
+    const int N[3] = {Nx, Ny, Nz}, bc[3] = {P->bc_x, P->bc_y, P->bc_z};
+    const size_t st[3] = {1, (size_t)Nx, (size_t)Nx * Ny};
+    /* line component c reads volume in[dir][c]: (x,y,z) -> (y,z,x) -> (z,x,y) */
+    static const int in[3][8] = {{0, 1, 2, 3, 4, 5, 6, 7}, {0, 2, 3, 1, 5, 6, 4, 7}, {0, 3, 1, 2, 6, 4, 5, 7}};
+    /* fhat comps [rho,M1,M2,M3,.,.,E] -> dq volume (0 rho, 1 Mx, 2 My, 3 Mz, 4 E) */
+    static const int out[3][7] = {{0, 1, 2, 3, -1, -1, 4}, {0, 2, 3, 1, -1, -1, 4}, {0, 3, 1, 2, -1, -1, 4}};
+    const int a1 = (dir + 1) % 3, a2 = (dir + 2) % 3, n = N[dir];
+    memset(dq, 0, 5 * vol * sizeof(double));
+    memset(bsA, 0, vol * sizeof(double));
+    memset(bsB, 0, vol * sizeof(double));
+#pragma omp parallel
+    {
+        double (*line)[8] = malloc(sizeof(double[8]) * n);
+        double (*fh)[7] = malloc(sizeof(double[7]) * n);
+        double *b2 = malloc(sizeof(double) * n), *b3 = malloc(sizeof(double) * n);
+        double *work = malloc(sizeof(double) * 32 * n);
+#pragma omp for schedule(static) collapse(2)
+        for (int v = NB - 1; v <= N[a2] - NB; ++v)
+            for (int u = NB - 1; u <= N[a1] - NB; ++u) {
+                const size_t o = st[a1] * u + st[a2] * v;
+                for (int s = 0; s < n; ++s)
+                    for (int c = 0; c < 8; ++c) line[s][c] = q[in[dir][c] * vol + o + st[dir] * s];
+                memset(fh, 0, sizeof(double[7]) * n);
+                sweep_line(n, line, P->gam, P->eps, bc[dir], 0, 0, fh, b2, b3, work);
+                for (int s = NB - 1; s <= n - NB; ++s) {
+                    for (int c = 0; c < 7; ++c)
+                        if (out[dir][c] >= 0) dq[out[dir][c] * vol + o + st[dir] * s] = fh[s][c] - fh[s - 1][c];
+                    bsA[o + st[dir] * s] = b2[s];
+                    bsB[o + st[dir] * s] = b3[s];
+                }
+            }
+        free(line); free(fh); free(b2); free(b3); free(work);
+    }
+}
+
+typedef struct { double *dF[3], *fl[6], *O[3], *qE; } stage_work3;
+
+static void ct_update3(const orc_params3 *P, stage_work3 *W, const double *const bb[3], double c, double dt,
+                       double *const bn[3], double *Bc /* 3 volumes */)
+{
+    const int Nx = P->nx + 2 * NB, Ny = P->ny + 2 * NB, Nz = P->nz + 2 * NB;
+    const size_t vol = (size_t)Nx * Ny * Nz;
+    const double *fy = W->fl[0], *fz = W->fl[1], *gz = W->fl[2], *gx = W->fl[3], *hx = W->fl[4], *hy = W->fl[5];
+    double *Ox = W->O[0], *Oy = W->O[1], *Oz = W->O[2];
+    for (int m = 0; m < 3; ++m) memset(W->O[m], 0, vol * sizeof(double));
+#pragma omp parallel for schedule(static)
+    for (int k = 1; k < Nz - 1; ++k)
+        for (int j = 1; j < Ny - 1; ++j)
+            for (int i = 1; i < Nx - 1; ++i) {
+                Ox[ID3(i, j, k)] = 0.5 * (hy[ID3(i, j, k)] + hy[ID3(i, j + 1, k)] - gz[ID3(i, j, k)] - gz[ID3(i, j, k + 1)]);
+                Oy[ID3(i, j, k)] = 0.5 * (fz[ID3(i, j, k)] + fz[ID3(i, j, k + 1)] - hx[ID3(i, j, k)] - hx[ID3(i + 1, j, k)]);
+                Oz[ID3(i, j, k)] = 0.5 * (gx[ID3(i, j, k)] + gx[ID3(i + 1, j, k)] - fy[ID3(i, j, k)] - fy[ID3(i, j + 1, k)]);
+            }
+    const double cx = c * dt / P->dx, cy = c * dt / P->dy, cz = c * dt / P->dz;
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < Nz; ++k)
+        for (int j = 0; j < Ny; ++j)
+            for (int i = 0; i < Nx; ++i) {
+                const int inner = i >= 1 && i < Nx - 1 && j >= 1 && j < Ny - 1 && k >= 1 && k < Nz - 1;
+                const size_t a = ID3(i, j, k);
+                double ox = Ox[a], oy = Oy[a], oz = Oz[a];
+                double ox_j = inner ? Ox[ID3(i, j - 1, k)] : 0.0, ox_k = inner ? Ox[ID3(i, j, k - 1)] : 0.0;
+                double oy_i = inner ? Oy[ID3(i - 1, j, k)] : 0.0, oy_k = inner ? Oy[ID3(i, j, k - 1)] : 0.0;
+                double oz_i = inner ? Oz[ID3(i - 1, j, k)] : 0.0, oz_j = inner ? Oz[ID3(i, j - 1, k)] : 0.0;
+                bn[0][a] = bb[0][a] - cy * (oz - oz_j) + cz * (oy - oy_k);
+                bn[1][a] = bb[1][a] - cz * (ox - ox_k) + cx * (oz - oz_i);
+                bn[2][a] = bb[2][a] - cx * (oy - oy_i) + cy * (ox - ox_j);
+            }
+    memset(Bc, 0, 3 * vol * sizeof(double));
+#pragma omp parallel for schedule(static)
+    for (int k = NB; k <= Nz - 3; ++k)
+        for (int j = NB; j <= Ny - 3; ++j)
+            for (int i = NB; i <= Nx - 3; ++i) {
+                const double *x = bn[0], *y = bn[1], *z = bn[2];
+                Bc[ID3(i, j, k)] = (-x[ID3(i - 2, j, k)] + 9.0 * x[ID3(i - 1, j, k)] + 9.0 * x[ID3(i, j, k)] - x[ID3(i + 1, j, k)]) / 16.0;
+                Bc[vol + ID3(i, j, k)] = (-y[ID3(i, j - 2, k)] + 9.0 * y[ID3(i, j - 1, k)] + 9.0 * y[ID3(i, j, k)] - y[ID3(i, j + 1, k)]) / 16.0;
+                Bc[2 * vol + ID3(i, j, k)] = (-z[ID3(i, j, k - 2)] + 9.0 * z[ID3(i, j, k - 1)] + 9.0 * z[ID3(i, j, k)] - z[ID3(i, j, k + 1)]) / 16.0;
+            }
+}
+
+/* one stage: qk 9 volumes, base 8 volumes [..,E], out 9 volumes; roundtrip: E <- S2E(E2S(E)) as the 2-D reference */
+static void stage_3d(const orc_params3 *P, const double *qk, const double *base, const double *const bb[3], double c,
+                     double dt, int roundtrip, double *out, double *const bn[3], stage_work3 *W)
+{
+    const int Nx = P->nx + 2 * NB, Ny = P->ny + 2 * NB, Nz = P->nz + 2 * NB;
+    const size_t vol = (size_t)Nx * Ny * Nz;
+    memcpy(W->qE, qk, 7 * vol * sizeof(double));
+    memcpy(W->qE + 7 * vol, qk + 8 * vol, vol * sizeof(double));
+    sweep3(P, W->qE, 0, W->dF[0], W->fl[0], W->fl[1]);
+    sweep3(P, W->qE, 1, W->dF[1], W->fl[2], W->fl[3]);
+    sweep3(P, W->qE, 2, W->dF[2], W->fl[4], W->fl[5]);
+    double *qn = W->qE;
+    static const int dst[5] = {0, 1, 2, 3, 7};
+    const double ix = 1.0 / P->dx, iy = 1.0 / P->dy, iz = 1.0 / P->dz, cdt = c * dt;
+    for (int m = 0; m < 5; ++m) {
+        const double *b = base + dst[m] * vol, *fx = W->dF[0] + m * vol, *fy = W->dF[1] + m * vol, *fz = W->dF[2] + m * vol;
+        double *o = qn + dst[m] * vol;
+#pragma omp parallel for schedule(static)
+        for (size_t a = 0; a < vol; ++a) o[a] = b[a] - cdt * ((fx[a] * ix + fy[a] * iy) + fz[a] * iz);
+    }
+    boundaries_q3(qn, 8, P);
+    for (int m = 0; m < 6; ++m) boundaries_flux3(W->fl[m], P);
+    ct_update3(P, W, bb, c, dt, bn, qn + 4 * vol);
+    boundaries_q3(qn, 8, P);
+    memcpy(out, qn, 7 * vol * sizeof(double));
+    double *S = out + 7 * vol, *E = out + 8 * vol;
+#pragma omp parallel for schedule(static)
+    for (size_t a = 0; a < vol; ++a) {
+        S[a] = e2s(qn[a], qn[vol + a], qn[2 * vol + a], qn[3 * vol + a], qn[4 * vol + a], qn[5 * vol + a],
+                   qn[6 * vol + a], qn[7 * vol + a], P->gam);
+        E[a] = roundtrip ? s2e(qn[a], qn[vol + a], qn[2 * vol + a], qn[3 * vol + a], qn[4 * vol + a], qn[5 * vol + a],
+                               qn[6 * vol + a], S[a], P->gam)
+                         : qn[7 * vol + a];
+    }
+    boundaries_q3(out, 9, P);
+}
+
+int orc_rk4_step_3d(const orc_params3 *P, const double *q0, const double *bxb0, const double *byb0, const double *bzb0,
+                    double dt, int roundtrip, double *q4, double *bxb4, double *byb4, double *bzb4)
+{
+    const int Nx = P->nx + 2 * NB, Ny = P->ny + 2 * NB, Nz = P->nz + 2 * NB;
+    const size_t vol = (size_t)Nx * Ny * Nz;
+    stage_work3 W;
+    for (int m = 0; m < 3; ++m) { W.dF[m] = malloc(5 * vol * sizeof(double)); W.O[m] = malloc(vol * sizeof(double)); }
+    for (int m = 0; m < 6; ++m) W.fl[m] = malloc(vol * sizeof(double));
+    W.qE = malloc(8 * vol * sizeof(double));
+    double *q0E = malloc(8 * vol * sizeof(double)), *base = malloc(8 * vol * sizeof(double));
+    double *qs[4] = {NULL, malloc(9 * vol * sizeof(double)), malloc(9 * vol * sizeof(double)), malloc(9 * vol * sizeof(double))};
+    double *bs[4][3], *bbase[3];
+    for (int s = 1; s < 4; ++s) for (int m = 0; m < 3; ++m) bs[s][m] = malloc(vol * sizeof(double));
+    for (int m = 0; m < 3; ++m) bbase[m] = malloc(vol * sizeof(double));
+    if (!W.qE || !q0E || !base || !qs[1] || !qs[2] || !qs[3] || !bbase[2]) return -1;
+    memcpy(q0E, q0, 7 * vol * sizeof(double));
+    memcpy(q0E + 7 * vol, q0 + 8 * vol, vol * sizeof(double));
+    const double *const b0[3] = {bxb0, byb0, bzb0};
+
+    stage_3d(P, q0, q0E, b0, 0.5, dt, roundtrip, qs[1], bs[1], &W);
+    stage_3d(P, qs[1], q0E, b0, 0.5, dt, roundtrip, qs[2], bs[2], &W);
+    stage_3d(P, qs[2], q0E, b0, 1.0, dt, roundtrip, qs[3], bs[3], &W);
+    for (int c = 0; c < 8; ++c) {
+        const int src = (c == 7) ? 8 : c;
+        for (size_t a = 0; a < vol; ++a)
+            base[c * vol + a] = 1.0 / 3 * (-q0E[c * vol + a] + qs[1][src * vol + a] + 2 * qs[2][src * vol + a] + qs[3][src * vol + a]);
+    }
+    for (int m = 0; m < 3; ++m)
+        for (size_t a = 0; a < vol; ++a)
+            bbase[m][a] = 1.0 / 3 * (-b0[m][a] + bs[1][m][a] + 2 * bs[2][m][a] + bs[3][m][a]);
+    double *const b4[3] = {bxb4, byb4, bzb4};
+    const double *const bbc[3] = {bbase[0], bbase[1], bbase[2]};
+    stage_3d(P, qs[3], base, bbc, 1.0 / 6, dt, roundtrip, q4, b4, &W);
+    for (int m = 0; m < 3; ++m) boundaries_flux3(b4[m], P);
+
+    for (int m = 0; m < 3; ++m) { free(W.dF[m]); free(W.O[m]); free(bbase[m]); }
+    for (int m = 0; m < 6; ++m) free(W.fl[m]);
+    free(W.qE); free(q0E); free(base);
+    for (int s = 1; s < 4; ++s) { free(qs[s]); for (int m = 0; m < 3; ++m) free(bs[s][m]); }
+    return 0;
+}
+
+/* timestep in 3-D: the 2-D rule (x-face averages, S-based pressure, Weno5_2D.jl:1942-1984) with a third direction */
+int orc_timestep_3d(const orc_params3 *P, const double *q, double *dt, double vmax[3])
+{
+    const int Nx = P->nx + 2 * NB, Ny = P->ny + 2 * NB, Nz = P->nz + 2 * NB;
+    const size_t vol = (size_t)Nx * Ny * Nz;
+    double mx = -INFINITY, my = -INFINITY, mz = -INFINITY;
+#pragma omp parallel for reduction(max : mx, my, mz) schedule(static)
+    for (int k = NB; k <= Nz - NB - 1; ++k)
+        for (int j = NB; j <= Ny - NB - 1; ++j)
+            for (int i = NB; i <= Nx - NB - 1; ++i) {
+                size_t a = ID3(i, j, k), b = ID3(i + 1, j, k);
+                double rho = (q[a] + q[b]) / 2;
+                double vx = (q[vol + a] + q[vol + b]) / 2 / rho;
+                double vy = (q[2 * vol + a] + q[2 * vol + b]) / 2 / rho;
+                double vz = (q[3 * vol + a] + q[3 * vol + b]) / 2 / rho;
+                double Bx = (q[4 * vol + a] + q[4 * vol + b]) / 2;
+                double By = (q[5 * vol + a] + q[5 * vol + b]) / 2;
+                double Bz = (q[6 * vol + a] + q[6 * vol + b]) / 2;
+                double S = (q[7 * vol + a] + q[7 * vol + b]) / 2;
+                double pres = S * pow(rho, P->gam - 1);
+                double cs2 = P->gam * fabs(pres / rho);
+                double B2 = Bx * Bx + By * By + Bz * Bz;
+                double bbn2 = B2 / rho, s = bbn2 + cs2;
+                double rx = sqrt(fmax(0.0, s * s - 4 * (Bx * Bx / rho) * cs2));
+                double ry = sqrt(fmax(0.0, s * s - 4 * (By * By / rho) * cs2));
+                double rz = sqrt(fmax(0.0, s * s - 4 * (Bz * Bz / rho) * cs2));
+                mx = fmax(mx, fabs(vx) + sqrt(0.5 * (s + rx)));
+                my = fmax(my, fabs(vy) + sqrt(0.5 * (s + ry)));
+                mz = fmax(mz, fabs(vz) + sqrt(0.5 * (s + rz)));
+            }
+    vmax[0] = mx; vmax[1] = my; vmax[2] = mz;
+    *dt = P->cfl / (mx / P->dx + my / P->dy + mz / P->dz);
+    return 0;
+}
+
+int orc_divb_3d(const orc_params3 *P, const double *bxb, const double *byb, const double *bzb, double *divb)
+{
+    const int Nx = P->nx + 2 * NB, Ny = P->ny + 2 * NB, Nz = P->nz + 2 * NB;
+    memset(divb, 0, sizeof(double) * (size_t)Nx * Ny * Nz);
+    for (int k = NB - 1; k <= Nz - NB - 1; ++k)
+        for (int j = NB - 1; j <= Ny - NB - 1; ++j)
+            for (int i = NB - 1; i <= Nx - NB - 1; ++i)
+                divb[ID3(i, j, k)] = (bxb[ID3(i, j, k)] - bxb[ID3(i - 1, j, k)]) / P->dx
+                                   + (byb[ID3(i, j, k)] - byb[ID3(i, j - 1, k)]) / P->dy
+                                   + (bzb[ID3(i, j, k)] - bzb[ID3(i, j, k - 1)]) / P->dz;
+    return 0;
+}
+
+/* interpolateB_center2face (Weno5_2D.jl:1669-1682) with the z face field */
+int orc_center2face_3d(const orc_params3 *P, const double *q, double *bxb, double *byb, double *bzb)
+{
+    const int Nx = P->nx + 2 * NB, Ny = P->ny + 2 * NB, Nz = P->nz + 2 * NB;
+    const size_t vol = (size_t)Nx * Ny * Nz;
+    memset(bxb, 0, vol * sizeof(double)); memset(byb, 0, vol * sizeof(double)); memset(bzb, 0, vol * sizeof(double));
+    const double *Bx = q + 4 * vol, *By = q + 5 * vol, *Bz = q + 6 * vol;
+    for (int k = 1; k <= Nz - 3; ++k)
+        for (int j = 1; j <= Ny - 3; ++j)
+            for (int i = 1; i <= Nx - 3; ++i) {
+                bxb[ID3(i, j, k)] = (-Bx[ID3(i - 1, j, k)] + 9 * Bx[ID3(i, j, k)] + 9 * Bx[ID3(i + 1, j, k)] - Bx[ID3(i + 2, j, k)]) / 16;
+                byb[ID3(i, j, k)] = (-By[ID3(i, j - 1, k)] + 9 * By[ID3(i, j, k)] + 9 * By[ID3(i, j + 1, k)] - By[ID3(i, j + 2, k)]) / 16;
+                bzb[ID3(i, j, k)] = (-Bz[ID3(i, j, k - 1)] + 9 * Bz[ID3(i, j, k)] + 9 * Bz[ID3(i, j, k + 1)] - Bz[ID3(i, j, k + 2)]) / 16;
+            }
+    return 0;
+}
+
+int orc_boundaries_3d(const orc_params3 *P, double *q9, double *a, double *b, double *c)
+{
+    if (q9) boundaries_q3(q9, 9, P);
+    if (a) boundaries_flux3(a, P);
+    if (b) boundaries_flux3(b, P);
+    if (c) boundaries_flux3(c, P);
+    return 0;
+}
+
+int orc_advance_3d(const orc_params3 *P, double *q, double *bxb, double *byb, double *bzb, int nsteps, int roundtrip,
+                   double *t)
+{
+    const int Nx = P->nx + 2 * NB, Ny = P->ny + 2 * NB, Nz = P->nz + 2 * NB;
+    const size_t vol = (size_t)Nx * Ny * Nz;
+    double *q4 = malloc(9 * vol * sizeof(double)), *b4[3];
+    for (int m = 0; m < 3; ++m) b4[m] = malloc(vol * sizeof(double));
+    for (int s = 0; s < nsteps; ++s) {
+        double dt, vm[3];
+        orc_timestep_3d(P, q, &dt, vm);
+        if (orc_rk4_step_3d(P, q, bxb, byb, bzb, dt, roundtrip, q4, b4[0], b4[1], b4[2])) return -1;
+        memcpy(q, q4, 9 * vol * sizeof(double));
+        memcpy(bxb, b4[0], vol * sizeof(double)); memcpy(byb, b4[1], vol * sizeof(double)); memcpy(bzb, b4[2], vol * sizeof(double));
+        *t += dt;
+    }
+    free(q4); for (int m = 0; m < 3; ++m) free(b4[m]);
+    return 0;
+}

@@ -1,0 +1,97 @@
+"""
+CPU tests of the 3-D extension of the oracle.  The reference has no 3-D code (its RK4 docstring,
+Weno5_2D.jl:113-123, only states that the sweep functions serve every dimension), so the 3-D step is pinned by
+reduction: a state that is uniform along one coordinate must reproduce the 2-D oracle -- which is bit-identical to
+the reference -- in each of the three orientations; plus the invariants of the scheme and the symmetry under a
+cyclic renaming of the axes.
+"""
+import numpy as np
+import pytest
+
+from julia_b200 import problems as pr
+from julia_b200 import problems3d as p3
+from oracle import oracle_c as O
+
+I = slice(3, -3)
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+@pytest.mark.parametrize("orientation", [0, 1, 2])
+def test_uniform_along_one_axis_reproduces_the_2d_step(orientation):
+    g2, q, bx, by = pr.orszag_tang(16, ny=12, ysize=0.75)
+    dt = 0.6 * O.timestep_2d(g2, q)[0]
+    q2, bx2, by2 = O.rk4_step_2d(g2, q, bx, by, dt)
+    g, q3, b0, b1, b2 = p3.embed_2d(g2, q, bx, by, orientation, n3=3)
+    r = O.rk4_step_3d(g, q3, b0, b1, b2, dt)
+    faces = {orientation % 3: bx2, (orientation + 1) % 3: by2}
+    for idx in (3, 4, 5):                                  # every interior position along the uniform axis
+        for c in (0, 7, 8):
+            assert _rel(p3.extract_2d(r[0][..., c], orientation, idx)[I, I], q2[I, I, c]) < 2e-14
+        for base in ([1, 2, 3], [4, 5, 6]):
+            for m2 in range(3):
+                got = p3.extract_2d(r[0][..., base[p3.vector_component(orientation, m2)]], orientation, idx)
+                want = q2[I, I, base[m2]]
+                assert float(np.abs(got[I, I] - want).max()) < 2e-14 * max(1.0, np.abs(want).max())
+        for ax, want in faces.items():
+            assert _rel(p3.extract_2d(r[1 + ax], orientation, idx)[I, I], want[I, I]) < 2e-14
+
+
+def test_timestep_reduces_to_2d():
+    g2, q, bx, by = pr.orszag_tang(16)
+    dt2, vx, vy = O.timestep_2d(g2, q)
+    g, q3, *_ = p3.embed_2d(g2, q, bx, by, 0, n3=4, size3=1e9)      # a huge dz removes the z term of the CFL sum
+    dt3, vm = O.timestep_3d(g, q3)
+    assert abs(vm[0] - vx) < 1e-14 and abs(vm[1] - vy) < 1e-14
+    assert abs(dt3 - dt2) < 1e-9 * dt2
+
+
+def test_uniform_state_is_preserved_and_divb_stays_zero():
+    g = p3.Grid3D(nx=8, ny=6, nz=5)
+    X = np.ones(g.shape)
+    q, bx, by, bz = p3.assemble_3d(g, 1.3 * X, 0.4 * X, -0.3 * X, 0.2 * X, 0.7 * X, None, (0.5, -0.25, 0.75))
+    r = O.rk4_step_3d(g, q, bx, by, bz, 0.01)
+    assert _rel(r[0], q) < 1e-14
+    for a, b in zip(r[1:], (bx, by, bz)):
+        assert _rel(a, b) < 1e-15
+
+
+@pytest.mark.parametrize("bc", [pr.PERIODIC, pr.OUTFLOW])
+def test_conservation_and_divb_on_a_3d_state(bc):
+    g, q, bx, by, bz = p3.smooth_3d(12, 10, 9, bc=bc)
+    assert np.abs(O.divb_3d(g, bx, by, bz)[I, I, I]).max() < 1e-13
+    dt = O.timestep_3d(g, q)[0]
+    r = O.rk4_step_3d(g, q, bx, by, bz, dt)
+    assert np.abs(O.divb_3d(g, *r[1:])[I, I, I]).max() < 5e-13
+    assert np.isfinite(r[0]).all()
+    if bc == pr.PERIODIC:
+        for c in (0, 1, 2, 3):
+            s0, s1 = q[I, I, I, c].sum(), r[0][I, I, I, c].sum()
+            assert abs(s1 - s0) < 1e-11 * np.abs(q[I, I, I, c]).sum()
+        # face fluxes of B are conserved through the CT update
+        for a, b in zip(r[1:], (bx, by, bz)):
+            assert abs(a[I, I, I].sum() - b[I, I, I].sum()) < 1e-11 * np.abs(b[I, I, I]).sum()
+
+
+def test_cyclic_renaming_of_the_axes():
+    g, q, bx, by, bz = p3.smooth_3d(10, 9, 8)
+    dt = 0.8 * O.timestep_3d(g, q)[0]
+    r = O.rk4_step_3d(g, q, bx, by, bz, dt)
+    gr, qr, bxr, byr, bzr = p3.rotate_problem(g, q, bx, by, bz)
+    rr = O.rk4_step_3d(gr, qr, bxr, byr, bzr, dt)
+    _, q_want, bx_want, by_want, bz_want = p3.rotate_problem(g, *r)
+    assert _rel(rr[0][I, I, I], q_want[I, I, I]) < 1e-13
+    for a, b in zip(rr[1:], (bx_want, by_want, bz_want)):
+        assert _rel(a[I, I, I], b[I, I, I]) < 1e-13
+
+
+def test_center2face_and_helpers_agree_with_numpy():
+    g, q, bx, by, bz = p3.smooth_3d(8, 7, 6)
+    for a, b in zip(O.center2face_3d(g, q), p3.center2face_3d(q)):
+        assert np.array_equal(a, b)
+    # face -> centre -> compare with the state's own cell-centred field (interior)
+    Bc = p3.face2center_3d(bx, by, bz)
+    for m in range(3):
+        assert _rel(Bc[m][I, I, I], q[I, I, I, 4 + m]) < 1e-15
