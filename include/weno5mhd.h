@@ -135,6 +135,47 @@ int weno5_es_switch_mask(weno5_ctx *ctx, double *mask);
 int weno5_arr2img(weno5_ctx *ctx, int component, double lo, double hi, int log_scale, int ncolours, short *rimg,
                   double range_used[2]);
 
+/* ---- 3-D extension (SURVEY "next" row f4).  The reference has no 3-D solver; the docstring of classical_RK4_step
+ * (Weno5_2D.jl:113-123) states the design: the scheme is dimensionally unsplit and "the Roe solver / Weno functions are
+ * inherently the same for 1D, 2D and 3D", every direction being swept by the same functions on a rotated state.  These
+ * entry points are classical_RK4_step / timestep / boundaries! / compute_divB continued that way: a third sweep in the
+ * frame (z,x,y), flux differences of rho, M, E from three sweeps, constrained transport of three face fields from
+ * edge-centred EMFs (corner_fluxes, :319, per coordinate plane).  A state that is uniform along one axis reproduces the
+ * 2-D step.  Host arrays continue the 2-D layout:
+ *      q   (Nx,Ny,Nz,9)  [rho,Mx,My,Mz,Bx,By,Bz,S,E]     bxb, byb, bzb (Nx,Ny,Nz): B on the x-, y-, z-face i+1/2, ...
+ * with N* = n* + 2*3, column-major.  Single GPU. */
+typedef struct {
+    int nx, ny, nz;          /* interior cells                            */
+    double dx, dy, dz;
+    double gamma, cfl, eps;  /* as in weno5_params                        */
+    int bc_x, bc_y, bc_z;    /* WENO5_BC_*                                */
+    int es_roundtrip;        /* as in weno5_params                        */
+} weno5_params3d;
+
+typedef struct weno5_ctx3d weno5_ctx3d;
+int weno5_create_3d(const weno5_params3d *params, int device, weno5_ctx3d **out);
+int weno5_destroy_3d(weno5_ctx3d *ctx);
+/* bxb == byb == bzb == NULL derives the face fields with interpolateB_center2face (:1669); applies boundaries! (:39) */
+int weno5_upload_3d(weno5_ctx3d *ctx, const double *q, const double *bxb, const double *byb, const double *bzb);
+int weno5_download_3d(weno5_ctx3d *ctx, double *q, double *bxb, double *byb, double *bzb);
+/* timestep(q) (:1930) with three terms: dt = courFac / (vxmax/dx + vymax/dy + vzmax/dz) */
+int weno5_timestep_3d(weno5_ctx3d *ctx, double *dt, double vmax[3]);
+/* classical_RK4_step (:125) in place */
+int weno5_rk4_step_3d(weno5_ctx3d *ctx, double dt);
+/* the driver loop (:50-72) on the device, as weno5_advance */
+int weno5_advance_3d(weno5_ctx3d *ctx, int nsteps, double tmax, double *t, int *nsteps_done);
+/* compute_divB (:1986) with the z term -> (Nx,Ny,Nz) */
+int weno5_divb_3d(weno5_ctx3d *ctx, double *divb);
+/* interior sums of the 9 components of q and of bxb, byb, bzb */
+int weno5_totals_3d(weno5_ctx3d *ctx, double sums[12]);
+/* one-shot: host arrays in -> host arrays out */
+int weno5_classical_rk4_step_3d(const weno5_params3d *params, const double *q0, const double *bxb0, const double *byb0,
+                                const double *bzb0, double dt, double *q4, double *bxb4, double *byb4, double *bzb4);
+unsigned long long weno5_launch_count_3d(const weno5_ctx3d *ctx);
+/* accumulated device time (ms, CUDA events) and count of the sweep kernels since the last read */
+int weno5_profile_3d(weno5_ctx3d *ctx, int enable);
+int weno5_profile_read_3d(weno5_ctx3d *ctx, double *sweep_ms, unsigned long long *sweep_launches);
+
 /* ---- one-shot, reference-shaped calls: host arrays in -> host arrays out */
 /* (q4,bxb4,byb4) = classical_RK4_step(q0,bxb0,byb0,dt)   Weno5_2D.jl:125-317 */
 int weno5_classical_rk4_step_2d(const weno5_params *params, const double *q0, const double *bxb0,

@@ -1,0 +1,495 @@
+// 3-D extension of the WENO5 MHD step: per-thread bodies of every kernel and the stage sequence.
+//
+// The reference has no 3-D solver; its classical_RK4_step docstring (Weno5_2D.jl:113-123) states the design this file
+// follows: the scheme is dimensionally unsplit and every direction is swept by the same functions on a rotated state.
+// So the step is classical_RK4_step (:125-317) with a third sweep in the frame (z,x,y) -- the cyclic continuation of
+// rotate_state (:1897-1927) -- flux differences of rho, M, E from three sweeps, and constrained transport of three face
+// fields from edge-centred EMFs built of six transport fluxes (corner_fluxes :319-342 and the face updates :150-151
+// continued to 3-D, Ryu et al. 1998):
+//   x sweep: f_y = By vx, f_z = Bz vx;  y sweep: g_z = Bz vy, g_x = Bx vy;  z sweep: h_x = Bx vz, h_y = By vz
+//   Ox = (h_y + h_y[j+1] - g_z - g_z[k+1])/2,  Oy = (f_z + f_z[k+1] - h_x - h_x[i+1])/2,  Oz = (g_x + g_x[i+1] - f_y - f_y[j+1])/2
+//   bxb -= c dt ((Oz - Oz[j-1])/dy - (Oy - Oy[k-1])/dz), byb, bzb cyclically.
+// A state that is uniform along one axis reproduces the 2-D step in every orientation (tests/test_gpu_3d.py).
+//
+// Everything here is __host__ __device__: weno5_3d.cu wraps the bodies in kernels (one thread = one `tid` / one cell),
+// tests/hostmath/host3d.cpp runs the very same bodies and the same stage sequence in loops on the CPU, where they are
+// compared with the oracle without a GPU.  The product only ever runs them on the device.
+//
+// Layout: the public one, continued to 3-D: volume index i + Nx (j + Ny k), NBnd = 3 ghost layers, no padding --
+// weno5_upload_3d is a plain copy.  Ghost handling is by gather: a ghost location reads the location the boundary
+// rule maps it to (per axis: periodic wrap, outflow clamp), which reproduces boundaries! (:1684-1732) applied axis by
+// axis, including its rules for flux / face arrays (copy index 3 / N-2 outwards, zero rim).
+#pragma once
+#include <stddef.h>
+#include "weno5_math.cuh"
+
+namespace w5 {
+namespace d3 {
+
+constexpr int NB3 = 3;
+constexpr int NT3 = 256;                 // threads per CTA of the sweep kernels
+
+struct Dims {
+    int Nx, Ny, Nz;
+    int bc[3];                           // 0 outflow, 1 periodic
+};
+
+W5_HD size_t vidx(const Dims &d, int i, int j, int k)
+{
+    return (size_t)i + (size_t)d.Nx * ((size_t)j + (size_t)d.Ny * (size_t)k);
+}
+W5_HD int dimN(const Dims &d, int axis) { return axis == 0 ? d.Nx : (axis == 1 ? d.Ny : d.Nz); }
+
+// boundaries!(q) (Weno5_2D.jl:1686-1702) as a map: ghost cell -> interior cell [3, N-4] (0-based)
+W5_HD int map_cell(int idx, int N, int bc)
+{
+    const int n = N - 2 * NB3;
+    if (idx < NB3) return bc == 1 ? idx + n : NB3;
+    if (idx > N - NB3 - 1) return bc == 1 ? idx - n : N - NB3 - 1;
+    return idx;
+}
+// the flux / face-array rules (:1704-1729): outflow copies index 2 / N-3 (0-based) outwards, periodic wraps
+W5_HD int map_flux(int idx, int N, int bc)
+{
+    const int n = N - 2 * NB3;
+    if (bc == 1) {
+        if (idx < NB3) return idx + n;
+        if (idx > N - NB3 - 1) return idx - n;
+        return idx;
+    }
+    return idx < 2 ? 2 : (idx > N - 3 ? N - 3 : idx);
+}
+W5_HD bool on_rim(int idx, int N, int bc) { return bc != 1 && (idx == 0 || idx == N - 1); }
+
+// value of a flux / face array after boundaries! has been applied to it, read from the un-filled array
+W5_HD double flux_at(const double *f, const Dims &d, int i, int j, int k)
+{
+    if (on_rim(i, d.Nx, d.bc[0]) || on_rim(j, d.Ny, d.bc[1]) || on_rim(k, d.Nz, d.bc[2])) return 0.0;
+    return f[vidx(d, map_flux(i, d.Nx, d.bc[0]), map_flux(j, d.Ny, d.bc[1]), map_flux(k, d.Nz, d.bc[2]))];
+}
+
+// ------------------------------------------------------------------ directional sweep
+// weno5_flux_difference_E (Weno5_2D.jl:973-1018) along axis DIR of the volume, in the frame (DIR, DIR+1, DIR+2).
+struct SweepArgs {
+    const double *q[8];      // physical volumes rho,Mx,My,Mz,Bx,By,Bz,E
+    double *rhs[5];          // rho,Mx,My,Mz,E: sum over the sweeps of (fhat[c] - fhat[c-1]) / h
+    double *bsA, *bsB;       // the two transport fluxes of this direction (table above)
+    const double *dtp;       // device time step; 0 = finished, the kernel returns
+    Dims d;
+    double inv_h, gam, eps, g2;
+};
+
+// CTA tile: NF faces along the sweep x LW lines; x is always the fastest thread coordinate (coalesced loads)
+template <int DIR> struct SweepGeo {
+    static constexpr int NF = DIR == 0 ? 64 : 32;
+    static constexpr int LW = DIR == 0 ? 4 : 16;
+    static constexpr int SW = NF + 5;                  // cells along the sweep: faces f0 .. f0+NF-1 need f0-2 .. f0+NF+2
+    static constexpr int NCELLS = SW * LW, NFACES = NF * LW;
+    static constexpr int CBS = NCELLS, FBS = NFACES;
+    static constexpr int NFB = 5;                      // fhat components kept for the flux difference: rho, M1, M2, M3, E
+    static constexpr size_t SMEM = (size_t)(CQ_COUNT * CBS + NFB * FBS) * sizeof(double);
+    W5_HD static int cell_slot(int s, int l) { return DIR == 0 ? l * SW + s : s * LW + l; }
+    W5_HD static void cell_decode(int idx, int &s, int &l)
+    {
+        if (DIR == 0) { s = idx % SW; l = idx / SW; } else { l = idx % LW; s = idx / LW; }
+    }
+    W5_HD static int face_slot(int fs, int l) { return DIR == 0 ? l * NF + fs : fs * LW + l; }
+    W5_HD static void face_decode(int idx, int &fs, int &l)
+    {
+        if (DIR == 0) { fs = idx % NF; l = idx / NF; } else { l = idx % LW; fs = idx / LW; }
+    }
+    // number of tiles along the sweep: faces 2 .. n-3, a tile advances by NF-1 cells
+    W5_HD static int tiles_along(int n) { return (n - 5 + NF - 2) / (NF - 1); }
+    // grid: DIR 0: (tiles along x, line groups in j, k);  DIR 1: (line groups in i, tiles along y, k);
+    //       DIR 2: (line groups in i, tiles along z, j);  lines run over 2 .. N-3 (one ghost line each side)
+    W5_HD static void grid(const Dims &d, int g[3])
+    {
+        if (DIR == 0) { g[0] = tiles_along(d.Nx); g[1] = (d.Ny - 4 + LW - 1) / LW; g[2] = d.Nz - 4; }
+        if (DIR == 1) { g[0] = (d.Nx - 4 + LW - 1) / LW; g[1] = tiles_along(d.Ny); g[2] = d.Nz - 4; }
+        if (DIR == 2) { g[0] = (d.Nx - 4 + LW - 1) / LW; g[1] = tiles_along(d.Nz); g[2] = d.Ny - 4; }
+    }
+};
+
+// Position of a CTA: first face f0 along the sweep and the lateral coordinates (p1, p2) of line l
+template <int DIR> struct SweepPos {
+    int f0, n;            // first face, cells along the sweep
+    int l0, p2;           // first lateral coordinate of line 0, second lateral coordinate
+    int N1, N2;           // extents of the lateral axes
+    W5_HD SweepPos(const Dims &d, int bx, int by, int bz)
+    {
+        using T = SweepGeo<DIR>;
+        if (DIR == 0) { f0 = 2 + bx * (T::NF - 1); l0 = 2 + by * T::LW; p2 = 2 + bz; n = d.Nx; N1 = d.Ny; N2 = d.Nz; }
+        if (DIR == 1) { l0 = 2 + bx * T::LW; f0 = 2 + by * (T::NF - 1); p2 = 2 + bz; n = d.Ny; N1 = d.Nx; N2 = d.Nz; }
+        if (DIR == 2) { l0 = 2 + bx * T::LW; f0 = 2 + by * (T::NF - 1); p2 = 2 + bz; n = d.Nz; N1 = d.Nx; N2 = d.Ny; }
+    }
+    W5_HD bool line_ok(int l) const { return l0 + l <= N1 - 3; }                         // p2 <= N2-3 by the grid size
+    W5_HD bool line_interior(int l) const { return l0 + l >= 3 && l0 + l <= N1 - 4 && p2 >= 3 && p2 <= N2 - 4; }
+    W5_HD size_t gidx(const Dims &d, int s, int l) const
+    {
+        const int p1 = l0 + l;
+        return DIR == 0 ? vidx(d, s, p1, p2) : (DIR == 1 ? vidx(d, p1, s, p2) : vidx(d, p1, p2, s));
+    }
+};
+
+// sweep-frame component c reads physical volume sweep_in(DIR, c): (x,y,z) -> (y,z,x) -> (z,x,y)
+W5_HD int sweep_in(int dir, int c)
+{
+    // rho | M1 M2 M3 | B1 B2 B3 | E
+    if (c == 0 || c == 7) return c;
+    const int base = c < 4 ? 1 : 4, m = c - base;
+    return base + (m + dir) % 3;
+}
+// fhat component kept in slot m = 0..4 (rho, M1, M2, M3, E) -> rhs volume (rho, Mx, My, Mz, E)
+W5_HD int sweep_out(int dir, int m)
+{
+    if (m == 0 || m == 4) return m;
+    return 1 + (m - 1 + dir) % 3;
+}
+
+// phase 0: cons -> prim, wave speeds, flux of every cell of the tile -> shared memory
+template <int DIR>
+W5_HD void sweep_cells(const SweepArgs &a, int bx, int by, int bz, int tid, double *smem)
+{
+    using T = SweepGeo<DIR>;
+    const SweepPos<DIR> P(a.d, bx, by, bz);
+    double *cb = smem;
+    const int ni = P.n - 2 * NB3;
+    for (int idx = tid; idx < T::NCELLS; idx += NT3) {
+        int s, l;
+        T::cell_decode(idx, s, l);
+        if (!P.line_ok(l)) continue;
+        int cs = P.f0 - 2 + s;
+        // the stencil cell past the end of the line continues the boundary condition (quirk Q3 of the 2-D path)
+        if (cs >= P.n) cs = a.d.bc[DIR] == 1 ? cs - ni : P.n - 1;
+        if (cs >= P.n) cs = P.n - 1;                       // tiles reaching further than any face they own
+        const size_t g = P.gidx(a.d, cs, l);
+        double q[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) q[c] = a.q[sweep_in(DIR, c)][g];
+        CellOut o;
+        cell_quantities(q, a.gam, o);
+        const int i = T::cell_slot(s, l);
+#pragma unroll
+        for (int m = 0; m < 7; ++m) cb[(CQ_F0 + m) * T::CBS + i] = o.F[m];
+        cb[(CQ_Q0 + 0) * T::CBS + i] = q[0];
+        cb[(CQ_Q0 + 1) * T::CBS + i] = q[1];
+        cb[(CQ_Q0 + 2) * T::CBS + i] = q[2];
+        cb[(CQ_Q0 + 3) * T::CBS + i] = q[3];
+        cb[(CQ_Q0 + 4) * T::CBS + i] = q[5];
+        cb[(CQ_Q0 + 5) * T::CBS + i] = q[6];
+        cb[(CQ_Q0 + 6) * T::CBS + i] = q[7];
+        cb[CQ_V1 * T::CBS + i] = o.v1;
+        cb[CQ_V2 * T::CBS + i] = o.v2;
+        cb[CQ_V3 * T::CBS + i] = o.v3;
+        cb[CQ_B1 * T::CBS + i] = q[4];
+        cb[CQ_LF * T::CBS + i] = o.lf;
+        cb[CQ_LA * T::CBS + i] = o.la;
+        cb[CQ_LS * T::CBS + i] = o.ls;
+    }
+}
+
+// phase 1: numerical flux of every face of the tile (compute_eigenvectors_E_vec + weno5_interpolation,
+// Weno5_2D.jl:1250-1531, :1795-1895, through the structured forms of weno5_math.cuh) and the two transport fluxes
+template <int DIR>
+W5_HD void sweep_faces(const SweepArgs &a, int bx, int by, int bz, int tid, double *smem)
+{
+    using T = SweepGeo<DIR>;
+    const SweepPos<DIR> P(a.d, bx, by, bz);
+    const double *cb = smem;
+    double *fb = smem + CQ_COUNT * T::CBS;
+    for (int idx = tid; idx < T::NFACES; idx += NT3) {
+        int fs, l;
+        T::face_decode(idx, fs, l);
+        const int f = P.f0 + fs;
+        if (f > P.n - 3 || !P.line_ok(l)) continue;
+        const int iL = T::cell_slot(fs + 2, l), iR = T::cell_slot(fs + 3, l);
+        FaceCoef fc;
+        face_coefficients(cb[CQ_Q0 * T::CBS + iL], cb[CQ_Q0 * T::CBS + iR], cb[CQ_V1 * T::CBS + iL], cb[CQ_V1 * T::CBS + iR],
+                          cb[CQ_V2 * T::CBS + iL], cb[CQ_V2 * T::CBS + iR], cb[CQ_V3 * T::CBS + iL], cb[CQ_V3 * T::CBS + iR],
+                          cb[CQ_B1 * T::CBS + iL], cb[CQ_B1 * T::CBS + iR], cb[(CQ_Q0 + 4) * T::CBS + iL],
+                          cb[(CQ_Q0 + 4) * T::CBS + iR], cb[(CQ_Q0 + 5) * T::CBS + iL], cb[(CQ_Q0 + 5) * T::CBS + iR],
+                          cb[(CQ_Q0 + 6) * T::CBS + iL], cb[(CQ_Q0 + 6) * T::CBS + iR], a.gam, a.g2, fc);
+        double amax[7];
+        face_amax(cb[CQ_V1 * T::CBS + iL], cb[CQ_LF * T::CBS + iL], cb[CQ_LA * T::CBS + iL], cb[CQ_LS * T::CBS + iL],
+                  cb[CQ_V1 * T::CBS + iR], cb[CQ_LF * T::CBS + iR], cb[CQ_LA * T::CBS + iR], cb[CQ_LS * T::CBS + iR], amax);
+        auto load = [&](int k, double F[7], double x[7]) {
+            const int ii = T::cell_slot(fs + k, l);
+#pragma unroll
+            for (int m = 0; m < 7; ++m) {
+                F[m] = cb[(CQ_F0 + m) * T::CBS + ii];
+                x[m] = cb[(CQ_Q0 + m) * T::CBS + ii];
+            }
+        };
+        double fh[7], Fs[7];
+        RegStash st;
+        BackCoef bc;
+        split_back(fc, bc);
+        face_flux(fc, amax, a.eps, load, st, Fs);
+        back_project(bc, Fs, fh);
+        const int io = T::face_slot(fs, l);
+        fb[0 * T::FBS + io] = fh[0];
+        fb[1 * T::FBS + io] = fh[1];
+        fb[2 * T::FBS + io] = fh[2];
+        fb[3 * T::FBS + io] = fh[3];
+        fb[4 * T::FBS + io] = fh[6];
+        // transport fluxes (Weno5_2D.jl:1005-1008): the advective part of the induction flux, upwinded
+        const double bv2 = cb[CQ_B1 * T::CBS + iL] * cb[CQ_V2 * T::CBS + iL] + cb[CQ_B1 * T::CBS + iR] * cb[CQ_V2 * T::CBS + iR];
+        const double bv3 = cb[CQ_B1 * T::CBS + iL] * cb[CQ_V3 * T::CBS + iL] + cb[CQ_B1 * T::CBS + iR] * cb[CQ_V3 * T::CBS + iR];
+        const size_t g = P.gidx(a.d, f, l);
+        a.bsA[g] = fma(0.5, bv2, fh[4]);
+        a.bsB[g] = fma(0.5, bv3, fh[5]);
+    }
+}
+
+// phase 2: flux difference of the cells whose two faces the tile holds (Weno5_2D.jl:993-1003)
+template <int DIR>
+W5_HD void sweep_update(const SweepArgs &a, int bx, int by, int bz, int tid, const double *smem)
+{
+    using T = SweepGeo<DIR>;
+    const SweepPos<DIR> P(a.d, bx, by, bz);
+    const double *fb = smem + CQ_COUNT * T::CBS;
+    for (int idx = tid; idx < T::NFACES; idx += NT3) {
+        int fs, l;
+        T::face_decode(idx, fs, l);
+        const int c = P.f0 + fs;                       // cell c: faces c-1 (slot fs-1) and c (slot fs)
+        if (fs == 0 || c > P.n - NB3 - 1 || !P.line_ok(l) || !P.line_interior(l)) continue;
+        const int i0 = T::face_slot(fs - 1, l), i1 = T::face_slot(fs, l);
+        const size_t g = P.gidx(a.d, c, l);
+#pragma unroll
+        for (int m = 0; m < 5; ++m) {
+            const double dfl = (fb[m * T::FBS + i1] - fb[m * T::FBS + i0]) * a.inv_h;
+            double *r = a.rhs[sweep_out(DIR, m)];
+            if (DIR == 0) r[g] = dfl; else r[g] += dfl;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ constrained transport
+struct CtArgs3 {
+    const double *fl[6];       // f_y, f_z, g_z, g_x, h_x, h_y (as written by the sweeps: no ghost fill)
+    double *O[3];              // Ox, Oy, Oz
+    const double *b0[3], *b1[3], *b2[3], *b3[3];   // face fields of the step input and of stages 1-3
+    double *bn[3];             // face fields written by this stage
+    const double *dtp;
+    Dims d;
+    double c;                  // stage coefficient 1/2, 1/2, 1, 1/6
+    double idx_, idy_, idz_;   // 1/dx, 1/dy, 1/dz
+    int stage;
+};
+
+// corner_fluxes (Weno5_2D.jl:319-342) in 3-D: the three EMFs on the edges of cell (i,j,k); zero outside 1 .. N-2
+W5_HD void emf_cell(const CtArgs3 &a, int i, int j, int k)
+{
+    const Dims &d = a.d;
+    const size_t g = vidx(d, i, j, k);
+    const bool inner = i >= 1 && i < d.Nx - 1 && j >= 1 && j < d.Ny - 1 && k >= 1 && k < d.Nz - 1;
+    double ox = 0.0, oy = 0.0, oz = 0.0;
+    if (inner) {
+        const double *fy = a.fl[0], *fz = a.fl[1], *gz = a.fl[2], *gx = a.fl[3], *hx = a.fl[4], *hy = a.fl[5];
+        ox = 0.5 * (flux_at(hy, d, i, j, k) + flux_at(hy, d, i, j + 1, k) - flux_at(gz, d, i, j, k) - flux_at(gz, d, i, j, k + 1));
+        oy = 0.5 * (flux_at(fz, d, i, j, k) + flux_at(fz, d, i, j, k + 1) - flux_at(hx, d, i, j, k) - flux_at(hx, d, i + 1, j, k));
+        oz = 0.5 * (flux_at(gx, d, i, j, k) + flux_at(gx, d, i + 1, j, k) - flux_at(fy, d, i, j, k) - flux_at(fy, d, i, j + 1, k));
+    }
+    a.O[0][g] = ox; a.O[1][g] = oy; a.O[2][g] = oz;
+}
+
+// face-field RK update (Weno5_2D.jl:150-151, :195-196, :240-241, :284-285 with the stage-4 combination :279-281)
+W5_HD void face_update_cell(const CtArgs3 &a, double dt, int i, int j, int k)
+{
+    const Dims &d = a.d;
+    const size_t g = vidx(d, i, j, k);
+    const bool inner = i >= 1 && i < d.Nx - 1 && j >= 1 && j < d.Ny - 1 && k >= 1 && k < d.Nz - 1;
+    const double ox = a.O[0][g], oy = a.O[1][g], oz = a.O[2][g];
+    const double ox_j = inner ? a.O[0][vidx(d, i, j - 1, k)] : 0.0, ox_k = inner ? a.O[0][vidx(d, i, j, k - 1)] : 0.0;
+    const double oy_i = inner ? a.O[1][vidx(d, i - 1, j, k)] : 0.0, oy_k = inner ? a.O[1][vidx(d, i, j, k - 1)] : 0.0;
+    const double oz_i = inner ? a.O[2][vidx(d, i - 1, j, k)] : 0.0, oz_j = inner ? a.O[2][vidx(d, i, j - 1, k)] : 0.0;
+    double bb[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+        bb[m] = a.stage < 4 ? a.b0[m][g] : 1.0 / 3 * (-a.b0[m][g] + a.b1[m][g] + 2 * a.b2[m][g] + a.b3[m][g]);
+    const double cx = a.c * dt * a.idx_, cy = a.c * dt * a.idy_, cz = a.c * dt * a.idz_;
+    a.bn[0][g] = bb[0] - cy * (oz - oz_j) + cz * (oy - oy_k);
+    a.bn[1][g] = bb[1] - cz * (ox - ox_k) + cx * (oz - oz_i);
+    a.bn[2][g] = bb[2] - cx * (oy - oy_i) + cy * (ox - ox_j);
+}
+
+// boundaries! on a face array, in place: every location the rules write reads the location they copy (or 0)
+W5_HD bool face_is_ghost(const Dims &d, int i, int j, int k)
+{
+    const int c[3] = {i, j, k};
+    bool gh = false;
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+        const int N = dimN(d, ax);
+        gh = gh || (d.bc[ax] == 1 ? (c[ax] < NB3 || c[ax] > N - NB3 - 1) : (c[ax] < 2 || c[ax] > N - 3));
+    }
+    return gh;
+}
+W5_HD void face_bc_cell(double *f, const Dims &d, int i, int j, int k)
+{
+    if (face_is_ghost(d, i, j, k)) f[vidx(d, i, j, k)] = flux_at(f, d, i, j, k);
+}
+
+// ------------------------------------------------------------------ cell update of one stage
+struct UpdArgs3 {
+    const double *q0[9], *q1[9], *q2[9], *q3[9];   // step input and stages 1-3 (public component order, 7 = S, 8 = E)
+    const double *rhs[5];
+    const double *bn[3];       // this stage's face fields
+    double *qn[9];
+    const double *dtp;
+    Dims d;
+    double c, gam;
+    int stage, roundtrip;
+};
+
+// RK combination of rho, M, E (Weno5_2D.jl:139-146 ... :279), interpolateB_face2center (:344-356) for all three field
+// components, and what survives of ES_Switch (:1734-1768): S = E2S(q), E = S2E(q) when the round trip is on
+W5_HD void update_cell(const UpdArgs3 &a, double dt, int i, int j, int k)
+{
+    const Dims &d = a.d;
+    const size_t g = vidx(d, i, j, k);
+    const int comp[5] = {0, 1, 2, 3, 8};
+    double v[5];
+    const double cdt = a.c * dt;
+#pragma unroll
+    for (int m = 0; m < 5; ++m) {
+        const int c = comp[m];
+        const double b = a.stage < 4 ? a.q0[c][g] : 1.0 / 3 * (-a.q0[c][g] + a.q1[c][g] + 2 * a.q2[c][g] + a.q3[c][g]);
+        v[m] = b - cdt * a.rhs[m][g];
+    }
+    const double *x = a.bn[0], *y = a.bn[1], *z = a.bn[2];
+    const double Bx = (-x[vidx(d, i - 2, j, k)] + 9.0 * x[vidx(d, i - 1, j, k)] + 9.0 * x[g] - x[vidx(d, i + 1, j, k)]) / 16.0;
+    const double By = (-y[vidx(d, i, j - 2, k)] + 9.0 * y[vidx(d, i, j - 1, k)] + 9.0 * y[g] - y[vidx(d, i, j + 1, k)]) / 16.0;
+    const double Bz = (-z[vidx(d, i, j, k - 2)] + 9.0 * z[vidx(d, i, j, k - 1)] + 9.0 * z[g] - z[vidx(d, i, j, k + 1)]) / 16.0;
+    double S, E2;
+    e2s_s2e(v[0], v[1], v[2], v[3], Bx, By, Bz, v[4], a.gam, S, E2);
+    a.qn[0][g] = v[0]; a.qn[1][g] = v[1]; a.qn[2][g] = v[2]; a.qn[3][g] = v[3];
+    a.qn[4][g] = Bx; a.qn[5][g] = By; a.qn[6][g] = Bz;
+    a.qn[7][g] = S;
+    a.qn[8][g] = a.roundtrip ? E2 : v[4];
+}
+
+// boundaries!(q) in place: a ghost cell reads the interior cell the rules map it to (interior cells are not written)
+W5_HD void cell_bc(double *f, const Dims &d, int i, int j, int k)
+{
+    const int si = map_cell(i, d.Nx, d.bc[0]), sj = map_cell(j, d.Ny, d.bc[1]), sk = map_cell(k, d.Nz, d.bc[2]);
+    if (si != i || sj != j || sk != k) f[vidx(d, i, j, k)] = f[vidx(d, si, sj, sk)];
+}
+
+// ------------------------------------------------------------------ CFL, diagnostics, start-up
+// compute_global_vmax (Weno5_2D.jl:1942-1984: x-face averages, pressure from S) with a third direction
+W5_HD void vmax_cell(const double *const q[9], const Dims &d, double gam, int i, int j, int k, double v[3])
+{
+    const size_t a = vidx(d, i, j, k), b = a + 1;
+    const double rho = (q[0][a] + q[0][b]) / 2;
+    const double ri = fast_rcp(rho);
+    const double vx = (q[1][a] + q[1][b]) / 2 * ri, vy = (q[2][a] + q[2][b]) / 2 * ri, vz = (q[3][a] + q[3][b]) / 2 * ri;
+    const double Bx = (q[4][a] + q[4][b]) / 2, By = (q[5][a] + q[5][b]) / 2, Bz = (q[6][a] + q[6][b]) / 2;
+    const double S = (q[7][a] + q[7][b]) / 2;
+    const double pres = S * pow_gm1(rho, gam);
+    const double cs2 = gam * fabs(pres * ri);
+    const double bbn2 = (Bx * Bx + By * By + Bz * Bz) * ri;
+    const double sm = bbn2 + cs2;
+    const double rx = fast_sqrt(fmax(0.0, sm * sm - 4 * (Bx * Bx * ri) * cs2));
+    const double ry = fast_sqrt(fmax(0.0, sm * sm - 4 * (By * By * ri) * cs2));
+    const double rz = fast_sqrt(fmax(0.0, sm * sm - 4 * (Bz * Bz * ri) * cs2));
+    v[0] = fabs(vx) + fast_sqrt(0.5 * (sm + rx));
+    v[1] = fabs(vy) + fast_sqrt(0.5 * (sm + ry));
+    v[2] = fabs(vz) + fast_sqrt(0.5 * (sm + rz));
+    if (sm != sm) { v[0] = sm; v[1] = sm; v[2] = sm; }
+}
+
+// ctl[0]=dt ctl[1]=t ctl[2..4]=vmax ctl[5]=tmax ctl[6]=steps done ctl[7]=bad flag
+W5_HD void dt_from_vmax(const double vm[3], double *ctl, double dx, double dy, double dz, double cfl)
+{
+    const double t = ctl[1], tmax = ctl[5];
+    if (tmax > 0.0 && t >= tmax) { ctl[0] = 0.0; return; }
+    ctl[2] = vm[0]; ctl[3] = vm[1]; ctl[4] = vm[2];
+    double dt = cfl / (vm[0] / dx + vm[1] / dy + vm[2] / dz);       // timestep(), Weno5_2D.jl:1930-1940, three terms
+    if (!(dt > 0.0) || !(dt < 1e300)) { ctl[7] = 1.0; dt = 0.0; }
+    if (tmax > 0.0 && t + dt > tmax) dt = tmax - t;
+    ctl[0] = dt;
+}
+
+// compute_divB (Weno5_2D.jl:1986-1999) with the z term
+W5_HD void divb_cell(const double *bx, const double *by, const double *bz, double *out, const Dims &d, double idx_,
+                     double idy_, double idz_, int i, int j, int k)
+{
+    const size_t g = vidx(d, i, j, k);
+    const bool in = i >= 2 && i <= d.Nx - 4 && j >= 2 && j <= d.Ny - 4 && k >= 2 && k <= d.Nz - 4;
+    out[g] = in ? (bx[g] - bx[vidx(d, i - 1, j, k)]) * idx_ + (by[g] - by[vidx(d, i, j - 1, k)]) * idy_ +
+                      (bz[g] - bz[vidx(d, i, j, k - 1)]) * idz_
+                : 0.0;
+}
+
+// interpolateB_center2face (Weno5_2D.jl:1669-1682) with the z face field; 0 where the reference leaves it
+W5_HD void center2face_cell(const double *Bx, const double *By, const double *Bz, double *bx, double *by, double *bz,
+                            const Dims &d, int i, int j, int k)
+{
+    const size_t g = vidx(d, i, j, k);
+    const bool in = i >= 1 && i <= d.Nx - 3 && j >= 1 && j <= d.Ny - 3 && k >= 1 && k <= d.Nz - 3;
+    if (!in) { bx[g] = 0.0; by[g] = 0.0; bz[g] = 0.0; return; }
+    bx[g] = (-Bx[vidx(d, i - 1, j, k)] + 9 * Bx[g] + 9 * Bx[vidx(d, i + 1, j, k)] - Bx[vidx(d, i + 2, j, k)]) / 16;
+    by[g] = (-By[vidx(d, i, j - 1, k)] + 9 * By[g] + 9 * By[vidx(d, i, j + 1, k)] - By[vidx(d, i, j + 2, k)]) / 16;
+    bz[g] = (-Bz[vidx(d, i, j, k - 1)] + 9 * Bz[g] + 9 * Bz[vidx(d, i, j, k + 1)] - Bz[vidx(d, i, j, k + 2)]) / 16;
+}
+
+// ------------------------------------------------------------------ the step, written once for device and host
+// Buffers of one solver (device memory in the product, host memory in tests/hostmath/host3d.cpp)
+struct Bufs3 {
+    Dims d;
+    double dx, dy, dz, gam, eps, cfl;
+    int roundtrip;
+    double *Q[4][9];           // Q[0]: step input and result; Q[1..3]: stages 1-3
+    double *B[4][3];           // face fields, same roles
+    double *rhs[5], *fl[6], *O[3];
+    double *ctl;               // 8 doubles, see dt_from_vmax
+};
+
+// Exec provides: sweep<DIR>(SweepArgs), emf(CtArgs3), face_update(CtArgs3), update(UpdArgs3), cell_bc(double *const v[], n, Dims),
+// face_bc(double *const v[3], Dims); each returns when the work is enqueued (device) or done (host)
+template <class Exec>
+void enqueue_stage3(const Bufs3 &b, Exec &ex, int stage)
+{
+    static const double coef[5] = {0.0, 0.5, 0.5, 1.0, 1.0 / 6};
+    double *const *src = b.Q[stage - 1];
+    double *const *dst = b.Q[stage & 3];                 // stage 4 writes the result over the step input
+    SweepArgs s;
+    for (int c = 0; c < 7; ++c) s.q[c] = src[c];
+    s.q[7] = src[8];
+    for (int m = 0; m < 5; ++m) s.rhs[m] = b.rhs[m];
+    s.dtp = b.ctl; s.d = b.d; s.gam = b.gam; s.eps = b.eps; s.g2 = (b.gam - 2.0) / (b.gam - 1.0);
+    s.bsA = b.fl[0]; s.bsB = b.fl[1]; s.inv_h = 1.0 / b.dx; ex.template sweep<0>(s);
+    s.bsA = b.fl[2]; s.bsB = b.fl[3]; s.inv_h = 1.0 / b.dy; ex.template sweep<1>(s);
+    s.bsA = b.fl[4]; s.bsB = b.fl[5]; s.inv_h = 1.0 / b.dz; ex.template sweep<2>(s);
+
+    CtArgs3 ct;
+    for (int m = 0; m < 6; ++m) ct.fl[m] = b.fl[m];
+    for (int m = 0; m < 3; ++m) {
+        ct.O[m] = b.O[m];
+        ct.b0[m] = b.B[0][m]; ct.b1[m] = b.B[1][m]; ct.b2[m] = b.B[2][m]; ct.b3[m] = b.B[3][m];
+        ct.bn[m] = b.B[stage & 3][m];
+    }
+    ct.dtp = b.ctl; ct.d = b.d; ct.c = coef[stage]; ct.stage = stage;
+    ct.idx_ = 1.0 / b.dx; ct.idy_ = 1.0 / b.dy; ct.idz_ = 1.0 / b.dz;
+    ex.emf(ct);
+    ex.face_update(ct);
+
+    UpdArgs3 u;
+    for (int c = 0; c < 9; ++c) { u.q0[c] = b.Q[0][c]; u.q1[c] = b.Q[1][c]; u.q2[c] = b.Q[2][c]; u.q3[c] = b.Q[3][c]; u.qn[c] = dst[c]; }
+    for (int m = 0; m < 5; ++m) u.rhs[m] = b.rhs[m];
+    for (int m = 0; m < 3; ++m) u.bn[m] = b.B[stage & 3][m];
+    u.dtp = b.ctl; u.d = b.d; u.c = coef[stage]; u.gam = b.gam; u.stage = stage; u.roundtrip = b.roundtrip;
+    ex.update(u);
+    ex.cell_bc(dst, 9, b.d);
+    if (stage == 4) ex.face_bc(b.B[0], b.d);              // Weno5_2D.jl:313
+}
+
+template <class Exec>
+void enqueue_step3(const Bufs3 &b, Exec &ex)
+{
+    for (int stage = 1; stage <= 4; ++stage) enqueue_stage3(b, ex, stage);
+}
+
+}  // namespace d3
+}  // namespace w5

@@ -41,6 +41,9 @@ static int fail(int code, const char *fmt, ...)
     return code;
 }
 
+// error text for the other translation units of the library (weno5_3d.cu)
+namespace w5 { int api_fail(int code, const char *msg) { return fail(code, "%s", msg); } }
+
 #define CU(call)                                                                                   \
     do {                                                                                           \
         cudaError_t e_ = (call);                                                                   \

@@ -30,6 +30,13 @@ class Params(C.Structure):
                 ("bc_x", C.c_int), ("bc_y", C.c_int), ("es_roundtrip", C.c_int)]
 
 
+class Params3D(C.Structure):
+    """weno5_params3d -- the same constants for the 3-D extension."""
+    _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("dx", C.c_double), ("dy", C.c_double),
+                ("dz", C.c_double), ("gamma", C.c_double), ("cfl", C.c_double), ("eps", C.c_double),
+                ("bc_x", C.c_int), ("bc_y", C.c_int), ("bc_z", C.c_int), ("es_roundtrip", C.c_int)]
+
+
 _dp = C.POINTER(C.c_double)
 _vp = C.c_void_p
 
@@ -57,6 +64,19 @@ SIGNATURES = {
     "weno5_es_switch_count": (C.c_int, [_vp, C.POINTER(C.c_ulonglong)]),
     "weno5_es_switch_mask": (C.c_int, [_vp, _dp]),
     "weno5_arr2img": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_short), _dp]),
+    "weno5_create_3d": (C.c_int, [C.POINTER(Params3D), C.c_int, C.POINTER(_vp)]),
+    "weno5_destroy_3d": (C.c_int, [_vp]),
+    "weno5_upload_3d": (C.c_int, [_vp, _dp, _dp, _dp, _dp]),
+    "weno5_download_3d": (C.c_int, [_vp, _dp, _dp, _dp, _dp]),
+    "weno5_timestep_3d": (C.c_int, [_vp, _dp, _dp]),
+    "weno5_rk4_step_3d": (C.c_int, [_vp, C.c_double]),
+    "weno5_advance_3d": (C.c_int, [_vp, C.c_int, C.c_double, _dp, C.POINTER(C.c_int)]),
+    "weno5_divb_3d": (C.c_int, [_vp, _dp]),
+    "weno5_totals_3d": (C.c_int, [_vp, _dp]),
+    "weno5_classical_rk4_step_3d": (C.c_int, [C.POINTER(Params3D), _dp, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp, _dp]),
+    "weno5_launch_count_3d": (C.c_ulonglong, [_vp]),
+    "weno5_profile_3d": (C.c_int, [_vp, C.c_int]),
+    "weno5_profile_read_3d": (C.c_int, [_vp, _dp, C.POINTER(C.c_ulonglong)]),
     "weno5_classical_rk4_step_2d": (C.c_int, [C.POINTER(Params), _dp, _dp, _dp, C.c_double, _dp, _dp, _dp]),
     "weno5_classical_rk4_step_1d": (C.c_int, [C.POINTER(Params), _dp, C.c_double, _dp]),
     "weno5_step_host": (C.c_int, [_vp, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp]),

@@ -1,0 +1,136 @@
+"""
+GPU parity tests of the 3-D extension, through the C ABI (weno5_*_3d).  The reference has no 3-D code;
+the 3-D step is pinned to its 2-D step by reduction (a state uniform along one axis, in all three orientations) and
+compared with the 3-D oracle (itself pinned the same way, tests/test_oracle3d.py) on states that depend on all three
+coordinates, for every mix of boundary conditions and on grids whose lines cross CTA-tile boundaries.
+"""
+import numpy as np
+import pytest
+
+from julia_b200 import problems as pr
+from julia_b200 import problems3d as p3
+from julia_b200.solver3d import Solver3D, classical_RK4_step_3d
+from oracle import oracle_c as O
+
+pytestmark = pytest.mark.gpu
+I = slice(3, -3)
+
+
+def compare(got, want, tol):
+    assert np.isfinite(got[0]).all()
+    for c in range(9):
+        s = max(np.abs(want[0][..., c]).max(), 1.0)
+        assert np.abs(got[0][..., c] - want[0][..., c]).max() <= tol * s, c
+    for a, b in zip(got[1:], want[1:]):
+        assert np.abs(a - b).max() <= tol * max(np.abs(b).max(), 1.0)
+
+
+@pytest.mark.parametrize("shape", [(70, 5, 4), (5, 36, 4), (4, 5, 36), (40, 37, 35)])
+@pytest.mark.parametrize("bc", [(1, 1, 1), (0, 0, 0), (1, 0, 1), (0, 1, 0)])
+def test_step_matches_oracle_all_cells(built, shape, bc):
+    """one RK4 step on a smooth state, every cell and every face value including the ghost layers"""
+    g, q, bx, by, bz = p3.smooth_3d(*shape, seed=sum(shape) + bc[0])
+    g.bc_x, g.bc_y, g.bc_z = bc
+    q, bx, by, bz = (np.asfortranarray(a.copy()) for a in (q, bx, by, bz))
+    O.boundaries_3d(g, q, bx, by, bz)
+    with Solver3D(g) as s:
+        s.upload(q, bx, by, bz)
+        dt, vm = s.timestep()
+        dto, vmo = O.timestep_3d(g, q)
+        assert abs(dt - dto) <= 1e-12 * dto and np.allclose(vm, vmo, rtol=1e-12, atol=0)
+        s.rk4_step(0.8 * dto)
+        got = s.download()
+    want = O.rk4_step_3d(g, q, bx, by, bz, 0.8 * dto)
+    compare(got, want, 1e-11)
+
+
+@pytest.mark.parametrize("orientation", [0, 1, 2])
+def test_reduces_to_the_2d_step_in_every_orientation(built, orientation):
+    """uniform along one axis: the 3-D step must return the 2-D step of the same library (the path pinned against the
+    reference) and of the 2-D oracle, whichever two axes carry the problem"""
+    from julia_b200.solver import Solver
+    g2, q, bx, by = pr.orszag_tang(96, ny=64, ysize=2.0 / 3.0)
+    with Solver(g2) as s2:
+        s2.upload(q, bx, by)
+        dt = s2.timestep()[0]
+        s2.rk4_step(dt)
+        q2, bx2, by2 = s2.download()
+    qo, bxo, byo = O.rk4_step_2d(g2, q, bx, by, dt, fast=True)
+    g, q3, b0, b1, b2 = p3.embed_2d(g2, q, bx, by, orientation, n3=5)
+    got = classical_RK4_step_3d(g, q3, b0, b1, b2, dt)
+    for ref_q, ref_bx, ref_by, tol in ((q2, bx2, by2, 1e-12), (qo, bxo, byo, 1e-9)):   # oracle: degenerate faces, DESIGN 6
+        for idx in (3, 5, 7):
+            for c in (0, 7, 8):
+                a = p3.extract_2d(got[0][..., c], orientation, idx)
+                assert np.abs(a[I, I] - ref_q[I, I, c]).max() <= tol * np.abs(ref_q[..., c]).max()
+            for base in ([1, 2, 3], [4, 5, 6]):
+                for m2 in range(3):
+                    a = p3.extract_2d(got[0][..., base[p3.vector_component(orientation, m2)]], orientation, idx)
+                    assert np.abs(a[I, I] - ref_q[I, I, base[m2]]).max() <= tol
+            for ax, ref in ((orientation % 3, ref_bx), ((orientation + 1) % 3, ref_by)):
+                assert np.abs(p3.extract_2d(got[1 + ax], orientation, idx)[I, I] - ref[I, I]).max() <= tol
+
+
+def test_advance_conserves_and_keeps_divb_zero(built):
+    """the device-resident driver loop on the 3-D Orszag-Tang vortex: conservation and div B to round-off, agreement
+    with the oracle's loop in L1 (degenerate faces: L1 as north_star prescribes for non-smooth problems)"""
+    g, q, bx, by, bz = p3.orszag_tang_3d(48, nz=40)
+    with Solver3D(g) as s:
+        s.upload(q, bx, by, bz)
+        s0 = s.totals()
+        t, n = s.advance(6)
+        assert n == 6 and t > 0
+        s1 = s.totals()
+        divb = s.divb()
+        got = s.download()
+        nl = s.launch_count()
+    assert nl > 6 * 4 * 8
+    scale = np.abs(q[I, I, I]).reshape(-1, 9).sum(axis=0)
+    for c in (0, 1, 2, 3, 8):
+        assert abs(s1[c] - s0[c]) <= 1e-12 * scale[c], c
+    for m in range(3):
+        assert abs(s1[9 + m] - s0[9 + m]) <= 1e-12 * max(np.abs((bx, by, bz)[m][I, I, I]).sum(), 1.0)
+    assert np.abs(divb[I, I, I]).max() <= 1e-12 * np.abs(q[..., 4:7]).max() / g.dx
+    qo, bxo, byo, bzo, to = O.advance_3d(g, q, bx, by, bz, 6, fast=True)
+    assert abs(t - to) <= 1e-11 * to
+    for c in range(9):
+        l1 = np.abs(got[0][I, I, I, c] - qo[I, I, I, c]).sum() / max(np.abs(qo[I, I, I, c]).sum(), 1e-300)
+        assert l1 <= 1e-8, (c, l1)
+
+
+def test_blast_3d_outflow_and_tmax(built):
+    g, q, bx, by, bz = p3.blast_3d(32, bc=pr.OUTFLOW)
+    with Solver3D(g, es_roundtrip=False) as s:
+        s.upload(q)                                   # face fields derived on the device (interpolateB_center2face)
+        t, n = s.advance(1000, tmax=0.004)
+        assert abs(t - 0.004) < 1e-15 and 0 < n < 1000
+        got = s.download()
+    f = O.center2face_3d(g, q)
+    O.boundaries_3d(g, None, *f)
+    want = (q, *f)
+    tt, steps = 0.0, 0
+    while tt < 0.004:
+        dt = min(O.timestep_3d(g, want[0], fast=True)[0], 0.004 - tt)
+        want = O.rk4_step_3d(g, *want, dt, roundtrip=False, fast=True)
+        tt += dt
+        steps += 1
+    assert steps == n
+    for c in range(9):
+        l1 = np.abs(got[0][I, I, I, c] - want[0][I, I, I, c]).sum() / max(np.abs(want[0][I, I, I, c]).sum(), 1e-300)
+        assert l1 <= 1e-9, (c, l1)
+
+
+def test_argument_validation_3d(built):
+    import ctypes as C
+    from julia_b200 import lib as L
+    lib = L.load()
+    h = C.c_void_p()
+    bad = L.Params3D(3, 8, 8, 0.1, 0.1, 0.1, 5 / 3, 0.8, 1e-6, 1, 1, 1, 1)
+    assert lib.weno5_create_3d(C.byref(bad), 0, C.byref(h)) == L.ERR_ARG
+    bad = L.Params3D(8, 8, 8, 0.1, 0.1, 0.1, 5 / 3, 0.8, 1e-6, 1, 5, 1, 1)
+    assert lib.weno5_create_3d(C.byref(bad), 0, C.byref(h)) == L.ERR_ARG
+    assert lib.weno5_rk4_step_3d(None, 0.1) == L.ERR_ARG
+    g, q, bx, by, bz = p3.smooth_3d(8, 8, 8)
+    with Solver3D(g) as s:
+        with pytest.raises(L.Weno5Error):
+            s.rk4_step(0.1)                            # no state uploaded
