@@ -172,9 +172,10 @@ int weno5_totals_3d(weno5_ctx3d *ctx, double sums[12]);
 int weno5_classical_rk4_step_3d(const weno5_params3d *params, const double *q0, const double *bxb0, const double *byb0,
                                 const double *bzb0, double dt, double *q4, double *bxb4, double *byb4, double *bzb4);
 unsigned long long weno5_launch_count_3d(const weno5_ctx3d *ctx);
-/* accumulated device time (ms, CUDA events) and count of the sweep kernels since the last read */
+/* accumulated device time (ms, CUDA events) of the x, y and z sweep kernels and their total launch count since the
+ * last read */
 int weno5_profile_3d(weno5_ctx3d *ctx, int enable);
-int weno5_profile_read_3d(weno5_ctx3d *ctx, double *sweep_ms, unsigned long long *sweep_launches);
+int weno5_profile_read_3d(weno5_ctx3d *ctx, double sweep_ms[3], unsigned long long *sweep_launches);
 
 /* ---- one-shot, reference-shaped calls: host arrays in -> host arrays out */
 /* (q4,bxb4,byb4) = classical_RK4_step(q0,bxb0,byb0,dt)   Weno5_2D.jl:125-317 */

@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -55,7 +56,7 @@ struct DevGuard3 {
 
 // ------------------------------------------------------------------ kernels
 template <int DIR>
-__global__ void __launch_bounds__(NT3, 1) sweep3_kernel(const SweepArgs a)
+__global__ void __launch_bounds__(NT3, W5_3D_MINB) sweep3_kernel(const SweepArgs a)
 {
     extern __shared__ double smem3[];
     if (a.dtp[0] == 0.0) return;                           // finished (tmax reached): nothing to do
@@ -64,6 +65,40 @@ __global__ void __launch_bounds__(NT3, 1) sweep3_kernel(const SweepArgs a)
     sweep_faces<DIR>(a, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, smem3);
     __syncthreads();
     sweep_update<DIR>(a, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, smem3);
+}
+
+// y / z sweep with one thread per line (weno5_3d_body.cuh, sweep_march): no barrier, thread-private ring
+template <int DIR>
+__global__ void __launch_bounds__(MarchGeo::NT, 1) sweep3_march_kernel(const SweepArgs a, int nseg)
+{
+    extern __shared__ double smem3[];
+    if (a.dtp[0] == 0.0) return;
+    sweep_march<DIR>(a, nseg, blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, smem3);
+}
+
+// x sweep with LPL lanes per line (weno5_3d_body.cuh, xwarp_*): warp-private ring, __syncwarp between the phases
+template <int LPL>
+__global__ void __launch_bounds__(XWarpGeo<LPL>::NT, 1) sweep3_xwarp_kernel(const SweepArgs a, int nseg)
+{
+    extern __shared__ double smem3[];
+    if (a.dtp[0] == 0.0) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *wsm = smem3 + (size_t)warp * XWarpGeo<LPL>::PER_WARP;
+    const XWarpPos<LPL> P(a.d, nseg, blockIdx.x, blockIdx.y, blockIdx.z, warp, lane);
+    for (int chunk = 0; chunk < P.nchunks; ++chunk) {
+        xwarp_cells<LPL>(a, nseg, blockIdx.x, blockIdx.y, blockIdx.z, warp, lane, chunk, wsm);
+        __syncwarp();
+        xwarp_faces<LPL>(a, nseg, blockIdx.x, blockIdx.y, blockIdx.z, warp, lane, chunk, wsm);
+        __syncwarp();
+        xwarp_update<LPL>(a, nseg, blockIdx.x, blockIdx.y, blockIdx.z, warp, lane, chunk, wsm);
+    }
+}
+
+template <int LPL> void launch_xwarp(const SweepArgs &a, int nseg, cudaStream_t s)
+{
+    int g[3];
+    XWarpGeo<LPL>::grid(a.d, nseg, g);
+    sweep3_xwarp_kernel<LPL><<<dim3(g[0], g[1], g[2]), XWarpGeo<LPL>::NT, XWarpGeo<LPL>::SMEM, s>>>(a, nseg);
 }
 
 // elementwise kernels: one thread per cell of the box [lo, N-lo) in every axis; block (64, 2, 2)
@@ -210,6 +245,13 @@ struct weno5_ctx3d {
     double *sums = nullptr;         // 12 doubles
     unsigned long long *vbits = nullptr;
     bool have_state = false;
+    // sweep kernels: x by sweep3_xwarp_kernel (a warp per line), y and z by sweep3_march_kernel (a thread per line).
+    // WENO5_3D_SWEEP (tuning / cross-checks): tile = the CTA-tile kernel in all directions, xtile = for x only,
+    // xmarch = x by the thread-per-line kernel (uncoalesced)
+    bool xwarp = true;
+    int lpl = 32;                   // lanes per line of the x sweep (8, 16, 32)
+    bool march[3] = {false, true, true};
+    int nseg[3] = {1, 1, 1};        // segments per line of the marching sweeps
     unsigned long long launches = 0;
     // sweep timing (weno5_profile_3d)
     bool profiling = false;
@@ -237,7 +279,16 @@ struct DevExec {
             c->ev_used += 2;
             cudaEventRecord(e0, c->stream);
         }
-        sweep3_kernel<DIR><<<dim3(g[0], g[1], g[2]), NT3, SweepGeo<DIR>::SMEM, c->stream>>>(a);
+        if (DIR == 0 && c->xwarp) {
+            if (c->lpl == 8) launch_xwarp<8>(a, c->nseg[0], c->stream);
+            else if (c->lpl == 16) launch_xwarp<16>(a, c->nseg[0], c->stream);
+            else launch_xwarp<32>(a, c->nseg[0], c->stream);
+        } else if (c->march[DIR]) {
+            MarchGeo::grid(a.d, DIR, c->nseg[DIR], g);
+            sweep3_march_kernel<DIR><<<dim3(g[0], g[1], g[2]), MarchGeo::NT, MarchGeo::SMEM, c->stream>>>(a, c->nseg[DIR]);
+        } else {
+            sweep3_kernel<DIR><<<dim3(g[0], g[1], g[2]), NT3, SweepGeo<DIR>::SMEM, c->stream>>>(a);
+        }
         if (e1) cudaEventRecord(e1, c->stream);
         c->launches++;
     }
@@ -354,6 +405,33 @@ extern "C" int weno5_create_3d(const weno5_params3d *P, int device, weno5_ctx3d 
     CU3(cudaFuncSetAttribute(sweep3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepGeo<0>::SMEM));
     CU3(cudaFuncSetAttribute(sweep3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepGeo<1>::SMEM));
     CU3(cudaFuncSetAttribute(sweep3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SweepGeo<2>::SMEM));
+    CU3(cudaFuncSetAttribute(sweep3_xwarp_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XWarpGeo<8>::SMEM));
+    CU3(cudaFuncSetAttribute(sweep3_xwarp_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XWarpGeo<16>::SMEM));
+    CU3(cudaFuncSetAttribute(sweep3_xwarp_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XWarpGeo<32>::SMEM));
+    CU3(cudaFuncSetAttribute(sweep3_march_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MarchGeo::SMEM));
+    CU3(cudaFuncSetAttribute(sweep3_march_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MarchGeo::SMEM));
+    CU3(cudaFuncSetAttribute(sweep3_march_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MarchGeo::SMEM));
+    {
+        const char *e = getenv("WENO5_3D_SWEEP");
+        const bool tile = e && strcmp(e, "tile") == 0, xtile = e && strcmp(e, "xtile") == 0;
+        const bool xmarch = e && strcmp(e, "xmarch") == 0;
+        c->xwarp = !(tile || xtile || xmarch);
+        c->march[0] = xmarch;
+        c->march[1] = c->march[2] = !tile;
+        const char *ns = getenv("WENO5_3D_NSEG");                         // tuning knob: segments per line
+        for (int dir = 0; dir < 3; ++dir) {
+            c->nseg[dir] = ns ? atoi(ns) : MarchGeo::segments(b.d, dir, prop.multiProcessorCount);
+            if (c->nseg[dir] < 1) c->nseg[dir] = 1;
+        }
+        if (c->xwarp) {
+            int nsx, lpl;
+            xwarp_plan(b.d, prop.multiProcessorCount, nsx, lpl);
+            if (!ns) c->nseg[0] = nsx;
+            const char *le = getenv("WENO5_3D_LPL");                      // tuning knob: lanes per line of the x sweep
+            c->lpl = le ? atoi(le) : lpl;
+            if (c->lpl != 8 && c->lpl != 16) c->lpl = 32;
+        }
+    }
     cleanup.c = nullptr;
     *out = c;
     return WENO5_OK;
@@ -526,17 +604,17 @@ extern "C" int weno5_profile_3d(weno5_ctx3d *c, int enable)
     return WENO5_OK;
 }
 
-extern "C" int weno5_profile_read_3d(weno5_ctx3d *c, double *sweep_ms, unsigned long long *sweep_launches)
+extern "C" int weno5_profile_read_3d(weno5_ctx3d *c, double sweep_ms[3], unsigned long long *sweep_launches)
 {
     ENTER3(c);
     CU3(cudaStreamSynchronize(c->stream));
-    double ms = 0.0;
-    for (size_t k = 0; k + 1 < c->ev_used; k += 2) {
+    double ms[3] = {0.0, 0.0, 0.0};
+    for (size_t k = 0; k + 1 < c->ev_used; k += 2) {       // launches are enqueued x, y, z, x, y, z, ...
         float x = 0.f;
         CU3(cudaEventElapsedTime(&x, c->ev[k], c->ev[k + 1]));
-        ms += x;
+        ms[(k / 2) % 3] += x;
     }
-    if (sweep_ms) *sweep_ms = ms;
+    if (sweep_ms) { sweep_ms[0] = ms[0]; sweep_ms[1] = ms[1]; sweep_ms[2] = ms[2]; }
     if (sweep_launches) *sweep_launches = c->ev_used / 2;
     c->ev_used = 0;
     return WENO5_OK;

@@ -27,7 +27,28 @@ namespace w5 {
 namespace d3 {
 
 constexpr int NB3 = 3;
-constexpr int NT3 = 256;                 // threads per CTA of the sweep kernels
+// CTA shape of the sweep kernels (overridable at compile time for tuning runs): threads, faces along the sweep and
+// lines per tile for the x sweep (0) and for the y / z sweeps (1).  Two 128-thread CTAs per SM overlap one CTA's cell
+// phase and barriers with the other's face phase.
+#ifndef W5_3D_NT
+#define W5_3D_NT 128
+#endif
+#ifndef W5_3D_NF0
+#define W5_3D_NF0 123
+#endif
+#ifndef W5_3D_LW0
+#define W5_3D_LW0 1
+#endif
+#ifndef W5_3D_NF1
+#define W5_3D_NF1 32
+#endif
+#ifndef W5_3D_LW1
+#define W5_3D_LW1 8
+#endif
+#ifndef W5_3D_MINB
+#define W5_3D_MINB 2
+#endif
+constexpr int NT3 = W5_3D_NT;            // threads per CTA of the sweep kernels
 
 struct Dims {
     int Nx, Ny, Nz;
@@ -68,6 +89,11 @@ W5_HD double flux_at(const double *f, const Dims &d, int i, int j, int k)
     return f[vidx(d, map_flux(i, d.Nx, d.bc[0]), map_flux(j, d.Ny, d.bc[1]), map_flux(k, d.Nz, d.bc[2]))];
 }
 
+// Lines a sweep has to cover along a lateral axis: the transport fluxes are read one line beyond the interior only
+// where flux_at clamps (outflow); on a periodic axis it wraps into the interior and the ghost lines are never read.
+W5_HD int line_lo(int bc) { return bc == 1 ? NB3 : NB3 - 1; }
+W5_HD int line_count(int N, int bc) { return N - 2 * line_lo(bc); }
+
 // ------------------------------------------------------------------ directional sweep
 // weno5_flux_difference_E (Weno5_2D.jl:973-1018) along axis DIR of the volume, in the frame (DIR, DIR+1, DIR+2).
 struct SweepArgs {
@@ -81,8 +107,8 @@ struct SweepArgs {
 
 // CTA tile: NF faces along the sweep x LW lines; x is always the fastest thread coordinate (coalesced loads)
 template <int DIR> struct SweepGeo {
-    static constexpr int NF = DIR == 0 ? 64 : 32;
-    static constexpr int LW = DIR == 0 ? 4 : 16;
+    static constexpr int NF = DIR == 0 ? W5_3D_NF0 : W5_3D_NF1;
+    static constexpr int LW = DIR == 0 ? W5_3D_LW0 : W5_3D_LW1;
     static constexpr int SW = NF + 5;                  // cells along the sweep: faces f0 .. f0+NF-1 need f0-2 .. f0+NF+2
     static constexpr int NCELLS = SW * LW, NFACES = NF * LW;
     static constexpr int CBS = NCELLS, FBS = NFACES;
@@ -101,12 +127,14 @@ template <int DIR> struct SweepGeo {
     // number of tiles along the sweep: faces 2 .. n-3, a tile advances by NF-1 cells
     W5_HD static int tiles_along(int n) { return (n - 5 + NF - 2) / (NF - 1); }
     // grid: DIR 0: (tiles along x, line groups in j, k);  DIR 1: (line groups in i, tiles along y, k);
-    //       DIR 2: (line groups in i, tiles along z, j);  lines run over 2 .. N-3 (one ghost line each side)
+    //       DIR 2: (line groups in i, tiles along z, j);  lines run over the interior, plus one ghost line each side on
+    //       outflow axes (line_lo)
     W5_HD static void grid(const Dims &d, int g[3])
     {
-        if (DIR == 0) { g[0] = tiles_along(d.Nx); g[1] = (d.Ny - 4 + LW - 1) / LW; g[2] = d.Nz - 4; }
-        if (DIR == 1) { g[0] = (d.Nx - 4 + LW - 1) / LW; g[1] = tiles_along(d.Ny); g[2] = d.Nz - 4; }
-        if (DIR == 2) { g[0] = (d.Nx - 4 + LW - 1) / LW; g[1] = tiles_along(d.Nz); g[2] = d.Ny - 4; }
+        const int cx = line_count(d.Nx, d.bc[0]), cy = line_count(d.Ny, d.bc[1]), cz = line_count(d.Nz, d.bc[2]);
+        if (DIR == 0) { g[0] = tiles_along(d.Nx); g[1] = (cy + LW - 1) / LW; g[2] = cz; }
+        if (DIR == 1) { g[0] = (cx + LW - 1) / LW; g[1] = tiles_along(d.Ny); g[2] = cz; }
+        if (DIR == 2) { g[0] = (cx + LW - 1) / LW; g[1] = tiles_along(d.Nz); g[2] = cy; }
     }
 };
 
@@ -115,14 +143,19 @@ template <int DIR> struct SweepPos {
     int f0, n;            // first face, cells along the sweep
     int l0, p2;           // first lateral coordinate of line 0, second lateral coordinate
     int N1, N2;           // extents of the lateral axes
+    int hi1;              // last line along the first lateral axis
     W5_HD SweepPos(const Dims &d, int bx, int by, int bz)
     {
         using T = SweepGeo<DIR>;
-        if (DIR == 0) { f0 = 2 + bx * (T::NF - 1); l0 = 2 + by * T::LW; p2 = 2 + bz; n = d.Nx; N1 = d.Ny; N2 = d.Nz; }
-        if (DIR == 1) { l0 = 2 + bx * T::LW; f0 = 2 + by * (T::NF - 1); p2 = 2 + bz; n = d.Ny; N1 = d.Nx; N2 = d.Nz; }
-        if (DIR == 2) { l0 = 2 + bx * T::LW; f0 = 2 + by * (T::NF - 1); p2 = 2 + bz; n = d.Nz; N1 = d.Nx; N2 = d.Ny; }
+        const int a1 = DIR == 0 ? 1 : 0, a2 = DIR == 2 ? 1 : 2;          // lateral axes: (y,z), (x,z), (x,y)
+        const int lo1 = line_lo(d.bc[a1]), lo2 = line_lo(d.bc[a2]);
+        n = dimN(d, DIR); N1 = dimN(d, a1); N2 = dimN(d, a2);
+        hi1 = N1 - 1 - lo1;
+        p2 = lo2 + bz;                                                   // <= N2-1-lo2 by the grid size
+        if (DIR == 0) { f0 = 2 + bx * (T::NF - 1); l0 = lo1 + by * T::LW; }
+        else          { l0 = lo1 + bx * T::LW; f0 = 2 + by * (T::NF - 1); }
     }
-    W5_HD bool line_ok(int l) const { return l0 + l <= N1 - 3; }                         // p2 <= N2-3 by the grid size
+    W5_HD bool line_ok(int l) const { return l0 + l <= hi1; }
     W5_HD bool line_interior(int l) const { return l0 + l >= 3 && l0 + l <= N1 - 4 && p2 >= 3 && p2 <= N2 - 4; }
     W5_HD size_t gidx(const Dims &d, int s, int l) const
     {
@@ -261,6 +294,358 @@ W5_HD void sweep_update(const SweepArgs &a, int bx, int by, int bz, int tid, con
             double *r = a.rhs[sweep_out(DIR, m)];
             if (DIR == 0) r[g] = dfl; else r[g] += dfl;
         }
+    }
+}
+
+// ------------------------------------------------------------------ y / z sweep: one thread marches one line
+// In the y and z sweeps the stencil runs across the threads' lines, never along them: a thread that marches along the
+// sweep axis needs nobody else's cells.  So every thread owns one line (x index = lane: coalesced), keeps the last six
+// cells in a private ring in shared memory (thread-interleaved, conflict-free), computes per march step one cell, one
+// face and one flux difference, and carries the previous face's fhat in registers.  No barrier in the kernel, no cell
+// is computed twice and no face but the one two segments share, and the eight warps of an SM drift freely, so the cell
+// and update work of one warp overlaps the face work of another.
+// Per thread: 6 slots x (F[7], q7[7]) + 4 slots x (v1, v2, v3, B1, lf, la, ls) = 112 doubles; 256 threads = 224 KB.
+struct MarchGeo {
+    static constexpr int NT = 256;                     // 32 lines along x  x  8 values of the other lateral axis
+    static constexpr int WARPS = NT / 32;
+    static constexpr int R6 = 14, R4 = 7;
+    static constexpr int PER_THREAD = 6 * R6 + 4 * R4;
+    static constexpr size_t SMEM = (size_t)NT * PER_THREAD * sizeof(double);
+    // lines of a warp run along the lane axis, the warps of a CTA along the row axis: (x, z) for the y sweep, (x, y) for
+    // the z sweep -- lanes along x, every access coalesced -- and (y, z) for the x sweep, where a warp's 32 lines are
+    // Nx apart: its loads and stores touch one 32-byte sector per lane, which the next three march steps use up (L2)
+    W5_HD static int lane_axis(int dir) { return dir == 0 ? 1 : 0; }
+    W5_HD static int row_axis(int dir) { return dir == 2 ? 1 : 2; }
+    // grid: (groups of 32 lines along the lane axis, groups of 8 along the row axis, segments along the sweep)
+    W5_HD static void grid(const Dims &d, int dir, int nseg, int g[3])
+    {
+        const int al = lane_axis(dir), ar = row_axis(dir);
+        g[0] = (line_count(dimN(d, al), d.bc[al]) + 31) / 32;
+        g[1] = (line_count(dimN(d, ar), d.bc[ar]) + WARPS - 1) / WARPS;
+        g[2] = nseg;
+    }
+    // segments per line: the count whose last wave of CTAs is fullest, a segment's prologue (5 cells + the shared
+    // face, ~1.5 march steps) charged against its length
+    static int segments(const Dims &d, int dir, int ctas_per_wave)   // host only
+    {
+        int g[3];
+        grid(d, dir, 1, g);
+        const int base = g[0] * g[1], ni = dimN(d, dir) - 2 * NB3;
+        int best = 1;
+        double best_cost = 1e300;
+        for (int ns = 1; ns <= ni / 8 && ns <= 64; ++ns) {
+            const int per = (ni + ns - 1) / ns;
+            const int used = (ni + per - 1) / per;                       // segments that own cells
+            const long waves = ((long)base * used + ctas_per_wave - 1) / ctas_per_wave;
+            const double cost = (double)waves * (per + 1.5);
+            if (cost < best_cost * (1.0 - 1e-9)) { best_cost = cost; best = ns; }
+        }
+        return best;
+    }
+};
+
+W5_HD void prefetch_l2(const double *p)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
+W5_HD void red_add(double *p, double v)
+{
+#if defined(__CUDA_ARCH__)
+    atomicAdd(p, v);                                   // result unused: a fire-and-forget RED, no load latency in the march
+#else
+    *p += v;
+#endif
+}
+
+template <int DIR>
+W5_HD void sweep_march(const SweepArgs &a, int nseg, int bx, int by, int bz, int tid, double *smem)
+{
+    using M = MarchGeo;
+    const Dims &d = a.d;
+    const int al = M::lane_axis(DIR), ar = M::row_axis(DIR);
+    const int n = dimN(d, DIR), N1 = dimN(d, al), N2 = dimN(d, ar);
+    const int p1 = line_lo(d.bc[al]) + bx * 32 + (tid & 31);
+    const int p2 = line_lo(d.bc[ar]) + by * M::WARPS + (tid >> 5);
+    if (p1 > N1 - 1 - line_lo(d.bc[al]) || p2 > N2 - 1 - line_lo(d.bc[ar])) return;
+    const bool interior = p1 >= NB3 && p1 <= N1 - NB3 - 1 && p2 >= NB3 && p2 <= N2 - NB3 - 1;
+    // segment: cells [cA, cB) of the interior 3 .. n-4; faces cA-1 .. cB-1, and face n-3 where flux_at clamps onto it
+    const int ni = n - 2 * NB3;
+    const int per = (ni + nseg - 1) / nseg;
+    const int cA = NB3 + bz * per, cB = cA + per < n - NB3 ? cA + per : n - NB3;
+    if (cA >= cB) return;
+    const int fA = cA - 1;
+    const int fLast = (cB == n - NB3 && d.bc[DIR] != 1) ? n - NB3 : cB - 1;
+    const size_t sstride = DIR == 0 ? 1 : (DIR == 1 ? (size_t)d.Nx : (size_t)d.Nx * d.Ny);
+    const size_t g0 = DIR == 0 ? vidx(d, 0, p1, p2) : (DIR == 1 ? vidx(d, p1, 0, p2) : vidx(d, p1, p2, 0));   // cell 0 of the line
+    double *r6 = smem + tid;                           // entry e of slot s: r6[(s * R6 + e) * NT]
+    double *r4 = smem + (size_t)6 * M::R6 * M::NT + tid;
+
+    auto line_cell = [&](int c) {                      // stencil cell past the end of the line: quirk Q3
+        if (c >= n) c = d.bc[DIR] == 1 ? c - ni : n - 1;
+        return c >= n ? n - 1 : c;
+    };
+    auto cell_in = [&](int c, int s6, int s4) {
+        const size_t g = g0 + sstride * (size_t)line_cell(c);
+        double q[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) q[k] = a.q[sweep_in(DIR, k)][g];
+        CellOut o;
+        cell_quantities(q, a.gam, o);
+        double *e6 = r6 + (size_t)s6 * M::R6 * M::NT, *e4 = r4 + (size_t)s4 * M::R4 * M::NT;
+#pragma unroll
+        for (int m = 0; m < 7; ++m) e6[m * M::NT] = o.F[m];
+        e6[7 * M::NT] = q[0]; e6[8 * M::NT] = q[1]; e6[9 * M::NT] = q[2]; e6[10 * M::NT] = q[3];
+        e6[11 * M::NT] = q[5]; e6[12 * M::NT] = q[6]; e6[13 * M::NT] = q[7];
+        e4[0] = o.v1; e4[1 * M::NT] = o.v2; e4[2 * M::NT] = o.v3; e4[3 * M::NT] = q[4];
+        e4[4 * M::NT] = o.lf; e4[5 * M::NT] = o.la; e4[6 * M::NT] = o.ls;
+    };
+
+    // cell c lives in ring slot (c - (fA-2)) mod 6 and face-only slot (c - (fA-2)) mod 4
+    for (int c = 0; c < 5; ++c) cell_in(fA - 2 + c, c, c & 3);          // prologue: cells fA-2 .. fA+2
+    int b6 = 0, b4 = 2;                                // slot of cell f-2; face-only slot of cell f
+    double fprev[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int f = fA; f <= fLast; ++f) {
+        {
+            const size_t gp = g0 + sstride * (size_t)line_cell(f + 4);   // next step's cell: start its trip from DRAM now
+#pragma unroll
+            for (int k = 0; k < 8; ++k) prefetch_l2(a.q[k] + gp);
+        }
+        cell_in(f + 3, b6 + 5 >= 6 ? b6 - 1 : b6 + 5, (b4 + 3) & 3);
+        const int sL = b6 + 2 >= 6 ? b6 - 4 : b6 + 2, sR = b6 + 3 >= 6 ? b6 - 3 : b6 + 3;
+        const double *L6 = r6 + (size_t)sL * M::R6 * M::NT, *R6p = r6 + (size_t)sR * M::R6 * M::NT;
+        const double *L4 = r4 + (size_t)b4 * M::R4 * M::NT, *R4p = r4 + (size_t)((b4 + 1) & 3) * M::R4 * M::NT;
+        FaceCoef fc;
+        face_coefficients(L6[7 * M::NT], R6p[7 * M::NT], L4[0], R4p[0], L4[1 * M::NT], R4p[1 * M::NT], L4[2 * M::NT],
+                          R4p[2 * M::NT], L4[3 * M::NT], R4p[3 * M::NT], L6[11 * M::NT], R6p[11 * M::NT], L6[12 * M::NT],
+                          R6p[12 * M::NT], L6[13 * M::NT], R6p[13 * M::NT], a.gam, a.g2, fc);
+        double amax[7];
+        face_amax(L4[0], L4[4 * M::NT], L4[5 * M::NT], L4[6 * M::NT], R4p[0], R4p[4 * M::NT], R4p[5 * M::NT], R4p[6 * M::NT], amax);
+        auto load = [&](int k, double F[7], double x[7]) {
+            const int sk = b6 + k >= 6 ? b6 + k - 6 : b6 + k;
+            const double *e = r6 + (size_t)sk * M::R6 * M::NT;
+#pragma unroll
+            for (int m = 0; m < 7; ++m) {
+                F[m] = e[m * M::NT];
+                x[m] = e[(7 + m) * M::NT];
+            }
+        };
+        double fh[7], Fs[7];
+        RegStash st;
+        BackCoef bc;
+        split_back(fc, bc);
+        face_flux(fc, amax, a.eps, load, st, Fs);
+        back_project(bc, Fs, fh);
+        const double bv2 = L4[3 * M::NT] * L4[1 * M::NT] + R4p[3 * M::NT] * R4p[1 * M::NT];
+        const double bv3 = L4[3 * M::NT] * L4[2 * M::NT] + R4p[3 * M::NT] * R4p[2 * M::NT];
+        const size_t g = g0 + sstride * (size_t)f;
+        a.bsA[g] = fma(0.5, bv2, fh[4]);
+        a.bsB[g] = fma(0.5, bv3, fh[5]);
+        const double fcur[5] = {fh[0], fh[1], fh[2], fh[3], fh[6]};
+        if (f > fA && f < cB && interior) {            // cell f: faces f-1 (fprev) and f
+#pragma unroll
+            for (int m = 0; m < 5; ++m) {
+                const double dfl = (fcur[m] - fprev[m]) * a.inv_h;
+                if (DIR == 0) a.rhs[m][g] = dfl; else red_add(a.rhs[sweep_out(DIR, m)] + g, dfl);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < 5; ++m) fprev[m] = fcur[m];
+        b6 = b6 + 1 >= 6 ? 0 : b6 + 1;
+        b4 = (b4 + 1) & 3;
+    }
+}
+
+// ------------------------------------------------------------------ x sweep: a warp marches its own lines
+// Along x the stencil runs along the lanes, so here groups of LPL lanes own a line (32 / LPL lines per warp): per march
+// step a group computes LPL new cells (one contiguous load of LPL doubles per component), LPL faces and LPL flux
+// differences; the cells live in a warp-private ring in shared memory (a cell is read by the six faces around it), the
+// fhat of the faces in a double-buffered strip so that a group's first lane finds its left face from the previous
+// step.  Warps never meet a CTA barrier -- the three phases of a step are separated by __syncwarp only -- and drift
+// freely like the threads of sweep_march.  LPL = 8, 16 or 32 is chosen per grid so that the last step of a line is
+// as full as possible (a line of nx cells has nx+1 faces: with 32 lanes per line 256 cells would take 9 steps for
+// 8.03 steps of work).
+template <int LPL> struct XWarpGeo {
+    static constexpr int NT = 256, WARPS = NT / 32;
+    static constexpr int LPW = 32 / LPL;               // lines per warp
+    static constexpr int RL = 2 * LPL;                 // ring slots per line (power of two >= LPL + 5)
+    static constexpr int RING = LPW * RL;              // = 64 cell slots per warp
+    static constexpr int NFB = 5;
+    static constexpr int FBL = LPL + 1;                // fhat strip of a line: entry l+1 = face of lane l
+    static constexpr int FBW = LPW * FBL;
+    static constexpr int PER_WARP = CQ_COUNT * RING + 2 * NFB * FBW;
+    static constexpr size_t SMEM = (size_t)WARPS * PER_WARP * sizeof(double);
+    static_assert(LPL >= 8 && RL >= LPL + 5, "the prologue needs five lanes and the ring LPL + 5 slots");
+    // grid: (groups of 8 * LPW lines along y, lines along z, segments along x)
+    W5_HD static void grid(const Dims &d, int nseg, int g[3])
+    {
+        g[0] = (line_count(d.Ny, d.bc[1]) + WARPS * LPW - 1) / (WARPS * LPW);
+        g[1] = line_count(d.Nz, d.bc[2]);
+        g[2] = nseg;
+    }
+};
+
+// host only: segments per line (lines are cut only when there are too few of them to fill the GPU) and lanes per line
+inline void xwarp_plan(const Dims &d, int ctas_per_wave, int &nseg, int &lpl)
+{
+    const int ni = d.Nx - 2 * NB3;
+    const int lines = line_count(d.Ny, d.bc[1]) * line_count(d.Nz, d.bc[2]);
+    nseg = 1;
+    while ((lines + 31) / 32 * nseg < 2 * ctas_per_wave && ni / (nseg + 1) >= 32) ++nseg;
+    const int per = (ni + nseg - 1) / nseg;
+    const int nf = per + 1 + (d.bc[0] != 1 ? 1 : 0);   // faces of the longest segment
+    lpl = 32;
+    double best = 1e300;
+    for (int l = 32; l >= 8; l /= 2) {                 // steps x lanes per useful face; ties go to the wider group
+        const double cost = (double)((nf + l - 1) / l) * l / nf;
+        if (cost < best - 1e-12) { best = cost; lpl = l; }
+    }
+}
+
+// geometry of a lane's line and segment, shared by the three phases
+template <int LPL> struct XWarpPos {
+    using X = XWarpGeo<LPL>;
+    int sub, ll;              // line of the warp, lane within the line's group
+    int j, k, n, ni, cA, cB, fA, fLast, nchunks;
+    bool ok, interior;
+    size_t g0;
+    W5_HD XWarpPos(const Dims &d, int nseg, int bx, int by, int bz, int warp, int lane)
+    {
+        sub = lane / LPL; ll = lane % LPL;
+        j = line_lo(d.bc[1]) + (bx * X::WARPS + warp) * X::LPW + sub;
+        k = line_lo(d.bc[2]) + by;
+        n = d.Nx; ni = n - 2 * NB3;
+        const int per = (ni + nseg - 1) / nseg;
+        cA = NB3 + bz * per;
+        cB = cA + per < n - NB3 ? cA + per : n - NB3;
+        fA = cA - 1;
+        fLast = (cB == n - NB3 && d.bc[0] != 1) ? n - NB3 : cB - 1;
+        nchunks = cA < cB ? (fLast - fA + LPL) / LPL : 0;              // the same for every lane of the CTA
+        ok = j <= d.Ny - 1 - line_lo(d.bc[1]) && cA < cB;
+        interior = j >= NB3 && j <= d.Ny - NB3 - 1 && k >= NB3 && k <= d.Nz - NB3 - 1;
+        g0 = ok ? vidx(d, 0, j, k) : 0;
+    }
+    W5_HD int slot(int c) const { return sub * X::RL + ((c - (fA - 2)) & (X::RL - 1)); }
+    W5_HD int fslot(int l) const { return sub * X::FBL + l; }
+    W5_HD int line_cell(int c, int bc) const
+    {
+        if (c >= n) c = bc == 1 ? c - ni : n - 1;
+        return c >= n ? n - 1 : c;
+    }
+};
+
+template <int LPL>
+W5_HD void xwarp_cell(const SweepArgs &a, const XWarpPos<LPL> &P, int c, double *cb)
+{
+    constexpr int CBS = XWarpGeo<LPL>::RING;
+    const size_t g = P.g0 + (size_t)P.line_cell(c, a.d.bc[0]);
+    double q[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) q[m] = a.q[m][g];
+    CellOut o;
+    cell_quantities(q, a.gam, o);
+    const int i = P.slot(c);
+#pragma unroll
+    for (int m = 0; m < 7; ++m) cb[(CQ_F0 + m) * CBS + i] = o.F[m];
+    cb[(CQ_Q0 + 0) * CBS + i] = q[0];
+    cb[(CQ_Q0 + 1) * CBS + i] = q[1];
+    cb[(CQ_Q0 + 2) * CBS + i] = q[2];
+    cb[(CQ_Q0 + 3) * CBS + i] = q[3];
+    cb[(CQ_Q0 + 4) * CBS + i] = q[5];
+    cb[(CQ_Q0 + 5) * CBS + i] = q[6];
+    cb[(CQ_Q0 + 6) * CBS + i] = q[7];
+    cb[CQ_V1 * CBS + i] = o.v1;
+    cb[CQ_V2 * CBS + i] = o.v2;
+    cb[CQ_V3 * CBS + i] = o.v3;
+    cb[CQ_B1 * CBS + i] = q[4];
+    cb[CQ_LF * CBS + i] = o.lf;
+    cb[CQ_LA * CBS + i] = o.la;
+    cb[CQ_LS * CBS + i] = o.ls;
+}
+
+// phase 0 of march step `chunk`: the new cells (and, before the first step, the five cells in front of the first face)
+template <int LPL>
+W5_HD void xwarp_cells(const SweepArgs &a, int nseg, int bx, int by, int bz, int warp, int lane, int chunk, double *wsm)
+{
+    const XWarpPos<LPL> P(a.d, nseg, bx, by, bz, warp, lane);
+    if (!P.ok || chunk >= P.nchunks) return;
+    if (chunk == 0 && P.ll < 5) xwarp_cell(a, P, P.fA - 2 + P.ll, wsm);
+    const int c = P.fA + 3 + LPL * chunk + P.ll;
+    if (c <= P.fLast + 3) xwarp_cell(a, P, c, wsm);
+    if (c + LPL <= P.fLast + 3) {                       // next step's cell: start its trip from DRAM now
+        const size_t gp = P.g0 + (size_t)P.line_cell(c + LPL, a.d.bc[0]);
+#pragma unroll
+        for (int m = 0; m < 8; ++m) prefetch_l2(a.q[m] + gp);
+    }
+}
+
+// phase 1: the faces
+template <int LPL>
+W5_HD void xwarp_faces(const SweepArgs &a, int nseg, int bx, int by, int bz, int warp, int lane, int chunk, double *wsm)
+{
+    using X = XWarpGeo<LPL>;
+    constexpr int CBS = X::RING;
+    const XWarpPos<LPL> P(a.d, nseg, bx, by, bz, warp, lane);
+    if (!P.ok || chunk >= P.nchunks) return;
+    const int f = P.fA + LPL * chunk + P.ll;
+    if (f > P.fLast) return;
+    const double *cb = wsm;
+    double *fb = wsm + CQ_COUNT * X::RING + (chunk & 1) * X::NFB * X::FBW;
+    const int iL = P.slot(f), iR = P.slot(f + 1);
+    FaceCoef fc;
+    face_coefficients(cb[CQ_Q0 * CBS + iL], cb[CQ_Q0 * CBS + iR], cb[CQ_V1 * CBS + iL], cb[CQ_V1 * CBS + iR],
+                      cb[CQ_V2 * CBS + iL], cb[CQ_V2 * CBS + iR], cb[CQ_V3 * CBS + iL], cb[CQ_V3 * CBS + iR],
+                      cb[CQ_B1 * CBS + iL], cb[CQ_B1 * CBS + iR], cb[(CQ_Q0 + 4) * CBS + iL], cb[(CQ_Q0 + 4) * CBS + iR],
+                      cb[(CQ_Q0 + 5) * CBS + iL], cb[(CQ_Q0 + 5) * CBS + iR], cb[(CQ_Q0 + 6) * CBS + iL],
+                      cb[(CQ_Q0 + 6) * CBS + iR], a.gam, a.g2, fc);
+    double amax[7];
+    face_amax(cb[CQ_V1 * CBS + iL], cb[CQ_LF * CBS + iL], cb[CQ_LA * CBS + iL], cb[CQ_LS * CBS + iL],
+              cb[CQ_V1 * CBS + iR], cb[CQ_LF * CBS + iR], cb[CQ_LA * CBS + iR], cb[CQ_LS * CBS + iR], amax);
+    auto load = [&](int kk, double F[7], double x[7]) {
+        const int ii = P.slot(f - 2 + kk);
+#pragma unroll
+        for (int m = 0; m < 7; ++m) {
+            F[m] = cb[(CQ_F0 + m) * CBS + ii];
+            x[m] = cb[(CQ_Q0 + m) * CBS + ii];
+        }
+    };
+    double fh[7], Fs[7];
+    RegStash st;
+    BackCoef bc;
+    split_back(fc, bc);
+    face_flux(fc, amax, a.eps, load, st, Fs);
+    back_project(bc, Fs, fh);
+    const int io = P.fslot(P.ll + 1);
+    fb[0 * X::FBW + io] = fh[0];
+    fb[1 * X::FBW + io] = fh[1];
+    fb[2 * X::FBW + io] = fh[2];
+    fb[3 * X::FBW + io] = fh[3];
+    fb[4 * X::FBW + io] = fh[6];
+    const double bv2 = cb[CQ_B1 * CBS + iL] * cb[CQ_V2 * CBS + iL] + cb[CQ_B1 * CBS + iR] * cb[CQ_V2 * CBS + iR];
+    const double bv3 = cb[CQ_B1 * CBS + iL] * cb[CQ_V3 * CBS + iL] + cb[CQ_B1 * CBS + iR] * cb[CQ_V3 * CBS + iR];
+    a.bsA[P.g0 + f] = fma(0.5, bv2, fh[4]);
+    a.bsB[P.g0 + f] = fma(0.5, bv3, fh[5]);
+}
+
+// phase 2: the flux differences (the x sweep runs first in a stage: plain stores)
+template <int LPL>
+W5_HD void xwarp_update(const SweepArgs &a, int nseg, int bx, int by, int bz, int warp, int lane, int chunk, const double *wsm)
+{
+    using X = XWarpGeo<LPL>;
+    const XWarpPos<LPL> P(a.d, nseg, bx, by, bz, warp, lane);
+    if (!P.ok || chunk >= P.nchunks || !P.interior) return;
+    const int c = P.fA + LPL * chunk + P.ll;           // cell c: faces c-1 and c
+    if (c <= P.fA || c >= P.cB) return;
+    const double *cur = wsm + CQ_COUNT * X::RING + (chunk & 1) * X::NFB * X::FBW;
+    const double *prv = wsm + CQ_COUNT * X::RING + ((chunk & 1) ^ 1) * X::NFB * X::FBW;
+#pragma unroll
+    for (int m = 0; m < 5; ++m) {
+        const double left = P.ll > 0 ? cur[m * X::FBW + P.fslot(P.ll)] : prv[m * X::FBW + P.fslot(LPL)];
+        a.rhs[m][P.g0 + c] = (cur[m * X::FBW + P.fslot(P.ll + 1)] - left) * a.inv_h;
     }
 }
 

@@ -93,9 +93,10 @@ class Solver3D:
         L.check(self.lib.weno5_profile_3d(self.h, 1 if enable else 0))
 
     def profile_read(self):
-        ms, n = C.c_double(), C.c_ulonglong()
-        L.check(self.lib.weno5_profile_read_3d(self.h, C.byref(ms), C.byref(n)))
-        return ms.value, int(n.value)
+        """(ms of the x, y, z sweep kernels, total launches) since profile(True) / the last read"""
+        ms, n = (C.c_double * 3)(), C.c_ulonglong()
+        L.check(self.lib.weno5_profile_read_3d(self.h, ms, C.byref(n)))
+        return [float(x) for x in ms], int(n.value)
 
 
 def classical_RK4_step_3d(g, q0, bxb0, byb0, bzb0, dt, es_roundtrip=True):

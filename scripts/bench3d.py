@@ -30,8 +30,10 @@ def main():
         divb = float(abs(s.divb()[3:-3, 3:-3, 3:-3]).max())
     cells = n ** 3
     print(json.dumps({"workload": f"orszag_tang_3d {n}^3 periodic", "steps": nd, "ms_per_step": 1e3 * wall / steps,
-                      "cell_updates_per_s": cells * steps / wall, "sweep_ms_per_launch": ms / max(nl, 1),
-                      "sweep_share": (ms / 2) / (1e3 * wall / steps), "sweep_launches_timed": nl,
+                      "cell_updates_per_s": cells * steps / wall,
+                      "sweep_ms_per_launch_xyz": [3 * m / max(nl, 1) for m in ms],
+                      "sweep_share": (sum(ms) / 2) / (1e3 * wall / steps), "sweep_launches_timed": nl,
+                      "lib": os.path.basename(os.environ.get("WENO5_LIB", "libweno5mhd.so")),
                       "max_divb": divb, "t_end": t}))
 
 

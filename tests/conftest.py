@@ -53,8 +53,10 @@ def host3d():
         subprocess.check_call([cxx, "-std=c++17", "-O2", "-mfma", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", so, src])
     lib = C.CDLL(so)
     dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
-    lib.h3_rk4_step.argtypes = [C.c_int, C.c_int, C.c_int, dp, C.c_double, C.c_double, ip, C.c_int, dp, dp, dp, dp,
+    lib.h3_rk4_step.argtypes = [C.c_int, C.c_int, C.c_int, dp, C.c_double, C.c_double, ip, C.c_int, C.c_int, dp, dp, dp, dp,
                                 C.c_double, dp, dp, dp, dp]
+    lib.h3_march_segments.argtypes = [C.c_int] * 5
+    lib.h3_xwarp_plan.argtypes = [C.c_int] * 5 + [ip, ip]
     lib.h3_timestep.argtypes = [C.c_int, C.c_int, C.c_int, dp, C.c_double, C.c_double, dp, dp, dp]
     lib.h3_divb_center2face.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp]
     return lib

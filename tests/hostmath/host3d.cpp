@@ -16,11 +16,31 @@ namespace {
 
 struct HostExec {
     std::vector<double> smem;
-    const double *dtp;
+    int nseg = 0;                   // > 0: sweeps by the marching kernel body with this many segments per line (< 0: y, z only)
+    int xwarp = 0;                  // > 0: x sweep by the warp-per-line body with this many segments
+    int lpl = 32;                   // and this many lanes per line
     template <int DIR> void sweep(const SweepArgs &a)
     {
         if (a.dtp[0] == 0.0) return;
         int g[3];
+        if (DIR == 0 && xwarp > 0) {
+            if (lpl == 8) run_xwarp<8>(a); else if (lpl == 16) run_xwarp<16>(a); else run_xwarp<32>(a);
+            return;
+        }
+        {
+            const int ns = nseg > 0 ? nseg : (DIR != 0 ? -nseg : 0);
+            if (ns > 0) {
+                MarchGeo::grid(a.d, DIR, ns, g);
+                smem.resize(MarchGeo::SMEM / sizeof(double));
+                for (int bz = 0; bz < g[2]; ++bz)
+                    for (int by = 0; by < g[1]; ++by)
+                        for (int bx = 0; bx < g[0]; ++bx) {
+                            std::fill(smem.begin(), smem.end(), std::numeric_limits<double>::quiet_NaN());
+                            for (int t = 0; t < MarchGeo::NT; ++t) sweep_march<DIR>(a, ns, bx, by, bz, t, smem.data());
+                        }
+                return;
+            }
+        }
         SweepGeo<DIR>::grid(a.d, g);
         smem.resize(SweepGeo<DIR>::SMEM / sizeof(double));
         for (int bz = 0; bz < g[2]; ++bz)
@@ -30,6 +50,27 @@ struct HostExec {
                     for (int t = 0; t < NT3; ++t) sweep_cells<DIR>(a, bx, by, bz, t, smem.data());
                     for (int t = 0; t < NT3; ++t) sweep_faces<DIR>(a, bx, by, bz, t, smem.data());
                     for (int t = 0; t < NT3; ++t) sweep_update<DIR>(a, bx, by, bz, t, smem.data());
+                }
+    }
+    template <int LPL> void run_xwarp(const SweepArgs &a)
+    {
+        using X = XWarpGeo<LPL>;
+        int g[3];
+        X::grid(a.d, xwarp, g);
+        smem.resize(X::SMEM / sizeof(double));
+        for (int bz = 0; bz < g[2]; ++bz)
+            for (int by = 0; by < g[1]; ++by)
+                for (int bx = 0; bx < g[0]; ++bx) {
+                    std::fill(smem.begin(), smem.end(), std::numeric_limits<double>::quiet_NaN());
+                    for (int w = 0; w < X::WARPS; ++w) {
+                        double *wsm = smem.data() + (size_t)w * X::PER_WARP;
+                        const XWarpPos<LPL> P(a.d, xwarp, bx, by, bz, w, 0);
+                        for (int ch = 0; ch < P.nchunks; ++ch) {
+                            for (int l = 0; l < 32; ++l) xwarp_cells<LPL>(a, xwarp, bx, by, bz, w, l, ch, wsm);
+                            for (int l = 0; l < 32; ++l) xwarp_faces<LPL>(a, xwarp, bx, by, bz, w, l, ch, wsm);
+                            for (int l = 0; l < 32; ++l) xwarp_update<LPL>(a, xwarp, bx, by, bz, w, l, ch, wsm);
+                        }
+                    }
                 }
     }
     template <class F> static void cells(const Dims &d, int lo, F f)
@@ -85,7 +126,7 @@ struct Host3 {
 
 // one classical_RK4_step of the 3-D extension through the product's kernel bodies; arrays in the public layout
 extern "C" int h3_rk4_step(int nx, int ny, int nz, const double h[3], double gam, double eps, const int bc[3], int roundtrip,
-                           const double *q0, const double *bx0, const double *by0, const double *bz0, double dt,
+                           int march_nseg, const double *q0, const double *bx0, const double *by0, const double *bz0, double dt,
                            double *q4, double *bx4, double *by4, double *bz4)
 {
     Host3 H(nx, ny, nz, h, gam, eps, 0.8, bc, roundtrip);
@@ -94,6 +135,12 @@ extern "C" int h3_rk4_step(int nx, int ny, int nz, const double h[3], double gam
     const double *f[3] = {bx0, by0, bz0};
     for (int m = 0; m < 3; ++m) std::memcpy(H.b.B[0][m], f[m], n * sizeof(double));
     HostExec ex;
+    // march_nseg = 10000 * (lanes per line) + 100 * (x-warp segments) + marching segments
+    ex.lpl = march_nseg / 10000 ? march_nseg / 10000 : 32;
+    march_nseg %= 10000;
+    ex.nseg = march_nseg % 100;
+    ex.xwarp = march_nseg / 100;
+    if (ex.xwarp > 0 && ex.nseg > 0) ex.nseg = -ex.nseg;
     // what weno5_upload_3d does: boundaries! on the state and the face arrays
     ex.cell_bc(H.b.Q[0], 9, H.b.d);
     ex.face_bc(H.b.B[0], H.b.d);
@@ -138,5 +185,23 @@ extern "C" int h3_divb_center2face(int nx, int ny, int nz, const double h[3], co
     const size_t n = (size_t)d.Nx * d.Ny * d.Nz;
     HostExec::cells(d, 0, [&](int i, int j, int k) { center2face_cell(q + 4 * n, q + 5 * n, q + 6 * n, bx, by, bz, d, i, j, k); });
     HostExec::cells(d, 0, [&](int i, int j, int k) { divb_cell(bx, by, bz, divb, d, 1.0 / h[0], 1.0 / h[1], 1.0 / h[2], i, j, k); });
+    return 0;
+}
+
+// the segment count the product would choose (MarchGeo::segments) for a grid on a GPU with `sms` SMs
+extern "C" int h3_march_segments(int nx, int ny, int nz, int dir, int sms)
+{
+    Dims d;
+    d.Nx = nx + 6; d.Ny = ny + 6; d.Nz = nz + 6;
+    d.bc[0] = d.bc[1] = d.bc[2] = 1;
+    return MarchGeo::segments(d, dir, sms);
+}
+
+extern "C" int h3_xwarp_plan(int nx, int ny, int nz, int bcx, int sms, int *nseg, int *lpl)
+{
+    Dims d;
+    d.Nx = nx + 6; d.Ny = ny + 6; d.Nz = nz + 6;
+    d.bc[0] = bcx; d.bc[1] = d.bc[2] = 1;
+    xwarp_plan(d, sms, *nseg, *lpl);
     return 0;
 }

@@ -19,12 +19,15 @@ def dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
-def host_step(lib, g, q, bx, by, bz, dt, roundtrip=True):
+def host_step(lib, g, q, bx, by, bz, dt, roundtrip=True, march=0):
+    """march = 0: tile kernel bodies in all three directions; > 0: the marching body with that many segments per
+    line; < 0: marching for y and z only (x by the tile body); 100 s + m: x by the warp-per-line body with s segments,
+    y and z marching with m segments, + 10000 l: l lanes per line in the x body (default 32)"""
     q4 = np.zeros_like(q, order="F")
     b4 = [np.zeros_like(bx, order="F") for _ in range(3)]
     h = (C.c_double * 3)(g.dx, g.dy, g.dz)
     bc = (C.c_int * 3)(int(g.bc_x), int(g.bc_y), int(g.bc_z))
-    rc = lib.h3_rk4_step(g.nx, g.ny, g.nz, h, g.gam, g.eps, bc, int(roundtrip), dp(q), dp(bx), dp(by), dp(bz), float(dt),
+    rc = lib.h3_rk4_step(g.nx, g.ny, g.nz, h, g.gam, g.eps, bc, int(roundtrip), int(march), dp(q), dp(bx), dp(by), dp(bz), float(dt),
                          dp(q4), dp(b4[0]), dp(b4[1]), dp(b4[2]))
     assert rc == 0
     return q4, b4[0], b4[1], b4[2]
@@ -41,9 +44,10 @@ def compare(got, want, tol):
         assert np.abs(a - b).max() <= tol * max(np.abs(b).max(), 1.0)
 
 
-@pytest.mark.parametrize("shape", [(70, 5, 4), (5, 36, 4), (4, 5, 36), (20, 19, 18)])
+@pytest.mark.parametrize("march", [0, 1, 3, -2, 102, 301, 80102, 160201])
+@pytest.mark.parametrize("shape", [(130, 5, 4), (5, 36, 4), (4, 5, 36), (37, 19, 18)])
 @pytest.mark.parametrize("bc", [(1, 1, 1), (0, 0, 0), (1, 0, 1), (0, 1, 0)])
-def test_kernel_bodies_reproduce_the_oracle_step(host3d, shape, bc):
+def test_kernel_bodies_reproduce_the_oracle_step(host3d, shape, bc, march):
     g, q, bx, by, bz = p3.smooth_3d(*shape, seed=sum(shape) + bc[0])
     g.bc_x, g.bc_y, g.bc_z = bc
     # re-derive ghosts for the boundary conditions under test, the way the driver would before its first step
@@ -51,7 +55,7 @@ def test_kernel_bodies_reproduce_the_oracle_step(host3d, shape, bc):
     O.boundaries_3d(g, q, bx, by, bz)
     dt = 0.8 * O.timestep_3d(g, q)[0]
     want = O.rk4_step_3d(g, q, bx, by, bz, dt)
-    got = host_step(host3d, g, q, bx, by, bz, dt)
+    got = host_step(host3d, g, q, bx, by, bz, dt, march=march)
     compare(got, want, 2e-13)
 
 
@@ -61,19 +65,20 @@ def test_two_steps_and_no_roundtrip(host3d):
     want = got = (q, bx, by, bz)
     for _ in range(2):
         want = O.rk4_step_3d(g, *want, dt, roundtrip=False)
-        got = host_step(host3d, g, *got, dt, roundtrip=False)
+        got = host_step(host3d, g, *got, dt, roundtrip=False, march=2)
     # Orszag-Tang has degenerate faces (B_t = 0 lines), where alpha_s is the square root of a round-off residual and
     # any two correct implementations differ; measured 5e-11
     compare(got, want, 1e-9)
 
 
+@pytest.mark.parametrize("march", [0, 2, 80101])
 @pytest.mark.parametrize("orientation", [0, 1, 2])
-def test_kernel_bodies_reduce_to_the_2d_reference_step(host3d, orientation):
+def test_kernel_bodies_reduce_to_the_2d_reference_step(host3d, orientation, march):
     g2, q, bx, by = pr.orszag_tang(16, ny=12, ysize=0.75)
     dt = 0.6 * O.timestep_2d(g2, q)[0]
     q2, bx2, by2 = O.rk4_step_2d(g2, q, bx, by, dt)
     g, q3, b0, b1, b2 = p3.embed_2d(g2, q, bx, by, orientation, n3=4)
-    r = host_step(host3d, g, q3, b0, b1, b2, dt)
+    r = host_step(host3d, g, q3, b0, b1, b2, dt, march=march)
     # the reduction needs vz = Bz = 0, i.e. Orszag-Tang, which has degenerate faces: the structured eigen-system of
     # the product and the dense one of the oracle differ there at the 1e-10 level (measured 5e-11)
     tol = 1e-9
@@ -101,3 +106,21 @@ def test_timestep_divb_center2face(host3d):
     for a, b in zip(f[:3], O.center2face_3d(g, q)):
         assert np.abs(a - b).max() <= 1e-15          # the host build contracts multiply-adds, the oracle does not
     assert np.abs(f[3] - O.divb_3d(g, f[0], f[1], f[2])).max() <= 1e-12
+
+
+def test_xwarp_plan(host3d):
+    ns, lpl = C.c_int(), C.c_int()
+    host3d.h3_xwarp_plan(256, 256, 256, 1, 148, C.byref(ns), C.byref(lpl))       # 257 faces: 33 steps of 8 lanes
+    assert (ns.value, lpl.value) == (1, 8)
+    host3d.h3_xwarp_plan(255, 256, 256, 1, 148, C.byref(ns), C.byref(lpl))       # 256 faces: 8 full steps of 32
+    assert (ns.value, lpl.value) == (1, 32)
+    host3d.h3_xwarp_plan(256, 8, 8, 1, 148, C.byref(ns), C.byref(lpl))           # 64 lines only: cut them
+    assert ns.value > 1 and lpl.value in (8, 16, 32)
+
+
+def test_march_segment_choice(host3d):
+    # 256^3 on 148 SMs: 8 x 32 CTAs per segment -> 4 segments of 64 cells fill 6.9 of 7 waves
+    assert host3d.h3_march_segments(256, 256, 256, 1, 148) == 4
+    for n in (8, 40, 100, 512):
+        ns = host3d.h3_march_segments(n, n, n, 2, 148)
+        assert 1 <= ns <= max(1, n // 8)
