@@ -473,7 +473,11 @@ template <int LPL> struct XWarpGeo {
     static constexpr int NT = 256, WARPS = NT / 32;
     static constexpr int LPW = 32 / LPL;               // lines per warp
     static constexpr int RL = 2 * LPL;                 // ring slots per line (power of two >= LPL + 5)
-    static constexpr int RING = LPW * RL;              // = 64 cell slots per warp
+    // distance of the lines' rings in shared memory: the 16 lanes of a half-warp must fall into 16 different 8-byte
+    // banks.  With 8 lanes per line the two lines of a half-warp sit at the same ring phase, so their rings are placed
+    // 8 banks apart (24 = 16 + 8); with 16 or 32 lanes per line a half-warp reads 16 consecutive slots of one ring.
+    static constexpr int RLS = LPL == 8 ? 24 : RL;
+    static constexpr int RING = LPW * RLS;             // cell slots per warp
     static constexpr int NFB = 5;
     static constexpr int FBL = LPL + 1;                // fhat strip of a line: entry l+1 = face of lane l
     static constexpr int FBW = LPW * FBL;
@@ -529,7 +533,7 @@ template <int LPL> struct XWarpPos {
         interior = j >= NB3 && j <= d.Ny - NB3 - 1 && k >= NB3 && k <= d.Nz - NB3 - 1;
         g0 = ok ? vidx(d, 0, j, k) : 0;
     }
-    W5_HD int slot(int c) const { return sub * X::RL + ((c - (fA - 2)) & (X::RL - 1)); }
+    W5_HD int slot(int c) const { return sub * X::RLS + ((c - (fA - 2)) & (X::RL - 1)); }
     W5_HD int fslot(int l) const { return sub * X::FBL + l; }
     W5_HD int line_cell(int c, int bc) const
     {
@@ -669,8 +673,15 @@ W5_HD void emf_cell(const CtArgs3 &a, int i, int j, int k)
     const size_t g = vidx(d, i, j, k);
     const bool inner = i >= 1 && i < d.Nx - 1 && j >= 1 && j < d.Ny - 1 && k >= 1 && k < d.Nz - 1;
     double ox = 0.0, oy = 0.0, oz = 0.0;
-    if (inner) {
-        const double *fy = a.fl[0], *fz = a.fl[1], *gz = a.fl[2], *gx = a.fl[3], *hx = a.fl[4], *hy = a.fl[5];
+    const double *fy = a.fl[0], *fz = a.fl[1], *gz = a.fl[2], *gx = a.fl[3], *hx = a.fl[4], *hy = a.fl[5];
+    // away from the ghost layers flux_at is the identity on all twelve reads (bit-identical, a third of the instructions)
+    const bool deep = i >= NB3 && i < d.Nx - NB3 - 1 && j >= NB3 && j < d.Ny - NB3 - 1 && k >= NB3 && k < d.Nz - NB3 - 1;
+    if (deep) {
+        const size_t sy = (size_t)d.Nx, sz = (size_t)d.Nx * d.Ny;
+        ox = 0.5 * (hy[g] + hy[g + sy] - gz[g] - gz[g + sz]);
+        oy = 0.5 * (fz[g] + fz[g + sz] - hx[g] - hx[g + 1]);
+        oz = 0.5 * (gx[g] + gx[g + 1] - fy[g] - fy[g + sy]);
+    } else if (inner) {
         ox = 0.5 * (flux_at(hy, d, i, j, k) + flux_at(hy, d, i, j + 1, k) - flux_at(gz, d, i, j, k) - flux_at(gz, d, i, j, k + 1));
         oy = 0.5 * (flux_at(fz, d, i, j, k) + flux_at(fz, d, i, j, k + 1) - flux_at(hx, d, i, j, k) - flux_at(hx, d, i + 1, j, k));
         oz = 0.5 * (flux_at(gx, d, i, j, k) + flux_at(gx, d, i + 1, j, k) - flux_at(fy, d, i, j, k) - flux_at(fy, d, i, j + 1, k));
@@ -727,6 +738,22 @@ struct UpdArgs3 {
     int stage, roundtrip;
 };
 
+// inverse of map_cell: the positions (own index first) whose value is that of interior cell idx after boundaries!
+W5_HD int cell_images(int idx, int N, int bc, int out[4])
+{
+    const int n = N - 2 * NB3;
+    int cnt = 0;
+    out[cnt++] = idx;
+    if (bc == 1) {
+        if (idx < 2 * NB3) out[cnt++] = idx + n;          // the first three interior cells appear behind the last
+        if (idx > N - 2 * NB3 - 1) out[cnt++] = idx - n;  // and the last three in front of the first
+    } else {
+        if (idx == NB3) for (int g = 0; g < NB3; ++g) out[cnt++] = g;
+        if (idx == N - NB3 - 1) for (int g = 0; g < NB3; ++g) out[cnt++] = N - NB3 + g;
+    }
+    return cnt;
+}
+
 // RK combination of rho, M, E (Weno5_2D.jl:139-146 ... :279), interpolateB_face2center (:344-356) for all three field
 // components, and what survives of ES_Switch (:1734-1768): S = E2S(q), E = S2E(q) when the round trip is on
 W5_HD void update_cell(const UpdArgs3 &a, double dt, int i, int j, int k)
@@ -748,10 +775,24 @@ W5_HD void update_cell(const UpdArgs3 &a, double dt, int i, int j, int k)
     const double Bz = (-z[vidx(d, i, j, k - 2)] + 9.0 * z[vidx(d, i, j, k - 1)] + 9.0 * z[g] - z[vidx(d, i, j, k + 1)]) / 16.0;
     double S, E2;
     e2s_s2e(v[0], v[1], v[2], v[3], Bx, By, Bz, v[4], a.gam, S, E2);
-    a.qn[0][g] = v[0]; a.qn[1][g] = v[1]; a.qn[2][g] = v[2]; a.qn[3][g] = v[3];
-    a.qn[4][g] = Bx; a.qn[5][g] = By; a.qn[6][g] = Bz;
-    a.qn[7][g] = S;
-    a.qn[8][g] = a.roundtrip ? E2 : v[4];
+    const double out[9] = {v[0], v[1], v[2], v[3], Bx, By, Bz, S, a.roundtrip ? E2 : v[4]};
+#pragma unroll
+    for (int c = 0; c < 9; ++c) a.qn[c][g] = out[c];
+    // boundaries!(q) by scatter: the cells next to a boundary also store their ghost images (the inverse of map_cell),
+    // so no separate ghost-fill pass runs over the volume after the update
+    int xi[4], yi[4], zi[4];
+    const int nxi = cell_images(i, d.Nx, d.bc[0], xi), nyi = cell_images(j, d.Ny, d.bc[1], yi),
+              nzi = cell_images(k, d.Nz, d.bc[2], zi);
+    if (nxi + nyi + nzi > 3) {
+        for (int cz = 0; cz < nzi; ++cz)
+            for (int cy = 0; cy < nyi; ++cy)
+                for (int cx = 0; cx < nxi; ++cx) {
+                    if (cx + cy + cz == 0) continue;
+                    const size_t gi = vidx(d, xi[cx], yi[cy], zi[cz]);
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) a.qn[c][gi] = out[c];
+                }
+    }
 }
 
 // boundaries!(q) in place: a ghost cell reads the interior cell the rules map it to (interior cells are not written)
@@ -865,8 +906,7 @@ void enqueue_stage3(const Bufs3 &b, Exec &ex, int stage)
     for (int m = 0; m < 5; ++m) u.rhs[m] = b.rhs[m];
     for (int m = 0; m < 3; ++m) u.bn[m] = b.B[stage & 3][m];
     u.dtp = b.ctl; u.d = b.d; u.c = coef[stage]; u.gam = b.gam; u.stage = stage; u.roundtrip = b.roundtrip;
-    ex.update(u);
-    ex.cell_bc(dst, 9, b.d);
+    ex.update(u);                                         // writes the ghost images too: no cell_bc pass
     if (stage == 4) ex.face_bc(b.B[0], b.d);              // Weno5_2D.jl:313
 }
 

@@ -82,6 +82,11 @@ if __name__ == "__main__":
     rep = sys.argv[2]
     steps = int(sys.argv[3]) if len(sys.argv) > 3 else 6
     agg, tot_b = launches(f"gpurun_out/launches_{tag}.csv", f"profiles/{tag}_launch_list.csv", steps)
+    if tag.endswith("3d"):           # 3-D extension (scripts/r2_profile3d.sh): summaries only, bench.py does not read them
+        full(rep, f"profiles/{tag}_sweep_kernels_ncu_full.txt", f"profiles/{tag}_sweep_kernels_ncu_full.json")
+        print(open(f"profiles/{tag}_launch_list.csv").read())
+        print(open(f"profiles/{tag}_sweep_kernels_ncu_full.txt").read())
+        sys.exit(0)
     s = full(rep, f"profiles/{tag}_flux_kernel_ncu_full.txt", f"profiles/{tag}_flux_kernel_ncu_full.json")
     tr, pipe = [], []
     for name, lst in s.items():
