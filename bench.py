@@ -149,6 +149,41 @@ def cpu_baseline(budget_s=15.0):
     return out
 
 
+def run_ext3d(n, steps, with_cpu):
+    """3-D extension beside the headline: weno5_advance_3d on the 3-D Orszag-Tang vortex n^3,
+    device-resident, dt recomputed every step; rate from the wall clock around the call (it returns after a stream
+    synchronize).  CPU arm: the 3-D oracle (OpenMP) on a 64^3 sample."""
+    import time
+    from julia_b200 import problems3d as p3
+    from julia_b200.solver3d import Solver3D
+    g, q, bx, by, bz = p3.orszag_tang_3d(n)
+    with Solver3D(g) as s:
+        s.upload(q, bx, by, bz)
+        s.advance(2)
+        t0 = time.perf_counter()
+        _, nd = s.advance(steps)
+        wall = time.perf_counter() - t0
+        s.profile(True)
+        s.advance(1)
+        ms, nl = s.profile_read()
+        divb = float(abs(s.divb()[3:-3, 3:-3, 3:-3]).max())
+        launches = s.launch_count()
+    out = {"workload": f"orszag_tang_3d {n}^3, periodic, one GPU", "steps": int(nd), "ms_per_step": 1e3 * wall / steps,
+           "value": n ** 3 * steps / wall, "unit": "cell-updates/s",
+           "sweep_ms_per_launch_xyz": [m / 4 for m in ms], "sweep_share_of_step": sum(ms) / (1e3 * wall / steps),
+           "algorithmic_bytes_per_cell_update": 1152, "max_divb": divb, "gpu_launches": int(launches),
+           "timing": "host clock around weno5_advance_3d (synchronises on return)"}
+    if with_cpu:
+        from oracle import oracle_c as O
+        g, q, bx, by, bz = p3.orszag_tang_3d(64)
+        t0 = time.perf_counter()
+        O.advance_3d(g, q, bx, by, bz, 1, fast=True)
+        sec = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": 64 ** 3 / sec, "unit": "cell-updates/s", "cores": O.num_threads(True), "kind": "port",
+                               "sample": f"orszag_tang_3d 64^3, 1 RK4 step incl. timestep, 3-D C oracle -O3 OpenMP, {sec:.1f} s"}
+    return out
+
+
 def host_threads():
     """All host cores for the CPU arm, at every N: torchrun exports OMP_NUM_THREADS=1 to its workers, which would
     leave the oracle on one thread (round-1 SCALE record).  Set before the oracle's OpenMP runtime starts, and
@@ -530,6 +565,11 @@ def run_gpu(args):
             line["cpu_baseline"] = cpu_baseline()
         else:
             line["cpu_baseline"] = None
+        if world == 1 and args.ext3d_n > 0:
+            try:
+                line["extension_3d"] = run_ext3d(args.ext3d_n, 5, not args.no_cpu)
+            except Exception as e:                       # the headline line must not depend on the extension
+                line["extension_3d"] = {"error": f"{type(e).__name__}: {e}"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -549,6 +589,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--strong-steps", type=int, default=4, help="timed steps of the strong-scaling leg (0: skip)")
+    ap.add_argument("--ext3d-n", type=int, default=192, help="N = 1: also time the 3-D extension on n^3 cells (0: skip)")
     ap.add_argument("--no-slab-check", action="store_true", help="N > 1: skip the slab bit-identity pre-check")
     ap.add_argument("--es-roundtrip", type=int, default=1, help="1: E <- S2E(E2S(E)) after every stage (2-D reference form)")
     args = ap.parse_args()

@@ -18,7 +18,8 @@ module Weno5GPU
 export Weno5Params, Solver, upload!, download, boundaries!, timestep, classical_RK4_step, set_es_switch!, es_switch_count, es_switch_mask, comm_halo_mode,
        pinned_array, free_pinned, pipe_overlapped, arr2img,
        classical_RK4_step!, advance!, compute_divB, compute_global_vmax, interpolateB_center2face,
-       state2conserved, WENO5_2D, WENO5_1D, Pipe, pipe_step!
+       state2conserved, WENO5_2D, WENO5_1D, Pipe, pipe_step!,
+       Weno5Params3D, Solver3D, WENO5_3D
 
 const NBnd = 3                                    # Weno5_2D.jl:9
 const BC_OUTFLOW, BC_PERIODIC = Cint(0), Cint(1)
@@ -243,6 +244,96 @@ function WENO5_1D(p::Weno5Params, q; tmax::Real=0.2)
     s = Solver(p); upload!(s, q)
     t, n = advance!(s, typemax(Int32); tmax=tmax)
     return download(s), t, n
+end
+
+# ---- 3-D extension (include/weno5mhd.h "3-D extension"; SURVEY 8 f4).  The reference has no 3-D solver: its
+# classical_RK4_step docstring (Weno5_2D.jl:113-123) says the sweep functions are the same in every dimension, and
+# these wrappers continue the 2-D names to q :: Array{Float64,4} (Nx,Ny,Nz,9), bxb/byb/bzb :: Array{Float64,3}.
+
+# mirrors `weno5_params3d`
+struct Weno5Params3D
+    nx::Cint; ny::Cint; nz::Cint
+    dx::Cdouble; dy::Cdouble; dz::Cdouble
+    gamma::Cdouble; cfl::Cdouble; eps::Cdouble
+    bc_x::Cint; bc_y::Cint; bc_z::Cint
+    es_roundtrip::Cint
+end
+
+Weno5Params3D(nx, ny, nz; xsize=1.0, ysize=1.0, zsize=1.0, gamma=5/3, cfl=0.8, eps=1e-6,
+              bc_x=BC_OUTFLOW, bc_y=BC_OUTFLOW, bc_z=BC_OUTFLOW, es_roundtrip=true) =
+    Weno5Params3D(nx, ny, nz, xsize/nx, ysize/ny, zsize/nz, gamma, cfl, eps, bc_x, bc_y, bc_z, es_roundtrip ? 1 : 0)
+
+mutable struct Solver3D
+    h::Ptr{Cvoid}
+    p::Weno5Params3D
+    function Solver3D(p::Weno5Params3D; device::Integer=0)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:weno5_create_3d, libweno5), Cint, (Ref{Weno5Params3D}, Cint, Ref{Ptr{Cvoid}}), p, device, h))
+        s = new(h[], p)
+        finalizer(x -> (x.h != C_NULL && ccall((:weno5_destroy_3d, libweno5), Cint, (Ptr{Cvoid},), x.h); x.h = C_NULL), s)
+        return s
+    end
+end
+
+dims(s::Solver3D) = (Int(s.p.nx) + 2NBnd, Int(s.p.ny) + 2NBnd, Int(s.p.nz) + 2NBnd)
+
+function upload!(s::Solver3D, q::Array{Float64,4}, bxb::Array{Float64,3}, byb::Array{Float64,3}, bzb::Array{Float64,3})
+    @assert size(q) == (dims(s)..., 9) && size(bxb) == size(byb) == size(bzb) == dims(s)
+    check(ccall((:weno5_upload_3d, libweno5), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                s.h, q, bxb, byb, bzb))
+end
+"q only: the three face fields are derived on the device (interpolateB_center2face, Weno5_2D.jl:1669)."
+upload!(s::Solver3D, q::Array{Float64,4}) =
+    check(ccall((:weno5_upload_3d, libweno5), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                s.h, q, C_NULL, C_NULL, C_NULL))
+
+function download(s::Solver3D)
+    d = dims(s)
+    q = Array{Float64}(undef, d..., 9); bxb = Array{Float64}(undef, d...); byb = similar(bxb); bzb = similar(bxb)
+    check(ccall((:weno5_download_3d, libweno5), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                s.h, q, bxb, byb, bzb))
+    return q, bxb, byb, bzb
+end
+
+"timestep(q) -> (dt, (vxmax, vymax, vzmax)): Weno5_2D.jl:1930 with a third term."
+function timestep(s::Solver3D)
+    dt = Ref(0.0); vm = zeros(3)
+    check(ccall((:weno5_timestep_3d, libweno5), Cint, (Ptr{Cvoid}, Ref{Float64}, Ptr{Float64}), s.h, dt, vm))
+    return dt[], (vm[1], vm[2], vm[3])
+end
+
+"classical_RK4_step on the resident state (Weno5_2D.jl:125 with a z sweep and three face fields)."
+classical_RK4_step!(s::Solver3D, dt::Real) =
+    check(ccall((:weno5_rk4_step_3d, libweno5), Cint, (Ptr{Cvoid}, Cdouble), s.h, dt))
+
+function advance!(s::Solver3D, nsteps::Integer; tmax::Real=0.0, t::Real=0.0)
+    tt = Ref(Float64(t)); nd = Ref{Cint}(0)
+    check(ccall((:weno5_advance_3d, libweno5), Cint, (Ptr{Cvoid}, Cint, Cdouble, Ref{Float64}, Ref{Cint}), s.h, nsteps, tmax, tt, nd))
+    return tt[], Int(nd[])
+end
+
+function compute_divB(s::Solver3D)
+    d = Array{Float64}(undef, dims(s)...)
+    check(ccall((:weno5_divb_3d, libweno5), Cint, (Ptr{Cvoid}, Ptr{Float64}), s.h, d))
+    return d
+end
+
+"(q4, bxb4, byb4, bzb4) = classical_RK4_step(q0, bxb0, byb0, bzb0, dt): host arrays in, host arrays out."
+function classical_RK4_step(p::Weno5Params3D, q::Array{Float64,4}, bxb::Array{Float64,3}, byb::Array{Float64,3},
+                            bzb::Array{Float64,3}, dt::Float64)
+    q4 = similar(q); bx4 = similar(bxb); by4 = similar(byb); bz4 = similar(bzb)
+    check(ccall((:weno5_classical_rk4_step_3d, libweno5), Cint,
+                (Ref{Weno5Params3D}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cdouble,
+                 Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), p, q, bxb, byb, bzb, dt, q4, bx4, by4, bz4))
+    return q4, bx4, by4, bz4
+end
+
+"The driver loop of WENO5_2D (Weno5_2D.jl:33-110) for a volume: state resident on the GPU, dt recomputed every step."
+function WENO5_3D(p::Weno5Params3D, q, bxb, byb, bzb; nstep::Integer=typemax(Int32) >> 12, tmax::Real=0.1)
+    s = Solver3D(p)
+    upload!(s, q, bxb, byb, bzb)
+    t, n = advance!(s, nstep; tmax=tmax)
+    return (download(s)..., t, n)
 end
 
 end # module

@@ -116,6 +116,20 @@ def test_params_layout_matches_ctypes_and_julia(tmp_path):
     assert layout == c["fields"]
     assert (off + 7) // 8 * 8 == c["sizeof_weno5_params"]
     assert "const NBnd = 3" in jl and "BC_OUTFLOW, BC_PERIODIC = Cint(0), Cint(1)" in jl
+    # the 3-D extension's struct: C layout vs ctypes vs the Julia text
+    assert C.sizeof(L.Params3D) == c["sizeof_weno5_params3d"] and C.alignment(L.Params3D) == c["alignof_weno5_params3d"]
+    assert [n for n, _ in L.Params3D._fields_] == list(c["fields3d"])
+    for name, _ in L.Params3D._fields_:
+        d = getattr(L.Params3D, name)
+        assert (d.offset, d.size) == (c["fields3d"][name]["offset"], c["fields3d"][name]["size"]), name
+    body = re.search(r"struct Weno5Params3D\n(.*?)\nend", jl, flags=re.S).group(1)
+    off, layout = 0, {}
+    for name, ty in re.findall(r"(\w+)::(Cint|Cdouble)", body):
+        off = (off + size[ty] - 1) // size[ty] * size[ty]
+        layout[name] = {"offset": off, "size": size[ty]}
+        off += size[ty]
+    assert layout == c["fields3d"]
+    assert (off + 7) // 8 * 8 == c["sizeof_weno5_params3d"]
 
 
 def test_pure_c_driver_links_against_the_library(built, tmp_path):
