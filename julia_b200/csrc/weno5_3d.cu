@@ -123,6 +123,14 @@ __global__ void face_update3_kernel(const CtArgs3 a)
     face_update_cell(a, dt, i, j, k);
 }
 
+__global__ void ct3_kernel(const CtArgs3 a)
+{
+    W5_CELL_IJK(a.d, 0);
+    const double dt = a.dtp[0];
+    if (!inside || dt == 0.0) return;
+    ct_cell(a, dt, i, j, k);
+}
+
 __global__ void update3_kernel(const UpdArgs3 a)
 {
     W5_CELL_IJK(a.d, NB3);
@@ -248,6 +256,7 @@ struct weno5_ctx3d {
     // sweep kernels: x by sweep3_xwarp_kernel (a warp per line), y and z by sweep3_march_kernel (a thread per line).
     // WENO5_3D_SWEEP (tuning / cross-checks): tile = the CTA-tile kernel in all directions, xtile = for x only,
     // xmarch = x by the thread-per-line kernel (uncoalesced)
+    bool fused_ct = false;          // WENO5_3D_CT=fused: EMFs and face update in one kernel (measured slower: 25.1 vs 24.3 ms/step at 256^3)
     bool xwarp = true;
     int lpl = 32;                   // lanes per line of the x sweep (8, 16, 32)
     bool march[3] = {false, true, true};
@@ -292,8 +301,17 @@ struct DevExec {
         if (e1) cudaEventRecord(e1, c->stream);
         c->launches++;
     }
-    void emf(const CtArgs3 &a) { emf3_kernel<<<cell_grid(a.d, 0, kBlock), kBlock, 0, c->stream>>>(a); c->launches++; }
-    void face_update(const CtArgs3 &a) { face_update3_kernel<<<cell_grid(a.d, 0, kBlock), kBlock, 0, c->stream>>>(a); c->launches++; }
+    void ct(const CtArgs3 &a)
+    {
+        if (c->fused_ct) {
+            ct3_kernel<<<cell_grid(a.d, 0, kBlock), kBlock, 0, c->stream>>>(a);
+            c->launches++;
+        } else {                                           // default: EMF volumes written and read back
+            emf3_kernel<<<cell_grid(a.d, 0, kBlock), kBlock, 0, c->stream>>>(a);
+            face_update3_kernel<<<cell_grid(a.d, 0, kBlock), kBlock, 0, c->stream>>>(a);
+            c->launches += 2;
+        }
+    }
     void update(const UpdArgs3 &a) { update3_kernel<<<cell_grid(a.d, NB3, kBlock), kBlock, 0, c->stream>>>(a); c->launches++; }
     void cell_bc(double *const v[], int n, const Dims &d)
     {
@@ -418,6 +436,8 @@ extern "C" int weno5_create_3d(const weno5_params3d *P, int device, weno5_ctx3d 
         c->xwarp = !(tile || xtile || xmarch);
         c->march[0] = xmarch;
         c->march[1] = c->march[2] = !tile;
+        const char *ce = getenv("WENO5_3D_CT");
+        c->fused_ct = ce && strcmp(ce, "fused") == 0;
         const char *ns = getenv("WENO5_3D_NSEG");                         // tuning knob: segments per line
         for (int dir = 0; dir < 3; ++dir) {
             c->nseg[dir] = ns ? atoi(ns) : MarchGeo::segments(b.d, dir, prop.multiProcessorCount);

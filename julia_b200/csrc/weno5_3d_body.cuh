@@ -304,13 +304,18 @@ W5_HD void sweep_update(const SweepArgs &a, int bx, int by, int bz, int tid, con
 // face and one flux difference, and carries the previous face's fhat in registers.  No barrier in the kernel, no cell
 // is computed twice and no face but the one two segments share, and the eight warps of an SM drift freely, so the cell
 // and update work of one warp overlaps the face work of another.
-// Per thread: 6 slots x (F[7], q7[7]) + 4 slots x (v1, v2, v3, B1, lf, la, ls) = 112 doubles; 256 threads = 224 KB.
+// The raw state of a cell travels global -> shared memory by cp.async one march step ahead (straight into the ring
+// slots it will occupy), so no global-load latency sits in the march.
+// Per thread: 7 slots x q7[7] (cells f-2 .. f+4, the last one in flight) + 6 x F[7] + 5 x B1 + 4 x (1/rho, lf, la, ls)
+// = 112 doubles; 256 threads = 224 KB.
 struct MarchGeo {
     static constexpr int NT = 256;                     // 32 lines along x  x  8 values of the other lateral axis
     static constexpr int WARPS = NT / 32;
-    static constexpr int R6 = 14, R4 = 7;
-    static constexpr int PER_THREAD = 6 * R6 + 4 * R4;
+    static constexpr int NQ = 7, NF = 6, NB = 5, NW = 4;             // ring lengths (cells)
+    static constexpr int OFF_Q = 0, OFF_F = OFF_Q + NQ * 7, OFF_B = OFF_F + NF * 7, OFF_W = OFF_B + NB;
+    static constexpr int PER_THREAD = OFF_W + NW * 4;
     static constexpr size_t SMEM = (size_t)NT * PER_THREAD * sizeof(double);
+    static_assert(PER_THREAD == 112, "ring budget");
     // lines of a warp run along the lane axis, the warps of a CTA along the row axis: (x, z) for the y sweep, (x, y) for
     // the z sweep -- lanes along x, every access coalesced -- and (y, z) for the x sweep, where a warp's 32 lines are
     // Nx apart: its loads and stores touch one 32-byte sector per lane, which the next three march steps use up (L2)
@@ -353,6 +358,34 @@ W5_HD void prefetch_l2(const double *p)
 #endif
 }
 
+// 8-byte asynchronous copy global -> shared (LDGSTS); on the host the copy happens at once
+W5_HD void cp_async_f64(double *dst_smem, const double *src)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+#else
+    *dst_smem = *src;
+#endif
+}
+W5_HD void cp_async_commit_wait_all()
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+#endif
+}
+W5_HD void cp_async_commit()
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+W5_HD void cp_async_wait_all()
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
 W5_HD void red_add(double *p, double v)
 {
 #if defined(__CUDA_ARCH__)
@@ -382,56 +415,72 @@ W5_HD void sweep_march(const SweepArgs &a, int nseg, int bx, int by, int bz, int
     const int fLast = (cB == n - NB3 && d.bc[DIR] != 1) ? n - NB3 : cB - 1;
     const size_t sstride = DIR == 0 ? 1 : (DIR == 1 ? (size_t)d.Nx : (size_t)d.Nx * d.Ny);
     const size_t g0 = DIR == 0 ? vidx(d, 0, p1, p2) : (DIR == 1 ? vidx(d, p1, 0, p2) : vidx(d, p1, p2, 0));   // cell 0 of the line
-    double *r6 = smem + tid;                           // entry e of slot s: r6[(s * R6 + e) * NT]
-    double *r4 = smem + (size_t)6 * M::R6 * M::NT + tid;
+    double *sm = smem + tid;                           // entry e of this thread: sm[e * NT]
+    auto Q = [&](int slot, int m) -> double & { return sm[(size_t)(M::OFF_Q + slot * 7 + m) * M::NT]; };
+    auto F = [&](int slot, int m) -> double & { return sm[(size_t)(M::OFF_F + slot * 7 + m) * M::NT]; };
+    auto B = [&](int slot) -> double & { return sm[(size_t)(M::OFF_B + slot) * M::NT]; };
+    auto W = [&](int slot, int m) -> double & { return sm[(size_t)(M::OFF_W + slot * 4 + m) * M::NT]; };
 
     auto line_cell = [&](int c) {                      // stencil cell past the end of the line: quirk Q3
         if (c >= n) c = d.bc[DIR] == 1 ? c - ni : n - 1;
         return c >= n ? n - 1 : c;
     };
-    auto cell_in = [&](int c, int s6, int s4) {
+    // raw state of cell c -> its ring slots (q7 and B1), asynchronously
+    auto fetch = [&](int c, int sq, int sb) {
         const size_t g = g0 + sstride * (size_t)line_cell(c);
+        cp_async_f64(&Q(sq, 0), a.q[0] + g);
+        cp_async_f64(&Q(sq, 1), a.q[sweep_in(DIR, 1)] + g);
+        cp_async_f64(&Q(sq, 2), a.q[sweep_in(DIR, 2)] + g);
+        cp_async_f64(&Q(sq, 3), a.q[sweep_in(DIR, 3)] + g);
+        cp_async_f64(&B(sb), a.q[sweep_in(DIR, 4)] + g);
+        cp_async_f64(&Q(sq, 4), a.q[sweep_in(DIR, 5)] + g);
+        cp_async_f64(&Q(sq, 5), a.q[sweep_in(DIR, 6)] + g);
+        cp_async_f64(&Q(sq, 6), a.q[7] + g);
+    };
+    // cell quantities of a cell whose raw state sits in the ring: flux -> F ring, 1/rho and wave speeds -> W ring
+    auto cell_in = [&](int sq, int sf, int sb, int sw) {
         double q[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) q[k] = a.q[sweep_in(DIR, k)][g];
+        q[0] = Q(sq, 0); q[1] = Q(sq, 1); q[2] = Q(sq, 2); q[3] = Q(sq, 3);
+        q[4] = B(sb); q[5] = Q(sq, 4); q[6] = Q(sq, 5); q[7] = Q(sq, 6);
         CellOut o;
         cell_quantities(q, a.gam, o);
-        double *e6 = r6 + (size_t)s6 * M::R6 * M::NT, *e4 = r4 + (size_t)s4 * M::R4 * M::NT;
 #pragma unroll
-        for (int m = 0; m < 7; ++m) e6[m * M::NT] = o.F[m];
-        e6[7 * M::NT] = q[0]; e6[8 * M::NT] = q[1]; e6[9 * M::NT] = q[2]; e6[10 * M::NT] = q[3];
-        e6[11 * M::NT] = q[5]; e6[12 * M::NT] = q[6]; e6[13 * M::NT] = q[7];
-        e4[0] = o.v1; e4[1 * M::NT] = o.v2; e4[2 * M::NT] = o.v3; e4[3 * M::NT] = q[4];
-        e4[4 * M::NT] = o.lf; e4[5 * M::NT] = o.la; e4[6 * M::NT] = o.ls;
+        for (int m = 0; m < 7; ++m) F(sf, m) = o.F[m];
+        W(sw, 0) = fast_rcp(q[0]);                     // v = M / rho is re-formed at the face: M * (1/rho), as cell_quantities does
+        W(sw, 1) = o.lf; W(sw, 2) = o.la; W(sw, 3) = o.ls;
     };
 
-    // cell c lives in ring slot (c - (fA-2)) mod 6 and face-only slot (c - (fA-2)) mod 4
-    for (int c = 0; c < 5; ++c) cell_in(fA - 2 + c, c, c & 3);          // prologue: cells fA-2 .. fA+2
-    int b6 = 0, b4 = 2;                                // slot of cell f-2; face-only slot of cell f
+    // cell c has the running index r = c - (fA-2) and lives in slot r mod NQ / NF / NB / NW of the four rings
+    for (int r = 0; r < 5; ++r) fetch(fA - 2 + r, r, r);               // prologue: cells fA-2 .. fA+2
+    cp_async_commit_wait_all();
+    for (int r = 0; r < 5; ++r) cell_in(r, r, r, r & 3);
+    fetch(fA + 3, 5, 0);                               // the first step's cell (B1 slot of cell fA-2, no longer needed)
+    cp_async_commit();
+    int rq = 0, rf = 0, rb = 2, rw = 2;                // slots of cell f-2 (Q, F rings) and of cell f (B1, W rings)
     double fprev[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     for (int f = fA; f <= fLast; ++f) {
-        {
-            const size_t gp = g0 + sstride * (size_t)line_cell(f + 4);   // next step's cell: start its trip from DRAM now
-#pragma unroll
-            for (int k = 0; k < 8; ++k) prefetch_l2(a.q[k] + gp);
-        }
-        cell_in(f + 3, b6 + 5 >= 6 ? b6 - 1 : b6 + 5, (b4 + 3) & 3);
-        const int sL = b6 + 2 >= 6 ? b6 - 4 : b6 + 2, sR = b6 + 3 >= 6 ? b6 - 3 : b6 + 3;
-        const double *L6 = r6 + (size_t)sL * M::R6 * M::NT, *R6p = r6 + (size_t)sR * M::R6 * M::NT;
-        const double *L4 = r4 + (size_t)b4 * M::R4 * M::NT, *R4p = r4 + (size_t)((b4 + 1) & 3) * M::R4 * M::NT;
+        cp_async_wait_all();                           // cell f+3 has landed (issued a step ago)
+        const int q3 = rq + 5 >= M::NQ ? rq + 5 - M::NQ : rq + 5, q4 = rq + 6 >= M::NQ ? rq + 6 - M::NQ : rq + 6;
+        const int b3 = rb + 3 >= M::NB ? rb + 3 - M::NB : rb + 3, b4 = rb + 4 >= M::NB ? rb + 4 - M::NB : rb + 4;
+        cell_in(q3, rf + 5 >= M::NF ? rf + 5 - M::NF : rf + 5, b3, (rw + 3) & 3);
+        if (f < fLast) { fetch(f + 4, q4, b4); cp_async_commit(); }    // next step's cell, into slots nothing reads now
+        const int qL = rq + 2 >= M::NQ ? rq + 2 - M::NQ : rq + 2, qR = rq + 3 >= M::NQ ? rq + 3 - M::NQ : rq + 3;
+        const int bR = rb + 1 >= M::NB ? rb + 1 - M::NB : rb + 1, wR = (rw + 1) & 3;
+        const double riL = W(rw, 0), riR = W(wR, 0);
+        const double v1L = Q(qL, 1) * riL, v2L = Q(qL, 2) * riL, v3L = Q(qL, 3) * riL;
+        const double v1R = Q(qR, 1) * riR, v2R = Q(qR, 2) * riR, v3R = Q(qR, 3) * riR;
+        const double B1L = B(rb), B1R = B(bR);
         FaceCoef fc;
-        face_coefficients(L6[7 * M::NT], R6p[7 * M::NT], L4[0], R4p[0], L4[1 * M::NT], R4p[1 * M::NT], L4[2 * M::NT],
-                          R4p[2 * M::NT], L4[3 * M::NT], R4p[3 * M::NT], L6[11 * M::NT], R6p[11 * M::NT], L6[12 * M::NT],
-                          R6p[12 * M::NT], L6[13 * M::NT], R6p[13 * M::NT], a.gam, a.g2, fc);
+        face_coefficients(Q(qL, 0), Q(qR, 0), v1L, v1R, v2L, v2R, v3L, v3R, B1L, B1R, Q(qL, 4), Q(qR, 4), Q(qL, 5), Q(qR, 5),
+                          Q(qL, 6), Q(qR, 6), a.gam, a.g2, fc);
         double amax[7];
-        face_amax(L4[0], L4[4 * M::NT], L4[5 * M::NT], L4[6 * M::NT], R4p[0], R4p[4 * M::NT], R4p[5 * M::NT], R4p[6 * M::NT], amax);
-        auto load = [&](int k, double F[7], double x[7]) {
-            const int sk = b6 + k >= 6 ? b6 + k - 6 : b6 + k;
-            const double *e = r6 + (size_t)sk * M::R6 * M::NT;
+        face_amax(v1L, W(rw, 1), W(rw, 2), W(rw, 3), v1R, W(wR, 1), W(wR, 2), W(wR, 3), amax);
+        auto load = [&](int k, double Fk[7], double x[7]) {
+            const int sq = rq + k >= M::NQ ? rq + k - M::NQ : rq + k, sf = rf + k >= M::NF ? rf + k - M::NF : rf + k;
 #pragma unroll
             for (int m = 0; m < 7; ++m) {
-                F[m] = e[m * M::NT];
-                x[m] = e[(7 + m) * M::NT];
+                Fk[m] = F(sf, m);
+                x[m] = Q(sq, m);
             }
         };
         double fh[7], Fs[7];
@@ -440,8 +489,8 @@ W5_HD void sweep_march(const SweepArgs &a, int nseg, int bx, int by, int bz, int
         split_back(fc, bc);
         face_flux(fc, amax, a.eps, load, st, Fs);
         back_project(bc, Fs, fh);
-        const double bv2 = L4[3 * M::NT] * L4[1 * M::NT] + R4p[3 * M::NT] * R4p[1 * M::NT];
-        const double bv3 = L4[3 * M::NT] * L4[2 * M::NT] + R4p[3 * M::NT] * R4p[2 * M::NT];
+        const double bv2 = B1L * v2L + B1R * v2R;
+        const double bv3 = B1L * v3L + B1R * v3R;
         const size_t g = g0 + sstride * (size_t)f;
         a.bsA[g] = fma(0.5, bv2, fh[4]);
         a.bsB[g] = fma(0.5, bv3, fh[5]);
@@ -455,8 +504,10 @@ W5_HD void sweep_march(const SweepArgs &a, int nseg, int bx, int by, int bz, int
         }
 #pragma unroll
         for (int m = 0; m < 5; ++m) fprev[m] = fcur[m];
-        b6 = b6 + 1 >= 6 ? 0 : b6 + 1;
-        b4 = (b4 + 1) & 3;
+        rq = rq + 1 >= M::NQ ? 0 : rq + 1;
+        rf = rf + 1 >= M::NF ? 0 : rf + 1;
+        rb = rb + 1 >= M::NB ? 0 : rb + 1;
+        rw = (rw + 1) & 3;
     }
 }
 
@@ -709,6 +760,57 @@ W5_HD void face_update_cell(const CtArgs3 &a, double dt, int i, int j, int k)
     a.bn[2][g] = bb[2] - cx * (oy - oy_i) + cy * (ox - ox_j);
 }
 
+// EMFs and face update in one pass (opt-in, WENO5_3D_CT=fused; measured slower than the two passes: the nine EMF
+// evaluations per cell cost more than the round trip of the three EMF volumes saves): a face needs the EMFs of its four edges -- for the three faces of a cell nine
+// evaluations, whose 36 reads of the transport fluxes are shared between neighbouring threads (L1) -- so the three EMF
+// volumes are never written or read.  The same expressions, evaluated in the same order, as emf_cell +
+// face_update_cell: bit-identical.
+W5_HD double emf_at(const CtArgs3 &a, int m, int i, int j, int k)
+{
+    const Dims &d = a.d;
+    if (!(i >= 1 && i < d.Nx - 1 && j >= 1 && j < d.Ny - 1 && k >= 1 && k < d.Nz - 1)) return 0.0;
+    const double *fy = a.fl[0], *fz = a.fl[1], *gz = a.fl[2], *gx = a.fl[3], *hx = a.fl[4], *hy = a.fl[5];
+    if (m == 0) return 0.5 * (flux_at(hy, d, i, j, k) + flux_at(hy, d, i, j + 1, k) - flux_at(gz, d, i, j, k) - flux_at(gz, d, i, j, k + 1));
+    if (m == 1) return 0.5 * (flux_at(fz, d, i, j, k) + flux_at(fz, d, i, j, k + 1) - flux_at(hx, d, i, j, k) - flux_at(hx, d, i + 1, j, k));
+    return 0.5 * (flux_at(gx, d, i, j, k) + flux_at(gx, d, i + 1, j, k) - flux_at(fy, d, i, j, k) - flux_at(fy, d, i, j + 1, k));
+}
+
+W5_HD void ct_cell(const CtArgs3 &a, double dt, int i, int j, int k)
+{
+    const Dims &d = a.d;
+    const size_t g = vidx(d, i, j, k);
+    const bool inner = i >= 1 && i < d.Nx - 1 && j >= 1 && j < d.Ny - 1 && k >= 1 && k < d.Nz - 1;
+    double ox, oy, oz, ox_j, ox_k, oy_i, oy_k, oz_i, oz_j;
+    // one more layer away from the ghost cells than emf_cell's fast path: the shifted EMFs read index - 1 too
+    const bool deep = i > NB3 && i < d.Nx - NB3 - 1 && j > NB3 && j < d.Ny - NB3 - 1 && k > NB3 && k < d.Nz - NB3 - 1;
+    if (deep) {
+        const double *fy = a.fl[0], *fz = a.fl[1], *gz = a.fl[2], *gx = a.fl[3], *hx = a.fl[4], *hy = a.fl[5];
+        const size_t sy = (size_t)d.Nx, sz = (size_t)d.Nx * d.Ny;
+        ox = 0.5 * (hy[g] + hy[g + sy] - gz[g] - gz[g + sz]);
+        ox_j = 0.5 * (hy[g - sy] + hy[g] - gz[g - sy] - gz[g - sy + sz]);
+        ox_k = 0.5 * (hy[g - sz] + hy[g - sz + sy] - gz[g - sz] - gz[g]);
+        oy = 0.5 * (fz[g] + fz[g + sz] - hx[g] - hx[g + 1]);
+        oy_i = 0.5 * (fz[g - 1] + fz[g - 1 + sz] - hx[g - 1] - hx[g]);
+        oy_k = 0.5 * (fz[g - sz] + fz[g] - hx[g - sz] - hx[g - sz + 1]);
+        oz = 0.5 * (gx[g] + gx[g + 1] - fy[g] - fy[g + sy]);
+        oz_i = 0.5 * (gx[g - 1] + gx[g] - fy[g - 1] - fy[g - 1 + sy]);
+        oz_j = 0.5 * (gx[g - sy] + gx[g - sy + 1] - fy[g - sy] - fy[g]);
+    } else {
+        ox = emf_at(a, 0, i, j, k); oy = emf_at(a, 1, i, j, k); oz = emf_at(a, 2, i, j, k);
+        ox_j = inner ? emf_at(a, 0, i, j - 1, k) : 0.0; ox_k = inner ? emf_at(a, 0, i, j, k - 1) : 0.0;
+        oy_i = inner ? emf_at(a, 1, i - 1, j, k) : 0.0; oy_k = inner ? emf_at(a, 1, i, j, k - 1) : 0.0;
+        oz_i = inner ? emf_at(a, 2, i - 1, j, k) : 0.0; oz_j = inner ? emf_at(a, 2, i, j - 1, k) : 0.0;
+    }
+    double bb[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+        bb[m] = a.stage < 4 ? a.b0[m][g] : 1.0 / 3 * (-a.b0[m][g] + a.b1[m][g] + 2 * a.b2[m][g] + a.b3[m][g]);
+    const double cx = a.c * dt * a.idx_, cy = a.c * dt * a.idy_, cz = a.c * dt * a.idz_;
+    a.bn[0][g] = bb[0] - cy * (oz - oz_j) + cz * (oy - oy_k);
+    a.bn[1][g] = bb[1] - cz * (ox - ox_k) + cx * (oz - oz_i);
+    a.bn[2][g] = bb[2] - cx * (oy - oy_i) + cy * (ox - ox_j);
+}
+
 // boundaries! on a face array, in place: every location the rules write reads the location they copy (or 0)
 W5_HD bool face_is_ghost(const Dims &d, int i, int j, int k)
 {
@@ -872,7 +974,7 @@ struct Bufs3 {
     double *ctl;               // 8 doubles, see dt_from_vmax
 };
 
-// Exec provides: sweep<DIR>(SweepArgs), emf(CtArgs3), face_update(CtArgs3), update(UpdArgs3), cell_bc(double *const v[], n, Dims),
+// Exec provides: sweep<DIR>(SweepArgs), ct(CtArgs3), update(UpdArgs3), cell_bc(double *const v[], n, Dims),
 // face_bc(double *const v[3], Dims); each returns when the work is enqueued (device) or done (host)
 template <class Exec>
 void enqueue_stage3(const Bufs3 &b, Exec &ex, int stage)
@@ -898,8 +1000,7 @@ void enqueue_stage3(const Bufs3 &b, Exec &ex, int stage)
     }
     ct.dtp = b.ctl; ct.d = b.d; ct.c = coef[stage]; ct.stage = stage;
     ct.idx_ = 1.0 / b.dx; ct.idy_ = 1.0 / b.dy; ct.idz_ = 1.0 / b.dz;
-    ex.emf(ct);
-    ex.face_update(ct);
+    ex.ct(ct);                                            // EMFs + face update (fused; or emf + face_update)
 
     UpdArgs3 u;
     for (int c = 0; c < 9; ++c) { u.q0[c] = b.Q[0][c]; u.q1[c] = b.Q[1][c]; u.q2[c] = b.Q[2][c]; u.q3[c] = b.Q[3][c]; u.qn[c] = dst[c]; }

@@ -79,11 +79,17 @@ struct HostExec {
             for (int j = lo; j < d.Ny - lo; ++j)
                 for (int i = lo; i < d.Nx - lo; ++i) f(i, j, k);
     }
-    void emf(const CtArgs3 &a) { if (a.dtp[0] != 0.0) cells(a.d, 0, [&](int i, int j, int k) { emf_cell(a, i, j, k); }); }
-    void face_update(const CtArgs3 &a)
+    bool fused_ct = true;
+    void ct(const CtArgs3 &a)
     {
         const double dt = a.dtp[0];
-        if (dt != 0.0) cells(a.d, 0, [&](int i, int j, int k) { face_update_cell(a, dt, i, j, k); });
+        if (dt == 0.0) return;
+        if (fused_ct) {
+            cells(a.d, 0, [&](int i, int j, int k) { ct_cell(a, dt, i, j, k); });
+        } else {
+            cells(a.d, 0, [&](int i, int j, int k) { emf_cell(a, i, j, k); });
+            cells(a.d, 0, [&](int i, int j, int k) { face_update_cell(a, dt, i, j, k); });
+        }
     }
     void update(const UpdArgs3 &a)
     {
@@ -135,6 +141,8 @@ extern "C" int h3_rk4_step(int nx, int ny, int nz, const double h[3], double gam
     const double *f[3] = {bx0, by0, bz0};
     for (int m = 0; m < 3; ++m) std::memcpy(H.b.B[0][m], f[m], n * sizeof(double));
     HostExec ex;
+    // march_nseg < 0: the split EMF / face-update kernels instead of the fused one (then as for -march_nseg)
+    if (march_nseg < 0) { ex.fused_ct = false; march_nseg = -march_nseg; }
     // march_nseg = 10000 * (lanes per line) + 100 * (x-warp segments) + marching segments
     ex.lpl = march_nseg / 10000 ? march_nseg / 10000 : 32;
     march_nseg %= 10000;

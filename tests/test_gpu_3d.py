@@ -84,7 +84,7 @@ def test_advance_conserves_and_keeps_divb_zero(built):
         divb = s.divb()
         got = s.download()
         nl = s.launch_count()
-    assert nl >= 6 * (4 * 6 + 2)          # per step: 4 x (3 sweeps, EMF, face update, cell update) + CFL reduction
+    assert nl >= 6 * (4 * 5 + 2)          # per step: 4 x (3 sweeps, EMF + face update, cell update) + CFL reduction
     scale = np.abs(q[I, I, I]).reshape(-1, 9).sum(axis=0)
     for c in (0, 1, 2, 3, 8):
         assert abs(s1[c] - s0[c]) <= 1e-12 * scale[c], c

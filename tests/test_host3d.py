@@ -21,8 +21,9 @@ def dp(a):
 
 def host_step(lib, g, q, bx, by, bz, dt, roundtrip=True, march=0):
     """march = 0: tile kernel bodies in all three directions; > 0: the marching body with that many segments per
-    line; < 0: marching for y and z only (x by the tile body); 100 s + m: x by the warp-per-line body with s segments,
-    y and z marching with m segments, + 10000 l: l lanes per line in the x body (default 32)"""
+    line; 100 s + m: x by the warp-per-line body with s segments,
+    y and z marching with m segments, + 10000 l: l lanes per line in the x body (default 32); negative: the same
+    with the split EMF / face-update kernels instead of the fused one"""
     q4 = np.zeros_like(q, order="F")
     b4 = [np.zeros_like(bx, order="F") for _ in range(3)]
     h = (C.c_double * 3)(g.dx, g.dy, g.dz)
@@ -44,7 +45,7 @@ def compare(got, want, tol):
         assert np.abs(a - b).max() <= tol * max(np.abs(b).max(), 1.0)
 
 
-@pytest.mark.parametrize("march", [0, 1, 3, -2, 102, 301, 80102, 160201])
+@pytest.mark.parametrize("march", [0, 1, 3, 102, 301, 80102, 160201, -80102])
 @pytest.mark.parametrize("shape", [(130, 5, 4), (5, 36, 4), (4, 5, 36), (37, 19, 18)])
 @pytest.mark.parametrize("bc", [(1, 1, 1), (0, 0, 0), (1, 0, 1), (0, 1, 0)])
 def test_kernel_bodies_reproduce_the_oracle_step(host3d, shape, bc, march):
