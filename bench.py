@@ -303,7 +303,7 @@ def run_e2e(args, lib, L, s, q, bx, by, gglob, local, world, cells_global, nyl, 
     # single GPU: the pipelined host step (y-slabs with overlap rows; H2D, compute and D2H overlap)
     if world == 1 and nyl >= 1024:
         from julia_b200.solver import Pipe
-        rows = 512
+        rows = 128
         oq, poq = pinned_array(lib, q.shape)
         obx, pobx = pinned_array(lib, bx.shape)
         oby, poby = pinned_array(lib, by.shape)
@@ -321,13 +321,15 @@ def run_e2e(args, lib, L, s, q, bx, by, gglob, local, world, cells_global, nyl, 
             torch.cuda.synchronize()
             pipe_s = time.time() - t0
         nslab = (nyl + rows - 1) // rows
-        up_rows = nslab * (rows + 2 * 16 + 8)
+        up_rows = q.shape[1] + 24                        # every public row once + the 24 wrap-around rows sent ahead
         e2e = {"value": cells_global * psteps / pipe_s, "unit": "cell-updates/s",
                "h2d_bytes_per_step": 10 * q.shape[0] * up_rows * 8, "d2h_bytes_per_step": bytes_dir, "steps": psteps,
                "path": "pipelined",
                "calls": "weno5_pipe_step(q0,bxb0,byb0,dt) -> (q4,bxb4,byb4,dt_next): host arrays in, host arrays out, "
-                        f"{nslab} y-slabs of {rows}+32 rows on 3 streams (copies and compute overlap), pinned host arrays; "
-                        "the S plane is not uploaded (output only)",
+                        f"{nslab} y-slabs of {rows}+32 rows on 3 compute streams; the input arrays cross PCIe once into an image "
+                        "on the device (upload stream, one event per row range) from which the slabs gather their windows, "
+                        "the result rows leave through a result image on a download stream; pinned host arrays; the S plane "
+                        "is not uploaded (output only)",
                "sequential": e2e_seq}
         for p_ in (poq, pobx, poby):
             lib.weno5_host_free(p_)

@@ -1364,8 +1364,15 @@ extern "C" int weno5_classical_rk4_step_1d(const weno5_params *P, const double *
 // rotate, so the H2D copy of slab k+1, the RK4 step of slab k and the D2H copy of slab k-1 overlap:
 // the call is bound by the PCIe transfer of the state (once in, once out) instead of
 // upload + compute + download in sequence.
+// Every row crosses PCIe once: the input arrays are uploaded, row range by row range, on a stream of their own into an
+// image of the whole grid on the device, and a slab gathers the rows of its window (its own and the overlap) from that
+// image as soon as the ranges it needs have arrived (one event per range).  Windows therefore cost no extra transfer,
+// and slabs can be small: the fill and drain of the pipeline -- the upload of the first window and the download of
+// the last slab, which nothing overlaps -- shrink with them.  (WENO5_PIPE_DIRECT=1: every slab uploads its whole
+// window from the host itself, the first version: 6-8 % more bytes up, and slabs of 512 rows were the best.)
 constexpr int PIPE_H = 16;
 constexpr int PIPE_NCTX = 3;
+constexpr int PIPE_NIN = 10;  // planes of the input image: 8 cell fields (no S) + bxb + byb
 
 struct weno5_pipe {
     weno5_params P;
@@ -1374,6 +1381,12 @@ struct weno5_pipe {
     int W;                    // interior rows of a slab window = R + 2 PIPE_H
     bool last_pinned = true;  // the last weno5_pipe_step got page-locked host arrays (its copies overlapped compute)
     weno5_ctx *ctx[PIPE_NCTX];
+    bool direct = false;      // slabs upload their windows themselves (no input image)
+    double *inbuf = nullptr;  // input image: PIPE_NIN planes of Nx x Ny doubles (public layout)
+    double *outbuf = nullptr; // result image: 11 planes in the host order (q[:,:,1..9], bxb, byb)
+    cudaStream_t up = nullptr, down = nullptr;
+    std::vector<cudaEvent_t> ev;   // [0]: the wrap-around rows (periodic), [1 + c]: upload range c
+    std::vector<cudaEvent_t> done; // [k]: slab k has put its rows into the result image
 };
 
 extern "C" int weno5_pipe_overlapped(const weno5_pipe *p) { return p && p->last_pinned ? 1 : 0; }
@@ -1382,6 +1395,17 @@ extern "C" int weno5_pipe_destroy(weno5_pipe *p)
 {
     if (!p) return 0;
     for (int k = 0; k < PIPE_NCTX; ++k) weno5_destroy(p->ctx[k]);
+    {
+        DevGuard dg_;
+        dg_.set(p->device);
+        for (cudaEvent_t e : p->ev) cudaEventDestroy(e);
+        for (cudaEvent_t e : p->done) cudaEventDestroy(e);
+        if (p->up) cudaStreamDestroy(p->up);
+        if (p->down) cudaStreamDestroy(p->down);
+        if (p->inbuf) cudaFree(p->inbuf);
+        if (p->outbuf) cudaFree(p->outbuf);
+        cudaGetLastError();
+    }
     delete p;
     return 0;
 }
@@ -1404,6 +1428,32 @@ extern "C" int weno5_pipe_create(const weno5_params *P, int device, int rows_per
         if (int r = create_ctx(P, device, p->W, 0, SIDE_NONE, SIDE_NONE, &p->ctx[k])) {
             weno5_pipe_destroy(p);
             return r;
+        }
+    }
+    p->direct = getenv("WENO5_PIPE_DIRECT") != nullptr;
+    if (!p->direct) {
+        DevGuard dg_;
+        const size_t hp = (size_t)(P->nx + 2 * WENO5_NBND) * (P->ny + 2 * WENO5_NBND);
+        const int nranges = (P->ny + 2 * WENO5_NBND + p->R - 1) / p->R;
+        cudaError_t e = dg_.set(device);
+        if (e == cudaSuccess) e = cudaMalloc(&p->inbuf, PIPE_NIN * hp * sizeof(double));
+        if (e == cudaSuccess) e = cudaMalloc(&p->outbuf, 11 * hp * sizeof(double));
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->up, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->down, cudaStreamNonBlocking);
+        for (int k = 0; e == cudaSuccess && k < nranges + 1; ++k) {
+            cudaEvent_t x;
+            e = cudaEventCreateWithFlags(&x, cudaEventDisableTiming);
+            if (e == cudaSuccess) p->ev.push_back(x);
+        }
+        const int nslab_ = (P->ny + p->R - 1) / p->R;
+        for (int k = 0; e == cudaSuccess && k < nslab_; ++k) {
+            cudaEvent_t x;
+            e = cudaEventCreateWithFlags(&x, cudaEventDisableTiming);
+            if (e == cudaSuccess) p->done.push_back(x);
+        }
+        if (e != cudaSuccess) {
+            weno5_pipe_destroy(p);
+            return fail(WENO5_ERR_CUDA, "pipelined step: %s", cudaGetErrorString(e));
         }
     }
     *out = p;
@@ -1465,6 +1515,40 @@ extern "C" int weno5_pipe_step(weno5_pipe *p, const double *q0, const double *bx
         CU(cudaMemsetAsync(c->vmax_bits, 0, 2 * sizeof(unsigned long long), c->stream));
     }
 
+    // ---- input image: host planes in the order of the slab planes (8 cell fields without S, bxb, byb)
+    const double *hsrc[PIPE_NIN];
+    const double *isrc[PIPE_NIN];
+    {
+        int n = 0;
+        for (int f = 0; f < NCELL; ++f)
+            if (f != C_S) { hsrc[n] = q0 + host_comp(f) * hp; isrc[n] = p->inbuf + (size_t)n * hp; ++n; }
+        hsrc[n] = bxb0; isrc[n] = p->inbuf + (size_t)n * hp; ++n;
+        hsrc[n] = byb0; isrc[n] = p->inbuf + (size_t)n * hp; ++n;
+    }
+    const int nranges = (Ny + p->R - 1) / p->R;
+    const int T0 = periodic ? ny + WENO5_NBND - (PIPE_H + 8) : Ny, T1 = periodic ? ny + WENO5_NBND : Ny;   // wrap-around rows
+    int next_range = 0;
+    auto upload_range = [&](int a, int b, cudaEvent_t ev) -> int {       // public rows [a, b) of every plane, then the event
+        for (int n = 0; n < PIPE_NIN; ++n)
+            CU(cudaMemcpyAsync(p->inbuf + (size_t)n * hp + (size_t)Nx * a, hsrc[n] + (size_t)Nx * a, (size_t)Nx * (b - a) * sizeof(double),
+                               cudaMemcpyHostToDevice, p->up));
+        CU(cudaEventRecord(ev, p->up));
+        return 0;
+    };
+    if (!p->direct && periodic)
+        if (int r = upload_range(T0, T1, p->ev[0])) return r;           // the first slab's window starts behind the last row
+    // rows [a, b) of the image are needed on stream s: enqueue the uploads up to them, wait for their events
+    auto need_rows = [&](int a, int b, cudaStream_t s) -> int {
+        if (a >= T0 && b <= T1) { CU(cudaStreamWaitEvent(s, p->ev[0], 0)); return 0; }
+        const int c1 = (b - 1) / p->R;
+        for (; next_range <= c1 && next_range < nranges; ++next_range) {
+            const int ra = next_range * p->R, rb = ra + p->R < Ny ? ra + p->R : Ny;
+            if (int r = upload_range(ra, rb, p->ev[1 + next_range])) return r;
+        }
+        for (int c = a / p->R; c <= c1; ++c) CU(cudaStreamWaitEvent(s, p->ev[1 + c], 0));
+        return 0;
+    };
+
     for (int k = 0; k < nslab; ++k) {
         weno5_ctx *c = p->ctx[k % PIPE_NCTX];
         const Geom &g = c->g;
@@ -1492,11 +1576,25 @@ extern "C" int weno5_pipe_step(weno5_pipe *p, const double *q0, const double *bx
             if (run > g.NYI - ii) run = g.NYI - ii;
             // S (q0[:,:,8]) is an output of the E-branch step, never an input (ES_Switch derives it from E,
             // Weno5_2D.jl:1738): its plane is not sent over PCIe
-            for (int f = 0; f < NCELL; ++f)
-                if (f != C_S)
-                    if (int r = copy_rows(c, c->Q0.q[f], q0 + host_comp(f) * hp, nullptr, Ny, src, ii, run)) return r;
-            if (int r = copy_rows(c, c->Q0.bx, bxb0, nullptr, Ny, src, ii, run)) return r;
-            if (int r = copy_rows(c, c->Q0.by, byb0, nullptr, Ny, src, ii, run)) return r;
+            if (p->direct) {
+                for (int f = 0; f < NCELL; ++f)
+                    if (f != C_S)
+                        if (int r = copy_rows(c, c->Q0.q[f], q0 + host_comp(f) * hp, nullptr, Ny, src, ii, run)) return r;
+                if (int r = copy_rows(c, c->Q0.bx, bxb0, nullptr, Ny, src, ii, run)) return r;
+                if (int r = copy_rows(c, c->Q0.by, byb0, nullptr, Ny, src, ii, run)) return r;
+            } else {
+                if (int r = need_rows(src, src + run, c->stream)) return r;
+                const double *sp[PIPE_NIN];
+                double *dp[PIPE_NIN];
+                int n = 0;
+                for (int f = 0; f < NCELL; ++f)
+                    if (f != C_S) { dp[n] = c->Q0.q[f] + 1 + (size_t)g.pitch * ii; ++n; }
+                dp[n++] = c->Q0.bx + 1 + (size_t)g.pitch * ii;
+                dp[n++] = c->Q0.by + 1 + (size_t)g.pitch * ii;
+                for (int m = 0; m < PIPE_NIN; ++m) sp[m] = isrc[m] + (size_t)Nx * src;
+                launch_gather_rows(sp, dp, PIPE_NIN, g.Nx, Nx, g.pitch, run, c->stream);
+                c->launches++;
+            }
             ii += run;
         }
         c->uploaded = true;
@@ -1513,12 +1611,35 @@ extern "C" int weno5_pipe_step(weno5_pipe *p, const double *q0, const double *bx
         if (phys_lo && r0 == 0) d0 = 1;                        // public ghost rows 0..2 = internal 1..3
         if (phys_hi && r1 == ny) d1 = g.NYI - 1;
         const int hj = w0 - 1 + d0;                            // public row of internal row d0
-        for (int f = 0; f < NCELL; ++f)
-            if (int r = copy_rows(c, c->Q0.q[f], nullptr, q4 + host_comp(f) * hp, Ny, hj, d0, d1 - d0)) return r;
-        if (int r = copy_rows(c, c->Q0.bx, nullptr, bxb4, Ny, hj, d0, d1 - d0)) return r;
-        if (int r = copy_rows(c, c->Q0.by, nullptr, byb4, Ny, hj, d0, d1 - d0)) return r;
+        if (p->direct) {
+            for (int f = 0; f < NCELL; ++f)
+                if (int r = copy_rows(c, c->Q0.q[f], nullptr, q4 + host_comp(f) * hp, Ny, hj, d0, d1 - d0)) return r;
+            if (int r = copy_rows(c, c->Q0.bx, nullptr, bxb4, Ny, hj, d0, d1 - d0)) return r;
+            if (int r = copy_rows(c, c->Q0.by, nullptr, byb4, Ny, hj, d0, d1 - d0)) return r;
+        } else {
+            // rows -> result image (contiguous, host order); the download stream takes them from there, so this
+            // slab's stream is free for its next window while they travel
+            const double *sp[11];
+            double *dp[11];
+            for (int f = 0; f < NCELL; ++f) {
+                sp[host_comp(f)] = c->Q0.q[f] + 1 + (size_t)g.pitch * d0;
+                dp[host_comp(f)] = p->outbuf + (size_t)host_comp(f) * hp + (size_t)Nx * hj;
+            }
+            sp[9] = c->Q0.bx + 1 + (size_t)g.pitch * d0; dp[9] = p->outbuf + 9 * hp + (size_t)Nx * hj;
+            sp[10] = c->Q0.by + 1 + (size_t)g.pitch * d0; dp[10] = p->outbuf + 10 * hp + (size_t)Nx * hj;
+            launch_gather_rows(sp, dp, 11, g.Nx, g.pitch, Nx, d1 - d0, c->stream);
+            c->launches++;
+            CU(cudaEventRecord(p->done[k], c->stream));
+            CU(cudaStreamWaitEvent(p->down, p->done[k], 0));
+            const size_t nb = (size_t)Nx * (d1 - d0) * sizeof(double), off = (size_t)Nx * hj;
+            for (int f = 0; f < 9; ++f)
+                CU(cudaMemcpyAsync(q4 + (size_t)f * hp + off, p->outbuf + (size_t)f * hp + off, nb, cudaMemcpyDeviceToHost, p->down));
+            CU(cudaMemcpyAsync(bxb4 + off, p->outbuf + 9 * hp + off, nb, cudaMemcpyDeviceToHost, p->down));
+            CU(cudaMemcpyAsync(byb4 + off, p->outbuf + 10 * hp + off, nb, cudaMemcpyDeviceToHost, p->down));
+        }
     }
 
+    if (!p->direct) { CU(cudaStreamSynchronize(p->up)); CU(cudaStreamSynchronize(p->down)); }
     unsigned long long vb[2] = {0ull, 0ull};
     for (int k = 0; k < PIPE_NCTX; ++k) {
         weno5_ctx *c = p->ctx[k];

@@ -1308,6 +1308,31 @@ void launch_halo_pack(double *const planes[], int n, const Geom &g, double *up, 
     halo_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a, unpack);
 }
 
+// ------------------------------------------------------------------ pipelined host step: rows of the input image -> slab planes
+// The host arrays of weno5_pipe_step are uploaded once, row range by row range, into an image of the whole grid
+// (public layout, unpadded); a slab takes the rows of its window from there.
+struct GatherArgs { const double *src[11]; double *dst[11]; int n, Nx, spitch, dpitch, rows; };
+
+__global__ void gather_rows_kernel(const GatherArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (i >= a.Nx) return;
+    const size_t so = (size_t)a.spitch * r + i, dof = (size_t)a.dpitch * r + i;
+    for (int k = 0; k < a.n; ++k) a.dst[k][dof] = a.src[k][so];
+}
+
+void launch_gather_rows(const double *const src[], double *const dst[], int n, int Nx, int spitch, int dpitch, int rows,
+                        cudaStream_t s)
+{
+    if (rows <= 0) return;
+    GatherArgs a;
+    a.n = n;
+    for (int k = 0; k < n; ++k) { a.src[k] = src[k]; a.dst[k] = dst[k]; }
+    a.Nx = Nx; a.spitch = spitch; a.dpitch = dpitch; a.rows = rows;
+    gather_rows_kernel<<<dim3((Nx + 255) / 256, rows), 256, 0, s>>>(a);
+}
+
 // ------------------------------------------------------------------ halo push over peer memory (NVLink)
 // One process per GPU; at weno5_comm_init every rank maps its neighbours' plane pools (CUDA IPC).  A stage's
 // exchange is then ONE kernel that stores this slab's 4 outermost interior rows of every plane straight into

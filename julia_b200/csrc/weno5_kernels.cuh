@@ -97,6 +97,9 @@ void launch_bc_fill(double *const planes[], int nplanes, const Geom &g, const in
                     const double *dtp, cudaStream_t s);
 void launch_halo_pack(double *const planes[], int n, const Geom &g, double *up, double *down, int has_up, int has_down,
                       int unpack, cudaStream_t s);
+// pipelined host step: `rows` rows of n unpadded source planes (pitch spitch) -> padded slab planes (pitch dpitch)
+void launch_gather_rows(const double *const src[], double *const dst[], int n, int Nx, int spitch, int dpitch, int rows,
+                        cudaStream_t s);
 // halo push over peer memory: edge rows of n planes -> the neighbours' ghost rows, then seq -> their flag words
 struct PushArgs {
     const double *src[NCELL];    // this slab's planes

@@ -191,7 +191,7 @@ ordinary `Array`s are pageable -- correct results, serialised copies (`pipe_over
 """
 mutable struct Pipe
     h::Ptr{Cvoid}
-    function Pipe(p::Weno5Params; device::Integer=0, rows_per_slab::Integer=512)
+    function Pipe(p::Weno5Params; device::Integer=0, rows_per_slab::Integer=128)
         h = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall((:weno5_pipe_create, libweno5), Cint, (Ref{Weno5Params}, Cint, Cint, Ref{Ptr{Cvoid}}), p, device, rows_per_slab, h))
         s = new(h[])

@@ -198,7 +198,7 @@ class Pipe:
     """Pipelined host -> host classical_RK4_step: y-slabs with overlap rows stream through the GPU so
     that upload, compute and download overlap (weno5_pipe_* in include/weno5mhd.h)."""
 
-    def __init__(self, g, device=0, rows_per_slab=512, es_roundtrip=True):
+    def __init__(self, g, device=0, rows_per_slab=128, es_roundtrip=True):
         self.lib = L.load()
         self.g = g
         self.params = make_params(g, es_roundtrip)

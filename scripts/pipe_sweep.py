@@ -15,7 +15,9 @@ a = [pinned(x.shape) for x in (q, bx, by)]; b = [pinned(x.shape) for x in (q, bx
 for dst, src in zip(a, (q, bx, by)): dst[...] = src
 with Solver(g) as s:
     s.upload(q, bx, by); dt0 = s.timestep()[0]
-for rows in (256, 512, 1024, 2048):
+rows_list = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else (128, 256, 512, 1024)
+ref = None
+for rows in rows_list:
     with Pipe(g, rows_per_slab=rows, es_roundtrip=False) as p:
         i, o = a, b
         *_, dtn = p.step(*i, dt0, out=tuple(o)); i, o = o, i
@@ -23,5 +25,10 @@ for rows in (256, 512, 1024, 2048):
         for _ in range(5):
             *_, dtn = p.step(*i, dtn, out=tuple(o)); i, o = o, i
         torch.cuda.synchronize(); t = (time.time() - t0) / 5
-    print(f"rows {rows}: {t*1e3:.2f} ms/step  {n*n/t:.3e} cell-upd/s")
+    # every slab size must give the same bits (the windows carry the whole domain of dependence of a step)
+    res = [x.copy() for x in i]
+    if ref is None:
+        ref = res
+    same = all(np.array_equal(x, y) for x, y in zip(res, ref))
+    print(f"rows {rows}: {t*1e3:.2f} ms/step  {n*n/t:.3e} cell-upd/s  direct={'WENO5_PIPE_DIRECT' in os.environ}  same_bits_as_first={same}")
     for dst, src in zip(a, (q, bx, by)): dst[...] = src
