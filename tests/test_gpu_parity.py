@@ -434,10 +434,13 @@ def test_tma_and_ldgsts_staging_agree_to_roundoff(tmp_path):
     assert np.isfinite(res["5"]["q"]).all()
 
 
+@pytest.mark.parametrize("rows,direct", [(64, False), (40, False), (100, False), (64, True)])
 @pytest.mark.parametrize("case", ["periodic", "outflow_ragged"])
-def test_pipelined_host_step_is_bit_identical(case):
+def test_pipelined_host_step_is_bit_identical(case, rows, direct, monkeypatch):
     """weno5_pipe_step streams y-slabs (+16 overlap rows = domain of dependence of one RK4 step)
-    through the GPU; every row of the result, the ghost rows and the returned next time step must
+    through the GPU -- inputs through an image of the grid on the device that the slabs gather their windows from,
+    or (direct) every slab uploading its own window -- for slab sizes that do and do not divide the grid;
+    every row of the result, the ghost rows and the returned next time step must
     equal the monolithic upload -> step -> download path bit for bit."""
     from julia_b200.solver import Pipe
     if case == "periodic":
@@ -450,7 +453,11 @@ def test_pipelined_host_step_is_bit_identical(case):
         s.rk4_step(dt)
         dt_next = s.timestep()[0]
         q_ref, bx_ref, by_ref = s.download()
-    with Pipe(g, rows_per_slab=64) as p:
+    if direct:
+        monkeypatch.setenv("WENO5_PIPE_DIRECT", "1")
+    else:
+        monkeypatch.delenv("WENO5_PIPE_DIRECT", raising=False)
+    with Pipe(g, rows_per_slab=rows) as p:
         q4, bx4, by4, dtn = p.step(q, bx, by, dt)
         assert np.array_equal(q4, q_ref) and np.array_equal(bx4, bx_ref) and np.array_equal(by4, by_ref)
         assert dtn == dt_next
