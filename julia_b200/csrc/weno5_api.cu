@@ -1528,10 +1528,15 @@ extern "C" int weno5_pipe_step(weno5_pipe *p, const double *q0, const double *bx
     const int nranges = (Ny + p->R - 1) / p->R;
     const int T0 = periodic ? ny + WENO5_NBND - (PIPE_H + 8) : Ny, T1 = periodic ? ny + WENO5_NBND : Ny;   // wrap-around rows
     int next_range = 0;
-    auto upload_range = [&](int a, int b, cudaEvent_t ev) -> int {       // public rows [a, b) of every plane, then the event
-        for (int n = 0; n < PIPE_NIN; ++n)
-            CU(cudaMemcpyAsync(p->inbuf + (size_t)n * hp + (size_t)Nx * a, hsrc[n] + (size_t)Nx * a, (size_t)Nx * (b - a) * sizeof(double),
-                               cudaMemcpyHostToDevice, p->up));
+    // public rows [a, b) of every plane, then the event.  The planes of q are hp doubles apart on both sides, so the
+    // same row range of several planes is ONE 2-D copy ("rows" = planes): host planes 0..6 (rho .. Bz) -> image planes
+    // 0..6, host plane 8 (E) -> image plane 7, bxb, byb: four copies per range instead of ten
+    auto upload_range = [&](int a, int b, cudaEvent_t ev) -> int {
+        const size_t w = (size_t)Nx * (b - a) * sizeof(double), off = (size_t)Nx * a, pitch = hp * sizeof(double);
+        const bool planes2d = pitch < ((size_t)1 << 31);                  // cudaMemcpy2D pitch limit (16384^2 planes exceed it)
+        if (planes2d) CU(cudaMemcpy2DAsync(p->inbuf + off, pitch, q0 + off, pitch, w, 7, cudaMemcpyHostToDevice, p->up));
+        for (int n = planes2d ? 7 : 0; n < PIPE_NIN; ++n)
+            CU(cudaMemcpyAsync(p->inbuf + (size_t)n * hp + off, hsrc[n] + off, w, cudaMemcpyHostToDevice, p->up));
         CU(cudaEventRecord(ev, p->up));
         return 0;
     };
@@ -1632,8 +1637,13 @@ extern "C" int weno5_pipe_step(weno5_pipe *p, const double *q0, const double *bx
             CU(cudaEventRecord(p->done[k], c->stream));
             CU(cudaStreamWaitEvent(p->down, p->done[k], 0));
             const size_t nb = (size_t)Nx * (d1 - d0) * sizeof(double), off = (size_t)Nx * hj;
-            for (int f = 0; f < 9; ++f)
-                CU(cudaMemcpyAsync(q4 + (size_t)f * hp + off, p->outbuf + (size_t)f * hp + off, nb, cudaMemcpyDeviceToHost, p->down));
+            // the nine planes of q4 are hp doubles apart on both sides: one 2-D copy whose "rows" are the planes
+            if (hp * sizeof(double) < ((size_t)1 << 31)) {
+                CU(cudaMemcpy2DAsync(q4 + off, hp * sizeof(double), p->outbuf + off, hp * sizeof(double), nb, 9, cudaMemcpyDeviceToHost, p->down));
+            } else {
+                for (int f = 0; f < 9; ++f)
+                    CU(cudaMemcpyAsync(q4 + (size_t)f * hp + off, p->outbuf + (size_t)f * hp + off, nb, cudaMemcpyDeviceToHost, p->down));
+            }
             CU(cudaMemcpyAsync(bxb4 + off, p->outbuf + 9 * hp + off, nb, cudaMemcpyDeviceToHost, p->down));
             CU(cudaMemcpyAsync(byb4 + off, p->outbuf + 10 * hp + off, nb, cudaMemcpyDeviceToHost, p->down));
         }
