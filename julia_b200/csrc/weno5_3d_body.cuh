@@ -532,7 +532,8 @@ template <int LPL> struct XWarpGeo {
     static constexpr int NFB = 5;
     static constexpr int FBL = LPL + 1;                // fhat strip of a line: entry l+1 = face of lane l
     static constexpr int FBW = LPW * FBL;
-    static constexpr int PER_WARP = CQ_COUNT * RING + 2 * NFB * FBW;
+    static constexpr int OFF_STAGE = CQ_COUNT * RING + 2 * NFB * FBW;   // raw state of the next step's cells: 2 x 8 x 32
+    static constexpr int PER_WARP = OFF_STAGE + 2 * 8 * 32;
     static constexpr size_t SMEM = (size_t)WARPS * PER_WARP * sizeof(double);
     static_assert(LPL >= 8 && RL >= LPL + 5, "the prologue needs five lanes and the ring LPL + 5 slots");
     // grid: (groups of 8 * LPW lines along y, lines along z, segments along x)
@@ -593,14 +594,11 @@ template <int LPL> struct XWarpPos {
     }
 };
 
+// cell quantities of cell c from its raw state q (sweep frame = physical frame for x) -> the line's ring
 template <int LPL>
-W5_HD void xwarp_cell(const SweepArgs &a, const XWarpPos<LPL> &P, int c, double *cb)
+W5_HD void xwarp_cell_from(const SweepArgs &a, const XWarpPos<LPL> &P, int c, const double q[8], double *cb)
 {
     constexpr int CBS = XWarpGeo<LPL>::RING;
-    const size_t g = P.g0 + (size_t)P.line_cell(c, a.d.bc[0]);
-    double q[8];
-#pragma unroll
-    for (int m = 0; m < 8; ++m) q[m] = a.q[m][g];
     CellOut o;
     cell_quantities(q, a.gam, o);
     const int i = P.slot(c);
@@ -622,19 +620,42 @@ W5_HD void xwarp_cell(const SweepArgs &a, const XWarpPos<LPL> &P, int c, double 
     cb[CQ_LS * CBS + i] = o.ls;
 }
 
-// phase 0 of march step `chunk`: the new cells (and, before the first step, the five cells in front of the first face)
+template <int LPL>
+W5_HD void xwarp_cell(const SweepArgs &a, const XWarpPos<LPL> &P, int c, double *cb)
+{
+    const size_t g = P.g0 + (size_t)P.line_cell(c, a.d.bc[0]);
+    double q[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) q[m] = a.q[m][g];
+    xwarp_cell_from<LPL>(a, P, c, q, cb);
+}
+
+// phase 0 of march step `chunk`: the new cells (and, before the first step, the five cells in front of the first face).
+// From the second step on a lane finds the raw state of its cell in its private staging slots, where cp.async put it
+// while the previous step's faces were computed, and sends for the cell of the step after.
 template <int LPL>
 W5_HD void xwarp_cells(const SweepArgs &a, int nseg, int bx, int by, int bz, int warp, int lane, int chunk, double *wsm)
 {
+    using X = XWarpGeo<LPL>;
     const XWarpPos<LPL> P(a.d, nseg, bx, by, bz, warp, lane);
     if (!P.ok || chunk >= P.nchunks) return;
-    if (chunk == 0 && P.ll < 5) xwarp_cell(a, P, P.fA - 2 + P.ll, wsm);
+    double *stage = wsm + X::OFF_STAGE + lane;          // entry m of buffer b: stage[(b * 8 + m) * 32]
     const int c = P.fA + 3 + LPL * chunk + P.ll;
-    if (c <= P.fLast + 3) xwarp_cell(a, P, c, wsm);
-    if (c + LPL <= P.fLast + 3) {                       // next step's cell: start its trip from DRAM now
+    if (chunk == 0) {
+        if (P.ll < 5) xwarp_cell(a, P, P.fA - 2 + P.ll, wsm);
+        if (c <= P.fLast + 3) xwarp_cell(a, P, c, wsm);
+    } else if (c <= P.fLast + 3) {
+        cp_async_wait_all();
+        double q[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) q[m] = stage[((chunk & 1) * 8 + m) * 32];
+        xwarp_cell_from<LPL>(a, P, c, q, wsm);
+    }
+    if (c + LPL <= P.fLast + 3 && chunk + 1 < P.nchunks) {
         const size_t gp = P.g0 + (size_t)P.line_cell(c + LPL, a.d.bc[0]);
 #pragma unroll
-        for (int m = 0; m < 8; ++m) prefetch_l2(a.q[m] + gp);
+        for (int m = 0; m < 8; ++m) cp_async_f64(&stage[(((chunk + 1) & 1) * 8 + m) * 32], a.q[m] + gp);
+        cp_async_commit();
     }
 }
 
