@@ -120,6 +120,27 @@ def test_blast_3d_outflow_and_tmax(built):
         assert l1 <= 1e-9, (c, l1)
 
 
+@pytest.mark.parametrize("env", [{"WENO5_3D_SWEEP": "tile"}, {"WENO5_3D_SWEEP": "xtile"}, {"WENO5_3D_SWEEP": "xmarch"},
+                                 {"WENO5_3D_CT": "fused"}, {"WENO5_3D_LPL": "32"}, {"WENO5_3D_NSEG": "3"}])
+def test_kernel_variants_agree(built, monkeypatch, env):
+    """the CTA-tile sweeps (the first version), the thread-per-line x sweep, the fused EMF + face-update kernel and other
+    lane / segment counts are the same arithmetic in a different division of labour: two steps must agree with the
+    default kernels to round-off"""
+    g, q, bx, by, bz = p3.smooth_3d(70, 37, 19, seed=11)
+    res = []
+    for e in ({}, env):
+        for k in ("WENO5_3D_SWEEP", "WENO5_3D_CT", "WENO5_3D_LPL", "WENO5_3D_NSEG"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in e.items():
+            monkeypatch.setenv(k, v)
+        with Solver3D(g) as s:
+            s.upload(q, bx, by, bz)
+            s.advance(2)
+            res.append(s.download())
+    for a, b in zip(*res):
+        assert np.abs(a - b).max() <= 1e-13 * max(np.abs(b).max(), 1.0)
+
+
 def test_argument_validation_3d(built):
     import ctypes as C
     from julia_b200 import lib as L
