@@ -503,10 +503,14 @@ extern "C" int weno5_download_3d(weno5_ctx3d *c, double *q, double *bxb, double 
 {
     ENTER3(c);
     if (!c->have_state) return fail3(WENO5_ERR_STATE, "no state uploaded");
-    if (q) if (int r = copy_vols(c, c->b.Q[0], nullptr, q, 9)) return r;
+    if (q) {
+        if (int r = copy_vols(c, c->b.Q[0], nullptr, q, 9)) return r;
+    }
     double *h[3] = {bxb, byb, bzb};
-    for (int m = 0; m < 3; ++m)
-        if (h[m]) if (int r = copy_vols(c, &c->b.B[0][m], nullptr, h[m], 1)) return r;
+    for (int m = 0; m < 3; ++m) {
+        if (!h[m]) continue;
+        if (int r = copy_vols(c, &c->b.B[0][m], nullptr, h[m], 1)) return r;
+    }
     CU3(cudaStreamSynchronize(c->stream));
     return WENO5_OK;
 }
@@ -606,7 +610,9 @@ extern "C" int weno5_classical_rk4_step_3d(const weno5_params3d *P, const double
                                            const double *bzb0, double dt, double *q4, double *bxb4, double *byb4, double *bzb4)
 {
     weno5_ctx3d *c = nullptr;
-    if (int r = weno5_create_3d(P, 0, &c)) return r;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }     // the caller's current device, as the 2-D one-shot call
+    if (int r = weno5_create_3d(P, dev, &c)) return r;
     int r = weno5_upload_3d(c, q0, bxb0, byb0, bzb0);
     if (!r) r = weno5_rk4_step_3d(c, dt);
     if (!r) r = weno5_download_3d(c, q4, bxb4, byb4, bzb4);
