@@ -141,3 +141,10 @@ def test_pure_c_driver_links_against_the_library(built, tmp_path):
                            "-lweno5mhd", "-Wl,-rpath," + os.path.dirname(L.LIB_PATH)])
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 1 and "usage" in r.stderr
+    # and the 3-D extension's driver
+    exe3 = str(tmp_path / "c_driver3d")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "abi", "c_driver3d.c"), "-o", exe3, "-L", os.path.dirname(L.LIB_PATH),
+                           "-lweno5mhd", "-Wl,-rpath," + os.path.dirname(L.LIB_PATH)])
+    r = subprocess.run([exe3], capture_output=True, text=True)
+    assert r.returncode == 1 and "usage" in r.stderr

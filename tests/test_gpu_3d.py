@@ -141,6 +141,38 @@ def test_kernel_variants_agree(built, monkeypatch, env):
         assert np.abs(a - b).max() <= 1e-13 * max(np.abs(b).max(), 1.0)
 
 
+def test_pure_c_driver_3d(built, tmp_path):
+    """tests/abi/c_driver3d.c -- create_3d, upload_3d, advance_3d, divb_3d, download_3d from plain C11, linked against
+    the library alone -- on a smooth 3-D state with outflow sides, against the 3-D oracle's driver loop"""
+    import os
+    import subprocess
+    from julia_b200 import lib as L
+    from util import ROOT
+    g, q, bx, by, bz = p3.smooth_3d(20, 14, 9, seed=3, bc=pr.OUTFLOW)
+    q, bx, by, bz = (np.asfortranarray(a.copy()) for a in (q, bx, by, bz))
+    O.boundaries_3d(g, q, bx, by, bz)
+    exe, fin, fout = str(tmp_path / "c_driver3d"), str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "abi", "c_driver3d.c"), "-o", exe, "-L", os.path.dirname(L.LIB_PATH),
+                           "-lweno5mhd", "-Wl,-rpath," + os.path.dirname(L.LIB_PATH)])
+    with open(fin, "wb") as f:
+        np.array([g.nx, g.ny, g.nz, 3, pr.OUTFLOW], dtype=np.int32).tofile(f)
+        np.array([g.xsize, g.ysize, g.zsize]).tofile(f)
+        for a in (q, bx, by, bz):
+            a.ravel(order="F").tofile(f)
+    subprocess.check_call([exe, fin, fout])
+    raw = np.fromfile(fout)
+    n = int(np.prod(g.shape))
+    t, done = raw[0], int(raw[1])
+    got_q = raw[2:2 + 9 * n].reshape(g.shape + (9,), order="F")
+    got_b = [raw[2 + (9 + m) * n:2 + (10 + m) * n].reshape(g.shape, order="F") for m in range(3)]
+    divb = raw[2 + 12 * n:2 + 13 * n].reshape(g.shape, order="F")
+    qo, bxo, byo, bzo, to = O.advance_3d(g, q, bx, by, bz, 3)
+    assert done == 3 and abs(t - to) <= 1e-12 * to
+    compare((got_q, *got_b), (qo, bxo, byo, bzo), 1e-11)
+    assert np.abs(divb - O.divb_3d(g, *got_b)).max() <= 1e-12
+
+
 def test_argument_validation_3d(built):
     import ctypes as C
     from julia_b200 import lib as L
