@@ -95,3 +95,21 @@ def test_center2face_and_helpers_agree_with_numpy():
     Bc = p3.face2center_3d(bx, by, bz)
     for m in range(3):
         assert _rel(Bc[m][I, I, I], q[I, I, I, 4 + m]) < 1e-15
+
+
+@pytest.mark.parametrize("bc", [(1, 1, 1), (0, 0, 0), (1, 0, 1)])
+def test_c_oracle_agrees_with_the_independent_numpy_restatement(bc):
+    """oracle/weno5_numpy3d.py sweeps every direction with the 2-D numpy restatement's own sweep function on a rotated
+    copy of the state and does the constrained transport with whole-array slices: no 3-D code in common with the C oracle"""
+    from oracle import weno5_numpy3d as N3
+    g, q, bx, by, bz = p3.smooth_3d(11, 9, 8, seed=5)
+    g.bc_x, g.bc_y, g.bc_z = bc
+    q, bx, by, bz = (np.asfortranarray(a.copy()) for a in (q, bx, by, bz))
+    O.boundaries_3d(g, q, bx, by, bz)
+    dt = 0.7 * O.timestep_3d(g, q)[0]
+    want = O.rk4_step_3d(g, q, bx, by, bz, dt)
+    got = N3.classical_RK4_step_3d(g, q, bx, by, bz, dt)
+    for c in range(9):
+        assert np.abs(got[0][I, I, I, c] - want[0][I, I, I, c]).max() <= 1e-13 * max(np.abs(want[0][..., c]).max(), 1.0), c
+    for a, b in zip(got[1:], want[1:]):
+        assert np.abs(a[I, I, I] - b[I, I, I]).max() <= 1e-13
