@@ -239,6 +239,26 @@ def blast_3d(n=64, bc=PERIODIC, gam=5.0 / 3.0):
     return (g,) + assemble_3d(g, one, z, z, z, P, None, (b, b, 0.0))
 
 
+def alfven_wave_3d(n=32, amp=0.1, gam=5.0 / 3.0):
+    """Circularly polarised Alfven wave (an exact nonlinear solution) along the diagonal of the periodic unit cube:
+    rho = 1, P = 0.1, B_par = 1 along e1 = (1,1,1)/sqrt 3, transverse field and velocity amp (sin phi e2 + cos phi e3),
+    phi = 2 pi (x + y + z); wavelength 1/sqrt 3, Alfven speed 1, period 1/sqrt 3.  The 3-D counterpart of alfven_wave
+    (BASELINE config 2); face fields from the vector potential amp/kappa (sin phi e2 + cos phi e3), kappa = 2 pi sqrt 3."""
+    g = Grid3D(nx=n, ny=n, nz=n, gam=gam)
+    e1 = np.array([1.0, 1.0, 1.0]) / np.sqrt(3.0)
+    e2 = np.array([1.0, -1.0, 0.0]) / np.sqrt(2.0)
+    e3 = np.cross(e1, e2)
+    kap = 2 * np.pi * np.sqrt(3.0)
+
+    def ph(x, y, z):
+        return 2 * np.pi * (x + y + z)
+    X, Y, Z = np.meshgrid(*g.centres(), indexing="ij")
+    s, c = np.sin(ph(X, Y, Z)), np.cos(ph(X, Y, Z))
+    v = [amp * (s * e2[m] + c * e3[m]) for m in range(3)]
+    A = [(lambda x, y, z, m=m: amp / kap * (np.sin(ph(x, y, z)) * e2[m] + np.cos(ph(x, y, z)) * e3[m])) for m in range(3)]
+    return (g,) + assemble_3d(g, np.ones_like(X), v[0], v[1], v[2], np.full_like(X, 0.1), A, tuple(e1))
+
+
 def smooth_3d(nx=24, ny=20, nz=16, seed=7, bc=PERIODIC, gam=5.0 / 3.0):
     """A smooth state with every component of v and B depending on all three coordinates (low Fourier modes),
     rho in [0.6,1.6], P in [0.4,1.4]; the kernel-level input of the 3-D parity tests."""
